@@ -1,0 +1,169 @@
+// Short-Weierstrass (a = 0) Jacobian arithmetic, generic over F in {Fq, Fq2},
+// and the two endomorphism-based subgroup predicates.
+//
+// What this replaces: ark-ec 0.2.0 is_in_correct_subgroup_assuming_on_curve,
+// reached from /root/reference/src/lib.rs:52 (G1) and :78 (G2), which multiplies
+// by r (254 doublings + 133 mixed additions).  Here:
+//   G1: phi(P) == -[z^2]P   with phi(x,y) = (beta x, y)        (2 x 64-bit ladders)
+//   G2: psi(P) == [z]P      with psi = twist o Frobenius o untwist (1 x 64-bit ladder)
+// Both return the same boolean as the r-multiplication for every on-curve point:
+// phi^2+phi+1 = 0 gives (z^4-z^2+1)P = rP = O; psi^2-t psi+p = 0 gives
+// (p-z)P = h1 r P = O and gcd(h1, h2) = 1 (checked in tests/test_oracle_pins.py).
+//
+// Exceptional cases: the addition formulas used here give Z3 = 0 whenever the two
+// inputs share an x coordinate (H = 0), and Z = 0 is sticky through every later
+// doubling/addition (Z3 is a multiple of Z1).  A point of prime order r never
+// meets such a case on these ladders (all partial scalars are < 2^128 and
+// != +-1 mod r), so "some Z became 0" implies "not in the subgroup", and the
+// final comparison demands Z != 0.  Hence no branches on exceptional cases.
+#pragma once
+#include "fq2.cuh"
+
+namespace ptau {
+
+template <class F>
+struct Jac {
+  F X, Y, Z;
+};
+
+// dbl-2009-l  (2M + 5S)
+template <class F>
+PTAU_HD void jac_dbl(Jac<F>& p) {
+  F A = fsqr(p.X);
+  F B = fsqr(p.Y);
+  F C = fsqr(B);
+  F D = fsqr(fadd(p.X, B));
+  D = fsub(fsub(D, A), C);
+  D = fdbl(D);
+  F E = fadd(fdbl(A), A);
+  F Fv = fsqr(E);
+  p.Z = fdbl(fmul(p.Z, p.Y));
+  p.X = fsub(Fv, fdbl(D));
+  C = fdbl(fdbl(fdbl(C)));
+  p.Y = fsub(fmul(fsub(D, p.X), E), C);
+}
+
+// madd-2007-bl  (7M + 4S): p += (x2, y2)
+template <class F>
+PTAU_HD void jac_madd(Jac<F>& p, const F& x2, const F& y2) {
+  F Z1Z1 = fsqr(p.Z);
+  F U2 = fmul(x2, Z1Z1);
+  F S2 = fmul(fmul(y2, p.Z), Z1Z1);
+  F H = fsub(U2, p.X);
+  F HH = fsqr(H);
+  F I = fdbl(fdbl(HH));
+  F J = fmul(H, I);
+  F rr = fdbl(fsub(S2, p.Y));
+  F V = fmul(p.X, I);
+  F X3 = fsub(fsub(fsqr(rr), J), fdbl(V));
+  F Y3 = fsub(fmul(rr, fsub(V, X3)), fdbl(fmul(p.Y, J)));
+  // Z3 = (Z1+H)^2 - Z1Z1 - HH = 2 Z1 H
+  p.Z = fdbl(fmul(p.Z, H));
+  p.X = X3;
+  p.Y = Y3;
+}
+
+// add-2007-bl  (11M + 5S): p += q
+template <class F>
+PTAU_HD void jac_add(Jac<F>& p, const Jac<F>& q) {
+  F Z1Z1 = fsqr(p.Z);
+  F Z2Z2 = fsqr(q.Z);
+  F U1 = fmul(p.X, Z2Z2);
+  F U2 = fmul(q.X, Z1Z1);
+  F S1 = fmul(fmul(p.Y, q.Z), Z2Z2);
+  F S2 = fmul(fmul(q.Y, p.Z), Z1Z1);
+  F H = fsub(U2, U1);
+  F I = fsqr(fdbl(H));
+  F J = fmul(H, I);
+  F rr = fdbl(fsub(S2, S1));
+  F V = fmul(U1, I);
+  F X3 = fsub(fsub(fsqr(rr), J), fdbl(V));
+  F Y3 = fsub(fmul(rr, fsub(V, X3)), fdbl(fmul(S1, J)));
+  // Z3 = ((Z1+Z2)^2 - Z1Z1 - Z2Z2) H = 2 Z1 Z2 H
+  p.Z = fmul(fdbl(fmul(p.Z, q.Z)), H);
+  p.X = X3;
+  p.Y = Y3;
+}
+
+// |z| = 0xd201000000010000 = 2^63 + 2^62 + 2^60 + 2^57 + 2^48 + 2^16
+#define PTAU_Z_ABS 0xd201000000010000ull
+
+// acc = [|z|] (x, y), affine base, mixed additions
+template <class F>
+PTAU_HD Jac<F> mul_zabs_affine(const F& x, const F& y, const F& one) {
+  Jac<F> acc;
+  acc.X = x;
+  acc.Y = y;
+  acc.Z = one;
+#pragma unroll 1
+  for (int i = 62; i >= 0; --i) {
+    jac_dbl(acc);
+    if ((PTAU_Z_ABS >> i) & 1ull) jac_madd(acc, x, y);
+  }
+  return acc;
+}
+
+// acc = [|z|] q, Jacobian base, full additions
+template <class F>
+PTAU_HD Jac<F> mul_zabs_jac(const Jac<F>& q) {
+  Jac<F> acc = q;
+#pragma unroll 1
+  for (int i = 62; i >= 0; --i) {
+    jac_dbl(acc);
+    if ((PTAU_Z_ABS >> i) & 1ull) jac_add(acc, q);
+  }
+  return acc;
+}
+
+// Jacobian p equals the finite affine point (x, y)?
+template <class F>
+PTAU_HD bool jac_eq_affine(const Jac<F>& p, const F& x, const F& y) {
+  F ZZ = fsqr(p.Z);
+  F ZZZ = fmul(ZZ, p.Z);
+  bool ok = !fis_zero(p.Z);
+  ok = ok && feq(p.X, fmul(x, ZZ));
+  ok = ok && feq(p.Y, fmul(y, ZZZ));
+  return ok;
+}
+
+// ---- constants (Montgomery form) --------------------------------------------
+#include "consts.inc"
+
+// y^2 == x^3 + 4
+PTAU_HD bool g1_on_curve(const Fq& x, const Fq& y) {
+  Fq rhs = fq_add(fq_mul(fq_sqr(x), x), k_b1_mont());
+  return fq_eq(fq_sqr(y), rhs);
+}
+
+// y^2 == x^3 + 4(1+u)
+PTAU_HD bool g2_on_curve(const Fq2& x, const Fq2& y) {
+  Fq2 b;
+  b.c0 = k_b1_mont();
+  b.c1 = b.c0;
+  Fq2 rhs = fq2_add(fq2_mul(fq2_sqr(x), x), b);
+  return fq2_eq(fq2_sqr(y), rhs);
+}
+
+// phi(P) == -[z^2]P   <=>   [|z|]([|z|]P) == (beta x, -y)
+PTAU_HD bool g1_in_subgroup(const Fq& x, const Fq& y) {
+  Jac<Fq> q = mul_zabs_affine(x, y, fq_one());
+  Jac<Fq> q2 = mul_zabs_jac(q);
+  return jac_eq_affine(q2, fq_mul(x, k_beta_mont()), fq_neg(y));
+}
+
+// psi(P) == [z]P   <=>   [|z|]P == -psi(P) = (psi_x, -psi_y)
+PTAU_HD bool g2_in_subgroup(const Fq2& x, const Fq2& y) {
+  Jac<Fq2> q = mul_zabs_affine(x, y, fq2_one());
+  // psi_x = conj(x) * (0, cx1) = (x1*cx1, x0*cx1)
+  Fq cx1 = k_psi_cx1_mont();
+  Fq2 px;
+  px.c0 = fq_mul(x.c1, cx1);
+  px.c1 = fq_mul(x.c0, cx1);
+  Fq2 cy;
+  cy.c0 = k_psi_cy0_mont();
+  cy.c1 = k_psi_cy1_mont();
+  Fq2 py = fq2_mul(fq2_conj(y), cy);
+  return jac_eq_affine(q, px, fq2_neg(py));
+}
+
+}  // namespace ptau

@@ -1,0 +1,132 @@
+// Fq2 = Fq[u]/(u^2+1) on top of fq.cuh, plus the field-generic spellings
+// (fadd/fsub/fmul/...) that curve.cuh is written against.
+//
+// On the device fq_mul / fq_sqr / fq2_mul / fq2_sqr are real (non-inlined)
+// functions: one Montgomery multiplication is ~330 SASS instructions, and the
+// double-and-add loops of the subgroup checks must stay inside the instruction
+// cache.  Arguments and results travel in registers (checked with -Xptxas -v:
+// no stack frame).
+#pragma once
+#include "fq.cuh"
+
+namespace ptau {
+
+#ifdef __CUDA_ARCH__
+__device__ __noinline__ Fq fq_mul(Fq a, Fq b) { return fq_mul_inl(a, b); }
+__device__ __noinline__ Fq fq_sqr(Fq a) { return fq_mul_inl(a, a); }
+#else
+inline Fq fq_mul(const Fq& a, const Fq& b) { return fq_mul_inl(a, b); }
+inline Fq fq_sqr(const Fq& a) { return fq_mul_inl(a, a); }
+#endif
+
+struct Fq2 {
+  Fq c0, c1;
+};
+
+PTAU_HD Fq2 fq2_zero() {
+  Fq2 r;
+  r.c0 = fq_zero();
+  r.c1 = fq_zero();
+  return r;
+}
+PTAU_HD Fq2 fq2_one() {
+  Fq2 r;
+  r.c0 = fq_one();
+  r.c1 = fq_zero();
+  return r;
+}
+PTAU_HD Fq2 fq2_add(const Fq2& a, const Fq2& b) {
+  Fq2 r;
+  r.c0 = fq_add(a.c0, b.c0);
+  r.c1 = fq_add(a.c1, b.c1);
+  return r;
+}
+PTAU_HD Fq2 fq2_sub(const Fq2& a, const Fq2& b) {
+  Fq2 r;
+  r.c0 = fq_sub(a.c0, b.c0);
+  r.c1 = fq_sub(a.c1, b.c1);
+  return r;
+}
+PTAU_HD Fq2 fq2_neg(const Fq2& a) {
+  Fq2 r;
+  r.c0 = fq_neg(a.c0);
+  r.c1 = fq_neg(a.c1);
+  return r;
+}
+PTAU_HD Fq2 fq2_dbl(const Fq2& a) {
+  Fq2 r;
+  r.c0 = fq_dbl(a.c0);
+  r.c1 = fq_dbl(a.c1);
+  return r;
+}
+PTAU_HD Fq2 fq2_conj(const Fq2& a) {
+  Fq2 r;
+  r.c0 = a.c0;
+  r.c1 = fq_neg(a.c1);
+  return r;
+}
+PTAU_HD bool fq2_is_zero(const Fq2& a) { return fq_is_zero(a.c0) && fq_is_zero(a.c1); }
+PTAU_HD bool fq2_eq(const Fq2& a, const Fq2& b) { return fq_eq(a.c0, b.c0) && fq_eq(a.c1, b.c1); }
+
+// Karatsuba: 3 Fq multiplications
+PTAU_HD Fq2 fq2_mul_inl(const Fq2& a, const Fq2& b) {
+  Fq v0 = fq_mul(a.c0, b.c0);
+  Fq v1 = fq_mul(a.c1, b.c1);
+  Fq s = fq_mul(fq_add(a.c0, a.c1), fq_add(b.c0, b.c1));
+  Fq2 r;
+  r.c0 = fq_sub(v0, v1);
+  r.c1 = fq_sub(fq_sub(s, v0), v1);
+  return r;
+}
+// complex squaring: 2 Fq multiplications
+PTAU_HD Fq2 fq2_sqr_inl(const Fq2& a) {
+  Fq t = fq_mul(a.c0, a.c1);
+  Fq2 r;
+  r.c0 = fq_mul(fq_add(a.c0, a.c1), fq_sub(a.c0, a.c1));
+  r.c1 = fq_dbl(t);
+  return r;
+}
+
+#ifdef __CUDA_ARCH__
+__device__ __noinline__ Fq2 fq2_mul(Fq2 a, Fq2 b) { return fq2_mul_inl(a, b); }
+__device__ __noinline__ Fq2 fq2_sqr(Fq2 a) { return fq2_sqr_inl(a); }
+#else
+inline Fq2 fq2_mul(const Fq2& a, const Fq2& b) { return fq2_mul_inl(a, b); }
+inline Fq2 fq2_sqr(const Fq2& a) { return fq2_sqr_inl(a); }
+#endif
+
+PTAU_HD Fq2 fq2_mul_fq(const Fq2& a, const Fq& k) {
+  Fq2 r;
+  r.c0 = fq_mul(a.c0, k);
+  r.c1 = fq_mul(a.c1, k);
+  return r;
+}
+
+// ---- field-generic spellings ------------------------------------------------
+PTAU_HD Fq fadd(const Fq& a, const Fq& b) { return fq_add(a, b); }
+PTAU_HD Fq fsub(const Fq& a, const Fq& b) { return fq_sub(a, b); }
+PTAU_HD Fq fneg(const Fq& a) { return fq_neg(a); }
+PTAU_HD Fq fdbl(const Fq& a) { return fq_dbl(a); }
+PTAU_HD Fq fmul(const Fq& a, const Fq& b) { return fq_mul(a, b); }
+PTAU_HD Fq fsqr(const Fq& a) { return fq_sqr(a); }
+PTAU_HD bool fis_zero(const Fq& a) { return fq_is_zero(a); }
+PTAU_HD bool feq(const Fq& a, const Fq& b) { return fq_eq(a, b); }
+
+PTAU_HD Fq2 fadd(const Fq2& a, const Fq2& b) { return fq2_add(a, b); }
+PTAU_HD Fq2 fsub(const Fq2& a, const Fq2& b) { return fq2_sub(a, b); }
+PTAU_HD Fq2 fneg(const Fq2& a) { return fq2_neg(a); }
+PTAU_HD Fq2 fdbl(const Fq2& a) { return fq2_dbl(a); }
+PTAU_HD Fq2 fmul(const Fq2& a, const Fq2& b) { return fq2_mul(a, b); }
+PTAU_HD Fq2 fsqr(const Fq2& a) { return fq2_sqr(a); }
+PTAU_HD bool fis_zero(const Fq2& a) { return fq2_is_zero(a); }
+PTAU_HD bool feq(const Fq2& a, const Fq2& b) { return fq2_eq(a, b); }
+
+// to / from Montgomery form
+PTAU_HD Fq fq_to_mont(const Fq& plain) { return fq_mul(plain, fq_r2()); }
+PTAU_HD Fq fq_from_mont(const Fq& m) {
+  Fq one = fq_zero();
+  one.l[0] = 1;
+  return fq_mul(m, one);
+}
+
+}  // namespace ptau

@@ -1,0 +1,59 @@
+// Host build of the *product's* per-point code (csrc/point.cuh compiled as plain
+// C++ with the carry-flag emulation in fq.cuh).  TEST VEHICLE ONLY: lets the
+// CPU-only test-suite check the exact limb-level algorithm the CUDA kernels run
+// against the oracle.  libptau_b200.so never links or calls this.
+#include <cstring>
+#include "../../kzg_setup_powersoftau_b200/csrc/point.cuh"
+
+using namespace ptau;
+
+template <int G, int INFMT>
+static uint32_t one(const uint8_t* in, int out_fmt, uint8_t* out, unsigned checks) {
+  uint32_t win[50], wout[50];
+  std::memcpy(win, in, record_bytes(G, INFMT));
+  std::memset(wout, 0, sizeof(wout));
+  uint32_t st = (G == PTAU_G1) ? g1_process<INFMT>(win, out_fmt, wout, checks)
+                               : g2_process<INFMT>(win, out_fmt, wout, checks);
+  std::memcpy(out, wout, record_bytes(G, out_fmt));
+  return st;
+}
+
+extern "C" int hostemul_convert(int group, int in_fmt, const uint8_t* in, int out_fmt, uint8_t* out,
+                                size_t n, unsigned checks, uint32_t* status) {
+  size_t ri = record_bytes(group, in_fmt), ro = record_bytes(group, out_fmt);
+  for (size_t i = 0; i < n; i++) {
+    uint32_t st;
+    const uint8_t* p = in + i * ri;
+    uint8_t* q = out + i * ro;
+    if (group == PTAU_G1) {
+      if (in_fmt == PTAU_FMT_ZCASH_UNCOMPRESSED) st = one<PTAU_G1, PTAU_FMT_ZCASH_UNCOMPRESSED>(p, out_fmt, q, checks);
+      else if (in_fmt == PTAU_FMT_ZCASH_COMPRESSED) st = one<PTAU_G1, PTAU_FMT_ZCASH_COMPRESSED>(p, out_fmt, q, checks);
+      else if (in_fmt == PTAU_FMT_ARK_UNCOMPRESSED) st = one<PTAU_G1, PTAU_FMT_ARK_UNCOMPRESSED>(p, out_fmt, q, checks);
+      else return -2;
+    } else {
+      if (in_fmt == PTAU_FMT_ZCASH_UNCOMPRESSED) st = one<PTAU_G2, PTAU_FMT_ZCASH_UNCOMPRESSED>(p, out_fmt, q, checks);
+      else if (in_fmt == PTAU_FMT_ZCASH_COMPRESSED) st = one<PTAU_G2, PTAU_FMT_ZCASH_COMPRESSED>(p, out_fmt, q, checks);
+      else if (in_fmt == PTAU_FMT_ARK_UNCOMPRESSED) st = one<PTAU_G2, PTAU_FMT_ARK_UNCOMPRESSED>(p, out_fmt, q, checks);
+      else return -2;
+    }
+    status[i] = st;
+  }
+  return 0;
+}
+
+// raw field ops for limb-level tests: a,b,out are 12 x u32 Montgomery limbs
+extern "C" void hostemul_fq_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
+  Fq x, y, r;
+  std::memcpy(x.l, a, 48);
+  std::memcpy(y.l, b, 48);
+  switch (op) {
+    case 0: r = fq_mul(x, y); break;
+    case 1: r = fq_add(x, y); break;
+    case 2: r = fq_sub(x, y); break;
+    case 3: r = fq_neg(x); break;
+    case 4: r = fq_sqr(x); break;
+    case 5: r = fq_pow_p34(x); break;
+    default: r = fq_zero();
+  }
+  std::memcpy(out, r.l, 48);
+}
