@@ -45,6 +45,9 @@
 #ifdef __cplusplus
 extern "C" {
 #endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
 
 /* groups */
 #define PTAU_G1 1
@@ -188,6 +191,9 @@ int ptau_load_phase1(ptau_ctx* ctx, const void* data, uint64_t len, uint64_t m, 
  * multiplication (ops = number of Fq multiplications). */
 int ptau_microbench(ptau_ctx* ctx, int gpu, int kind, int iters, double* ms, double* ops);
 
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
 #ifdef __cplusplus
 }
 #endif

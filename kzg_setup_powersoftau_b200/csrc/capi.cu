@@ -1,0 +1,674 @@
+// C-ABI host layer of libptau_b200.so (include/ptau_b200.h): context, per-GPU
+// streams and double buffers, index-range sharding, status reduction, and the
+// whole-file pipelines that reproduce the reference binaries' section tables
+// (/root/reference/src/bin/preprocess-kgz.rs:128-200,
+//  /root/reference/src/bin/preprocess-fastkgz.rs:129-214,
+//  /root/reference/src/lib.rs:82-121, :174-228).
+//
+// There is no CPU implementation of the point path in this library: without a
+// CUDA device every entry point returns PTAU_ERR_CUDA.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <chrono>
+#include <string>
+#include <vector>
+
+#include "../../include/ptau_b200.h"
+#include "kernels.h"
+
+namespace {
+
+constexpr int kMaxGpus = 8;
+constexpr int kBufs = 2;  // double buffering per GPU
+
+struct GpuSlot {
+  int device = -1;
+  cudaStream_t stream[kBufs] = {nullptr, nullptr};
+  void* d_in[kBufs] = {nullptr, nullptr};
+  void* d_out[kBufs] = {nullptr, nullptr};
+  size_t cap_in = 0, cap_out = 0;
+  unsigned long long* d_status = nullptr;
+  cudaEvent_t ev_first = nullptr, ev_last = nullptr;
+  cudaEvent_t ev_k0[kBufs] = {nullptr, nullptr}, ev_k1[kBufs] = {nullptr, nullptr};
+};
+
+}  // namespace
+
+struct ptau_ctx {
+  int n_gpus = 0;
+  size_t chunk_points = 0;
+  GpuSlot gpu[kMaxGpus];
+  ptau_timing timing;
+  std::string last_error;
+};
+
+namespace {
+
+#define CUDA_TRY(ctx, expr)                                                          \
+  do {                                                                               \
+    cudaError_t _e = (expr);                                                         \
+    if (_e != cudaSuccess) {                                                         \
+      if (ctx) (ctx)->last_error = std::string(#expr) + ": " + cudaGetErrorString(_e); \
+      return PTAU_ERR_CUDA;                                                          \
+    }                                                                                \
+  } while (0)
+
+int rec_size(int group, int fmt) {
+  if (group != PTAU_G1 && group != PTAU_G2) return 0;
+  bool g1 = group == PTAU_G1;
+  switch (fmt) {
+    case PTAU_FMT_ZCASH_UNCOMPRESSED:
+    case PTAU_FMT_ARK_UNCOMPRESSED:
+      return g1 ? 96 : 192;
+    case PTAU_FMT_ZCASH_COMPRESSED:
+      return g1 ? 48 : 96;
+    case PTAU_FMT_ARK_MONT_LIMBS:
+      return g1 ? 104 : 200;
+  }
+  return 0;
+}
+
+int ensure_buffers(ptau_ctx* ctx, GpuSlot& s, size_t need_in, size_t need_out) {
+  if (need_in > s.cap_in) {
+    for (int b = 0; b < kBufs; b++) {
+      if (s.d_in[b]) CUDA_TRY(ctx, cudaFree(s.d_in[b]));
+      s.d_in[b] = nullptr;
+      CUDA_TRY(ctx, cudaMalloc(&s.d_in[b], need_in));
+    }
+    s.cap_in = need_in;
+  }
+  if (need_out > s.cap_out) {
+    for (int b = 0; b < kBufs; b++) {
+      if (s.d_out[b]) CUDA_TRY(ctx, cudaFree(s.d_out[b]));
+      s.d_out[b] = nullptr;
+      CUDA_TRY(ctx, cudaMalloc(&s.d_out[b], need_out));
+    }
+    s.cap_out = need_out;
+  }
+  return PTAU_OK;
+}
+
+// ---- Fr arithmetic on the host (scalars of the synthetic generator) ----------
+typedef unsigned __int128 u128;
+struct Fr {
+  uint64_t l[4];
+};
+const uint64_t FR_MOD[4] = {0xffffffff00000001ull, 0x53bda402fffe5bfeull, 0x3339d80809a1d805ull,
+                            0x73eda753299d7d48ull};
+const uint64_t FR_INV = 0xfffffffeffffffffull;  // -r^-1 mod 2^64
+// R^2 mod r, R = 2^256
+const uint64_t FR_R2[4] = {0xc999e990f3f29c6dull, 0x2b6cedcb87925c23ull, 0x05d314967254398full,
+                           0x0748d9d99f59ff11ull};
+
+bool fr_ge_mod(const uint64_t* a) {
+  for (int i = 3; i >= 0; --i) {
+    if (a[i] > FR_MOD[i]) return true;
+    if (a[i] < FR_MOD[i]) return false;
+  }
+  return true;
+}
+Fr fr_mont_mul(const Fr& a, const Fr& b) {
+  uint64_t t[6] = {0, 0, 0, 0, 0, 0};
+  for (int i = 0; i < 4; i++) {
+    u128 c = 0;
+    for (int j = 0; j < 4; j++) {
+      c += (u128)a.l[j] * b.l[i] + t[j];
+      t[j] = (uint64_t)c;
+      c >>= 64;
+    }
+    c += t[4];
+    t[4] = (uint64_t)c;
+    t[5] = (uint64_t)(c >> 64);
+    uint64_t m = t[0] * FR_INV;
+    c = (u128)m * FR_MOD[0] + t[0];
+    c >>= 64;
+    for (int j = 1; j < 4; j++) {
+      c += (u128)m * FR_MOD[j] + t[j];
+      t[j - 1] = (uint64_t)c;
+      c >>= 64;
+    }
+    c += t[4];
+    t[3] = (uint64_t)c;
+    t[4] = t[5] + (uint64_t)(c >> 64);
+  }
+  Fr r;
+  memcpy(r.l, t, 32);
+  if (t[4] || fr_ge_mod(r.l)) {
+    u128 bw = 0;
+    for (int i = 0; i < 4; i++) {
+      u128 d = (u128)r.l[i] - FR_MOD[i] - (uint64_t)bw;
+      r.l[i] = (uint64_t)d;
+      bw = (d >> 64) & 1;
+    }
+  }
+  return r;
+}
+Fr fr_from_le32(const uint8_t* b) {
+  Fr r;
+  memcpy(r.l, b, 32);
+  return r;
+}
+Fr fr_to_mont(const Fr& a) {
+  Fr r2;
+  memcpy(r2.l, FR_R2, 32);
+  return fr_mont_mul(a, r2);
+}
+Fr fr_from_mont(const Fr& a) {
+  Fr one = {{1, 0, 0, 0}};
+  return fr_mont_mul(a, one);
+}
+Fr fr_pow_mont(Fr base_m, uint64_t e, const Fr& one_m) {
+  Fr acc = one_m;
+  while (e) {
+    if (e & 1) acc = fr_mont_mul(acc, base_m);
+    base_m = fr_mont_mul(base_m, base_m);
+    e >>= 1;
+  }
+  return acc;
+}
+
+struct Section {
+  int group;
+  uint64_t count;
+};
+
+}  // namespace
+
+extern "C" {
+
+int ptau_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+const char* ptau_strerror(int code) {
+  switch (code) {
+    case PTAU_OK: return "ok";
+    case PTAU_BAD_NON_CANONICAL: return "coordinate not canonical (>= p)";
+    case PTAU_BAD_FLAGS: return "illegal encoding flag bits";
+    case PTAU_BAD_INFINITY: return "point at infinity";
+    case PTAU_BAD_NOT_ON_CURVE: return "point not on the curve";
+    case PTAU_BAD_NOT_IN_SUBGROUP: return "point not in the prime-order subgroup";
+    case PTAU_ERR_CUDA: return "CUDA runtime error (no CPU fallback exists)";
+    case PTAU_ERR_ARG: return "invalid argument";
+    case PTAU_ERR_SIZE: return "buffer or file size does not match the layout";
+    case PTAU_ERR_NOMEM: return "out of memory";
+    case PTAU_ERR_IO: return "I/O error";
+  }
+  return "unknown";
+}
+
+int ptau_create(ptau_ctx** out, int n_gpus, const int* device_ids, size_t chunk_points) {
+  if (!out || n_gpus < 1 || n_gpus > kMaxGpus) return PTAU_ERR_ARG;
+  int have = 0;
+  if (cudaGetDeviceCount(&have) != cudaSuccess || have < 1) return PTAU_ERR_CUDA;
+  ptau_ctx* ctx = new ptau_ctx();
+  ctx->n_gpus = n_gpus;
+  ctx->chunk_points = chunk_points ? chunk_points : (size_t)1 << 18;
+  memset(&ctx->timing, 0, sizeof(ctx->timing));
+  for (int g = 0; g < n_gpus; g++) {
+    GpuSlot& s = ctx->gpu[g];
+    s.device = device_ids ? device_ids[g] : g;
+    if (s.device < 0 || s.device >= have) {
+      delete ctx;
+      return PTAU_ERR_ARG;
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, s.device) != cudaSuccess || prop.major < 10) {
+      delete ctx;
+      return PTAU_ERR_CUDA;  // kernels are built for sm_100a only
+    }
+    bool ok = cudaSetDevice(s.device) == cudaSuccess;
+    for (int b = 0; ok && b < kBufs; b++) {
+      ok = ok && cudaStreamCreateWithFlags(&s.stream[b], cudaStreamNonBlocking) == cudaSuccess;
+      ok = ok && cudaEventCreate(&s.ev_k0[b]) == cudaSuccess && cudaEventCreate(&s.ev_k1[b]) == cudaSuccess;
+    }
+    ok = ok && cudaEventCreate(&s.ev_first) == cudaSuccess && cudaEventCreate(&s.ev_last) == cudaSuccess;
+    ok = ok && cudaMalloc(&s.d_status, sizeof(unsigned long long)) == cudaSuccess;
+    if (!ok) {
+      ptau_destroy(ctx);
+      return PTAU_ERR_CUDA;
+    }
+  }
+  *out = ctx;
+  return PTAU_OK;
+}
+
+void ptau_destroy(ptau_ctx* ctx) {
+  if (!ctx) return;
+  for (int g = 0; g < ctx->n_gpus; g++) {
+    GpuSlot& s = ctx->gpu[g];
+    if (s.device < 0) continue;
+    cudaSetDevice(s.device);
+    for (int b = 0; b < kBufs; b++) {
+      if (s.stream[b]) cudaStreamSynchronize(s.stream[b]);
+      if (s.d_in[b]) cudaFree(s.d_in[b]);
+      if (s.d_out[b]) cudaFree(s.d_out[b]);
+      if (s.ev_k0[b]) cudaEventDestroy(s.ev_k0[b]);
+      if (s.ev_k1[b]) cudaEventDestroy(s.ev_k1[b]);
+      if (s.stream[b]) cudaStreamDestroy(s.stream[b]);
+    }
+    if (s.d_status) cudaFree(s.d_status);
+    if (s.ev_first) cudaEventDestroy(s.ev_first);
+    if (s.ev_last) cudaEventDestroy(s.ev_last);
+  }
+  delete ctx;
+}
+
+const char* ptau_last_error(ptau_ctx* ctx) { return ctx ? ctx->last_error.c_str() : ""; }
+
+int ptau_last_timing(ptau_ctx* ctx, ptau_timing* out) {
+  if (!ctx || !out) return PTAU_ERR_ARG;
+  *out = ctx->timing;
+  return PTAU_OK;
+}
+
+void* ptau_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) return nullptr;
+  return p;
+}
+void ptau_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+int ptau_host_register(void* p, size_t bytes) {
+  return cudaHostRegister(p, bytes, cudaHostRegisterPortable) == cudaSuccess ? PTAU_OK : PTAU_ERR_CUDA;
+}
+int ptau_host_unregister(void* p) { return cudaHostUnregister(p) == cudaSuccess ? PTAU_OK : PTAU_ERR_CUDA; }
+
+size_t ptau_record_size(int group, int fmt) { return (size_t)rec_size(group, fmt); }
+
+uint64_t ptau_response_size(uint64_t n) {
+  return 64 + (2 * n - 1) * 48 + n * 96 + n * 48 + n * 48 + 96 + (3 * 192 + 6 * 96);
+}
+uint64_t ptau_uncompressed_size(uint64_t n) { return (2 * n - 1) * 96 + n * 192 + n * 96 + n * 96 + 192; }
+uint64_t ptau_setup_size(int variant, uint64_t n) {
+  if (variant == PTAU_VARIANT_KGZ) return (2 * n - 1) * 96 + n * 96 + 96 + 96 + 192 + 192;
+  if (variant == PTAU_VARIANT_FASTKGZ) return (2 * n - 1) * 96 + n * 96 + 192 + 192 + n * 192;
+  return 0;
+}
+
+int ptau_status_decode(uint64_t status, uint64_t* bad_index) {
+  if (status == PTAU_STATUS_NONE) return PTAU_OK;
+  if (bad_index) *bad_index = status >> 8;
+  return (int)(status & 0xff);
+}
+
+int ptau_convert_device(ptau_ctx* ctx, int gpu, int group, int in_fmt, const void* d_in, int out_fmt, void* d_out,
+                        size_t n_points, unsigned checks, uint64_t base_index, uint64_t* d_status, void* stream) {
+  if (!ctx || gpu < 0 || gpu >= ctx->n_gpus || !d_status) return PTAU_ERR_ARG;
+  if (!rec_size(group, in_fmt) || !rec_size(group, out_fmt) || in_fmt == PTAU_FMT_ARK_MONT_LIMBS ||
+      out_fmt == PTAU_FMT_ZCASH_COMPRESSED)
+    return PTAU_ERR_ARG;
+  if (((uintptr_t)d_in | (uintptr_t)d_out) & 15) return PTAU_ERR_ARG;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->gpu[gpu].device));
+  CUDA_TRY(ctx, ptau::launch_convert(group, in_fmt, out_fmt, d_in, d_out, n_points, checks, base_index,
+                                     (unsigned long long*)d_status, (cudaStream_t)stream));
+  return PTAU_OK;
+}
+
+int ptau_convert(ptau_ctx* ctx, int group, int in_fmt, const void* in, int out_fmt, void* out, size_t n_points,
+                 unsigned checks, uint64_t* bad_index, int* bad_kind) {
+  if (!ctx || (!in && n_points) || (!out && n_points)) return PTAU_ERR_ARG;
+  const int ri = rec_size(group, in_fmt), ro = rec_size(group, out_fmt);
+  if (!ri || !ro || in_fmt == PTAU_FMT_ARK_MONT_LIMBS || out_fmt == PTAU_FMT_ZCASH_COMPRESSED) return PTAU_ERR_ARG;
+  auto t0 = std::chrono::steady_clock::now();
+  const int G = ctx->n_gpus;
+  const size_t chunk = ctx->chunk_points;
+  ptau_timing& tm = ctx->timing;
+  memset(&tm, 0, sizeof(tm));
+  tm.n_gpus = G;
+
+  struct Range {
+    size_t lo, hi, next;
+    int issued;
+  } rg[kMaxGpus];
+  const unsigned long long none = PTAU_STATUS_NONE;
+  for (int g = 0; g < G; g++) {
+    rg[g].lo = (size_t)(((unsigned __int128)n_points * g) / G);
+    rg[g].hi = (size_t)(((unsigned __int128)n_points * (g + 1)) / G);
+    rg[g].next = rg[g].lo;
+    rg[g].issued = 0;
+    GpuSlot& s = ctx->gpu[g];
+    CUDA_TRY(ctx, cudaSetDevice(s.device));
+    size_t maxpts = rg[g].hi - rg[g].lo < chunk ? rg[g].hi - rg[g].lo : chunk;
+    int rc = ensure_buffers(ctx, s, maxpts * ri + 16, maxpts * ro + 16);
+    if (rc) return rc;
+    CUDA_TRY(ctx, cudaMemcpyAsync(s.d_status, &none, sizeof(none), cudaMemcpyHostToDevice, s.stream[0]));
+    CUDA_TRY(ctx, cudaEventRecord(s.ev_first, s.stream[0]));
+    // stream[1] must not start before the status word is initialised
+    CUDA_TRY(ctx, cudaStreamWaitEvent(s.stream[1], s.ev_first, 0));
+  }
+  // breadth-first issue: one chunk per GPU per round, alternating the two streams
+  std::vector<float> kms[kMaxGpus];
+  bool more = true;
+  while (more) {
+    more = false;
+    for (int g = 0; g < G; g++) {
+      Range& r = rg[g];
+      if (r.next >= r.hi) continue;
+      GpuSlot& s = ctx->gpu[g];
+      CUDA_TRY(ctx, cudaSetDevice(s.device));
+      const int b = r.issued % kBufs;
+      size_t npts = r.hi - r.next < chunk ? r.hi - r.next : chunk;
+      if (r.issued >= kBufs) {
+        // the event pair of this buffer is about to be reused: harvest its time
+        CUDA_TRY(ctx, cudaEventSynchronize(s.ev_k1[b]));
+        float ms = 0;
+        CUDA_TRY(ctx, cudaEventElapsedTime(&ms, s.ev_k0[b], s.ev_k1[b]));
+        tm.kernel_ms[g] += ms;
+      }
+      const uint8_t* src = (const uint8_t*)in + r.next * (size_t)ri;
+      uint8_t* dst = (uint8_t*)out + r.next * (size_t)ro;
+      CUDA_TRY(ctx, cudaMemcpyAsync(s.d_in[b], src, npts * ri, cudaMemcpyHostToDevice, s.stream[b]));
+      CUDA_TRY(ctx, cudaEventRecord(s.ev_k0[b], s.stream[b]));
+      CUDA_TRY(ctx, ptau::launch_convert(group, in_fmt, out_fmt, s.d_in[b], s.d_out[b], npts, checks, r.next,
+                                         s.d_status, s.stream[b]));
+      CUDA_TRY(ctx, cudaEventRecord(s.ev_k1[b], s.stream[b]));
+      CUDA_TRY(ctx, cudaMemcpyAsync(dst, s.d_out[b], npts * ro, cudaMemcpyDeviceToHost, s.stream[b]));
+      tm.h2d_bytes[g] += npts * ri;
+      tm.d2h_bytes[g] += npts * ro;
+      tm.kernel_launches++;
+      r.next += npts;
+      r.issued++;
+      more = true;
+    }
+  }
+  unsigned long long status = PTAU_STATUS_NONE;
+  for (int g = 0; g < G; g++) {
+    GpuSlot& s = ctx->gpu[g];
+    CUDA_TRY(ctx, cudaSetDevice(s.device));
+    // join stream[1] into stream[0], read the status word back, stamp the end
+    CUDA_TRY(ctx, cudaEventRecord(s.ev_last, s.stream[1]));
+    CUDA_TRY(ctx, cudaStreamWaitEvent(s.stream[0], s.ev_last, 0));
+    unsigned long long st = PTAU_STATUS_NONE;
+    CUDA_TRY(ctx, cudaMemcpyAsync(&st, s.d_status, sizeof(st), cudaMemcpyDeviceToHost, s.stream[0]));
+    CUDA_TRY(ctx, cudaEventRecord(s.ev_last, s.stream[0]));
+    CUDA_TRY(ctx, cudaStreamSynchronize(s.stream[0]));
+    CUDA_TRY(ctx, cudaStreamSynchronize(s.stream[1]));
+    if (st < status) status = st;
+    float ms = 0;
+    CUDA_TRY(ctx, cudaEventElapsedTime(&ms, s.ev_first, s.ev_last));
+    tm.gpu_ms[g] = ms;
+    int pending = rg[g].issued < kBufs ? rg[g].issued : kBufs;
+    for (int b = 0; b < pending; b++) {
+      float k = 0;
+      CUDA_TRY(ctx, cudaEventElapsedTime(&k, s.ev_k0[b], s.ev_k1[b]));
+      tm.kernel_ms[g] += k;
+    }
+  }
+  tm.wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  if (status != PTAU_STATUS_NONE) {
+    if (bad_index) *bad_index = status >> 8;
+    if (bad_kind) *bad_kind = (int)(status & 0xff);
+    return (int)(status & 0xff);
+  }
+  return PTAU_OK;
+}
+
+// ---- generator -------------------------------------------------------------------
+int ptau_generate_device(ptau_ctx* ctx, int gpu, int group, int fmt, const uint8_t scalar0[32], const uint8_t step[32],
+                         uint64_t first, size_t n_points, void* d_out, void* stream) {
+  if (!ctx || gpu < 0 || gpu >= ctx->n_gpus || !scalar0 || !step) return PTAU_ERR_ARG;
+  if (fmt != PTAU_FMT_ZCASH_COMPRESSED && fmt != PTAU_FMT_ZCASH_UNCOMPRESSED) return PTAU_ERR_ARG;
+  if (!rec_size(group, fmt)) return PTAU_ERR_ARG;
+  if (n_points == 0) return PTAU_OK;
+  Fr one_m = fr_to_mont(Fr{{1, 0, 0, 0}});
+  Fr s0 = fr_from_le32(scalar0), st = fr_from_le32(step);
+  if (fr_ge_mod(s0.l) || fr_ge_mod(st.l)) return PTAU_ERR_ARG;
+  Fr step_m = fr_to_mont(st);
+  Fr cur = fr_mont_mul(fr_to_mont(s0), fr_pow_mont(step_m, first, one_m));
+  CUDA_TRY(ctx, cudaSetDevice(ctx->gpu[gpu].device));
+  // scalars are produced on the host in slabs and shipped as plain LE limbs
+  const size_t slab = (size_t)1 << 20;
+  uint32_t* h_sc = nullptr;
+  uint32_t* d_sc = nullptr;
+  size_t cap = n_points < slab ? n_points : slab;
+  CUDA_TRY(ctx, cudaHostAlloc((void**)&h_sc, cap * 32, cudaHostAllocDefault));
+  if (cudaMalloc((void**)&d_sc, cap * 32) != cudaSuccess) {
+    cudaFreeHost(h_sc);
+    ctx->last_error = "cudaMalloc(scalars)";
+    return PTAU_ERR_CUDA;
+  }
+  const int ro = rec_size(group, fmt);
+  int rc = PTAU_OK;
+  for (size_t off = 0; off < n_points && rc == PTAU_OK; off += slab) {
+    size_t n = n_points - off < slab ? n_points - off : slab;
+    for (size_t i = 0; i < n; i++) {
+      Fr plain = fr_from_mont(cur);
+      memcpy(h_sc + i * 8, plain.l, 32);
+      cur = fr_mont_mul(cur, step_m);
+    }
+    cudaError_t e = cudaMemcpyAsync(d_sc, h_sc, n * 32, cudaMemcpyHostToDevice, (cudaStream_t)stream);
+    if (e == cudaSuccess)
+      e = ptau::launch_generate(group, fmt, d_sc, (uint8_t*)d_out + off * ro, n, (cudaStream_t)stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);  // h_sc / d_sc are reused
+    if (e != cudaSuccess) {
+      ctx->last_error = std::string("generate: ") + cudaGetErrorString(e);
+      rc = PTAU_ERR_CUDA;
+    }
+  }
+  cudaFree(d_sc);
+  cudaFreeHost(h_sc);
+  return rc;
+}
+
+int ptau_generate(ptau_ctx* ctx, int group, int fmt, const uint8_t scalar0[32], const uint8_t step[32], uint64_t first,
+                  size_t n_points, void* out) {
+  if (!ctx || (!out && n_points)) return PTAU_ERR_ARG;
+  const int ro = rec_size(group, fmt);
+  if (!ro) return PTAU_ERR_ARG;
+  // one GPU is plenty for a generator; chunk through that GPU's output buffer
+  GpuSlot& s = ctx->gpu[0];
+  CUDA_TRY(ctx, cudaSetDevice(s.device));
+  const size_t chunk = ctx->chunk_points;
+  int rc = ensure_buffers(ctx, s, 16, (n_points < chunk ? n_points : chunk) * ro + 16);
+  if (rc) return rc;
+  for (size_t off = 0; off < n_points; off += chunk) {
+    size_t n = n_points - off < chunk ? n_points - off : chunk;
+    rc = ptau_generate_device(ctx, 0, group, fmt, scalar0, step, first + off, n, s.d_out[0], s.stream[0]);
+    if (rc) return rc;
+    CUDA_TRY(ctx, cudaMemcpyAsync((uint8_t*)out + off * ro, s.d_out[0], n * ro, cudaMemcpyDeviceToHost, s.stream[0]));
+    CUDA_TRY(ctx, cudaStreamSynchronize(s.stream[0]));
+  }
+  return PTAU_OK;
+}
+
+// ---- whole-file pipelines ----------------------------------------------------------
+static int run_sections(ptau_ctx* ctx, const Section* secs, int nsec, int in_fmt, const uint8_t* in,
+                        const int* out_fmt, uint8_t* const* out, unsigned checks, uint64_t* bad_index, int* bad_kind,
+                        int* bad_section) {
+  // Sections are processed in file order and the first failing section wins, so
+  // the reported (section, index) is the first bad point in file order.
+  ptau_timing total;
+  memset(&total, 0, sizeof(total));
+  total.n_gpus = ctx->n_gpus;
+  size_t off = 0;
+  for (int s = 0; s < nsec; s++) {
+    const int ri = rec_size(secs[s].group, in_fmt);
+    if (out[s]) {
+      int rc = ptau_convert(ctx, secs[s].group, in_fmt, in + off, out_fmt[s], out[s], secs[s].count, checks,
+                            bad_index, bad_kind);
+      total.wall_ms += ctx->timing.wall_ms;
+      total.kernel_launches += ctx->timing.kernel_launches;
+      for (int g = 0; g < ctx->n_gpus; g++) {
+        total.gpu_ms[g] += ctx->timing.gpu_ms[g];
+        total.kernel_ms[g] += ctx->timing.kernel_ms[g];
+        total.h2d_bytes[g] += ctx->timing.h2d_bytes[g];
+        total.d2h_bytes[g] += ctx->timing.d2h_bytes[g];
+      }
+      if (rc != PTAU_OK) {
+        if (bad_section) *bad_section = s;
+        ctx->timing = total;
+        return rc;
+      }
+    }
+    off += secs[s].count * (size_t)ri;
+  }
+  ctx->timing = total;
+  return PTAU_OK;
+}
+
+static int assemble_setup(int variant, uint64_t n, uint8_t* setup, const uint8_t* tau_g2_ark) {
+  // kgz tail: VerifierKey { g = tau_g1[0], gamma_g = alpha_g1[0], h = tau_g2[0], beta_h = tau_g2[1] }
+  //   (preprocess-kgz.rs:177-194)
+  // fastkgz: h, beta_h are the first two entries of powers_of_h, which follow
+  //   (preprocess-fastkgz.rs:163-208) -- already in place, copy h/beta_h in front.
+  const uint64_t g1_all = (2 * n - 1) * 96 + n * 96;
+  if (variant == PTAU_VARIANT_KGZ) {
+    uint8_t* tail = setup + g1_all;
+    memcpy(tail, setup, 96);                           // g
+    memcpy(tail + 96, setup + (2 * n - 1) * 96, 96);   // gamma_g
+    memcpy(tail + 192, tau_g2_ark, 192);               // h
+    memcpy(tail + 384, tau_g2_ark + 192, 192);         // beta_h
+  } else {
+    memcpy(setup + g1_all, tau_g2_ark, 384);           // h, beta_h
+  }
+  return PTAU_OK;
+}
+
+static int preprocess_common(ptau_ctx* ctx, int variant, int in_fmt, const uint8_t* body, uint64_t n, uint8_t* setup,
+                             unsigned checks, uint64_t* bad_index, int* bad_kind, int* bad_section) {
+  if (n < 2) return PTAU_ERR_ARG;
+  const bool fast = variant == PTAU_VARIANT_FASTKGZ;
+  const Section secs[5] = {{PTAU_G1, 2 * n - 1}, {PTAU_G2, n}, {PTAU_G1, n}, {PTAU_G1, n}, {PTAU_G2, 1}};
+  // tau_g2: kgz needs only [0], [1] in the output but the reference checks all n
+  // (preprocess-kgz.rs:146-148), so all n are converted; kgz keeps them in a
+  // scratch buffer, fastkgz writes them in place as powers_of_h.
+  const uint64_t g1_all = (2 * n - 1) * 96 + n * 96;
+  std::vector<uint8_t> scratch_g2;
+  uint8_t* tau_g2_out;
+  if (fast) {
+    tau_g2_out = setup + g1_all + 384;
+  } else {
+    scratch_g2.resize(n * 192);
+    tau_g2_out = scratch_g2.data();
+  }
+  std::vector<uint8_t> scratch_beta;
+  if (fast) scratch_beta.resize(n * 96);  // beta_tau_powers_g1: read, checked, dropped (preprocess-fastkgz.rs:156-159)
+  int fmts[5] = {PTAU_FMT_ARK_UNCOMPRESSED, PTAU_FMT_ARK_UNCOMPRESSED, PTAU_FMT_ARK_UNCOMPRESSED,
+                 PTAU_FMT_ARK_UNCOMPRESSED, PTAU_FMT_ARK_UNCOMPRESSED};
+  // beta_g2 (section 4) is never read by either binary (preprocess-fastkgz.rs:161)
+  uint8_t* outs[5] = {setup, tau_g2_out, setup + (2 * n - 1) * 96, fast ? scratch_beta.data() : nullptr, nullptr};
+  int rc = run_sections(ctx, secs, 5, in_fmt, body, fmts, outs, checks, bad_index, bad_kind, bad_section);
+  if (rc) return rc;
+  return assemble_setup(variant, n, setup, tau_g2_out);
+}
+
+int ptau_preprocess(ptau_ctx* ctx, int variant, const void* response, uint64_t response_len, uint64_t n_powers,
+                    void* setup_out, uint64_t setup_len, void* uncompressed_out, uint64_t uncompressed_len,
+                    unsigned checks, uint64_t* bad_index, int* bad_kind, int* bad_section) {
+  if (!ctx || !response || !setup_out) return PTAU_ERR_ARG;
+  if (variant != PTAU_VARIANT_KGZ && variant != PTAU_VARIANT_FASTKGZ) return PTAU_ERR_ARG;
+  // preprocess-kgz.rs:83: the response must have exactly CONTRIBUTION_BYTE_SIZE bytes
+  if (response_len != ptau_response_size(n_powers)) return PTAU_ERR_SIZE;
+  if (setup_len != ptau_setup_size(variant, n_powers)) return PTAU_ERR_SIZE;
+  if (uncompressed_out && uncompressed_len != ptau_uncompressed_size(n_powers)) return PTAU_ERR_SIZE;
+  // skip the 64-byte challenge hash (:96-101); the trailing public key is never read
+  const uint8_t* body = (const uint8_t*)response + 64;
+  if (uncompressed_out) {
+    // two stages, exactly as the reference: decompress everything into
+    // `powersoftau_uncompressed` (:105-124), then read that back (:128-160)
+    const uint64_t n = n_powers;
+    const Section secs[5] = {{PTAU_G1, 2 * n - 1}, {PTAU_G2, n}, {PTAU_G1, n}, {PTAU_G1, n}, {PTAU_G2, 1}};
+    int fmts[5];
+    uint8_t* outs[5];
+    size_t o = 0;
+    for (int s = 0; s < 5; s++) {
+      fmts[s] = PTAU_FMT_ZCASH_UNCOMPRESSED;
+      outs[s] = (uint8_t*)uncompressed_out + o;
+      o += secs[s].count * (size_t)rec_size(secs[s].group, PTAU_FMT_ZCASH_UNCOMPRESSED);
+    }
+    int rc = run_sections(ctx, secs, 5, PTAU_FMT_ZCASH_COMPRESSED, body, fmts, outs, PTAU_CHECKS_DECOMPRESS, bad_index,
+                          bad_kind, bad_section);
+    if (rc) return rc;
+    return preprocess_common(ctx, variant, PTAU_FMT_ZCASH_UNCOMPRESSED, (const uint8_t*)uncompressed_out, n_powers,
+                             (uint8_t*)setup_out, checks, bad_index, bad_kind, bad_section);
+  }
+  // fused: compressed -> checked -> ark, no intermediate file
+  return preprocess_common(ctx, variant, PTAU_FMT_ZCASH_COMPRESSED, body, n_powers, (uint8_t*)setup_out, checks,
+                           bad_index, bad_kind, bad_section);
+}
+
+int ptau_preprocess_uncompressed(ptau_ctx* ctx, int variant, const void* uncompressed, uint64_t uncompressed_len,
+                                 uint64_t n_powers, void* setup_out, uint64_t setup_len, unsigned checks,
+                                 uint64_t* bad_index, int* bad_kind, int* bad_section) {
+  if (!ctx || !uncompressed || !setup_out) return PTAU_ERR_ARG;
+  if (variant != PTAU_VARIANT_KGZ && variant != PTAU_VARIANT_FASTKGZ) return PTAU_ERR_ARG;
+  if (uncompressed_len != ptau_uncompressed_size(n_powers)) return PTAU_ERR_SIZE;
+  if (setup_len != ptau_setup_size(variant, n_powers)) return PTAU_ERR_SIZE;
+  return preprocess_common(ctx, variant, PTAU_FMT_ZCASH_UNCOMPRESSED, (const uint8_t*)uncompressed, n_powers,
+                           (uint8_t*)setup_out, checks, bad_index, bad_kind, bad_section);
+}
+
+int ptau_load_setup(ptau_ctx* ctx, int variant, const void* setup, uint64_t setup_len, uint64_t n, unsigned checks,
+                    void* g1_out, uint64_t g1_out_len, void* g2_out, uint64_t g2_out_len, uint64_t* bad_index,
+                    int* bad_kind) {
+  if (!ctx || !setup || !g1_out || !g2_out) return PTAU_ERR_ARG;
+  if (variant != PTAU_VARIANT_KGZ && variant != PTAU_VARIANT_FASTKGZ) return PTAU_ERR_ARG;
+  if (setup_len != ptau_setup_size(variant, n)) return PTAU_ERR_SIZE;
+  const bool fast = variant == PTAU_VARIANT_FASTKGZ;
+  const uint64_t n_g1 = (3 * n - 1) + (fast ? 0 : 2);
+  const uint64_t n_g2 = fast ? n + 2 : 2;
+  if (g1_out_len != n_g1 * 104 || g2_out_len != n_g2 * 200) return PTAU_ERR_SIZE;
+  // both layouts are "all G1 records, then all G2 records" (src/lib.rs:179-192, :202-215)
+  const Section secs[2] = {{PTAU_G1, n_g1}, {PTAU_G2, n_g2}};
+  int fmts[2] = {PTAU_FMT_ARK_MONT_LIMBS, PTAU_FMT_ARK_MONT_LIMBS};
+  uint8_t* outs[2] = {(uint8_t*)g1_out, (uint8_t*)g2_out};
+  int sec = 0;
+  int rc = run_sections(ctx, secs, 2, PTAU_FMT_ARK_UNCOMPRESSED, (const uint8_t*)setup, fmts, outs, checks, bad_index,
+                        bad_kind, &sec);
+  if (rc > 0 && sec == 1 && bad_index) *bad_index += n_g1;  // index in file order over all points
+  return rc;
+}
+
+int ptau_load_phase1(ptau_ctx* ctx, const void* data, uint64_t len, uint64_t m, unsigned checks, void* g1_out,
+                     uint64_t g1_out_len, void* g2_out, uint64_t g2_out_len, uint64_t* bad_index, int* bad_kind) {
+  if (!ctx || !data || !g1_out || !g2_out) return PTAU_ERR_ARG;
+  // src/lib.rs:92-110: alpha, beta_g1 (G1), beta_g2 (G2), m G1, m G2, m G1, m G1
+  if (len != 2 * 96 + 192 + m * 96 + m * 192 + m * 96 + m * 96) return PTAU_ERR_SIZE;
+  if (g1_out_len != (2 + 3 * m) * 104 || g2_out_len != (1 + m) * 200) return PTAU_ERR_SIZE;
+  const Section secs[5] = {{PTAU_G1, 2}, {PTAU_G2, 1}, {PTAU_G1, m}, {PTAU_G2, m}, {PTAU_G1, 2 * m}};
+  int fmts[5] = {PTAU_FMT_ARK_MONT_LIMBS, PTAU_FMT_ARK_MONT_LIMBS, PTAU_FMT_ARK_MONT_LIMBS, PTAU_FMT_ARK_MONT_LIMBS,
+                 PTAU_FMT_ARK_MONT_LIMBS};
+  uint8_t* g1 = (uint8_t*)g1_out;
+  uint8_t* g2 = (uint8_t*)g2_out;
+  uint8_t* outs[5] = {g1, g2, g1 + 2 * 104, g2 + 200, g1 + (2 + m) * 104};
+  int sec = 0;
+  return run_sections(ctx, secs, 5, PTAU_FMT_ZCASH_UNCOMPRESSED, (const uint8_t*)data, fmts, outs, checks, bad_index,
+                      bad_kind, &sec);
+}
+
+int ptau_microbench(ptau_ctx* ctx, int gpu, int kind, int iters, double* ms, double* ops) {
+  if (!ctx || gpu < 0 || gpu >= ctx->n_gpus || !ms || !ops || iters < 1) return PTAU_ERR_ARG;
+  GpuSlot& s = ctx->gpu[gpu];
+  CUDA_TRY(ctx, cudaSetDevice(s.device));
+  cudaDeviceProp prop;
+  CUDA_TRY(ctx, cudaGetDeviceProperties(&prop, s.device));
+  const int block = 256;
+  const int grid = prop.multiProcessorCount * (kind == 2 ? 2 : 4);
+  uint32_t* d_out = nullptr;
+  CUDA_TRY(ctx, cudaMalloc((void**)&d_out, (size_t)grid * block * 4));
+  double o = 0;
+  cudaError_t e = ptau::launch_microbench(kind, iters > 16 ? 16 : iters, d_out, grid, block, &o, s.stream[0]);  // warm-up
+  if (e == cudaSuccess) e = cudaEventRecord(s.ev_k0[0], s.stream[0]);
+  if (e == cudaSuccess) e = ptau::launch_microbench(kind, iters, d_out, grid, block, &o, s.stream[0]);
+  if (e == cudaSuccess) e = cudaEventRecord(s.ev_k1[0], s.stream[0]);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s.stream[0]);
+  float t = 0;
+  if (e == cudaSuccess) e = cudaEventElapsedTime(&t, s.ev_k0[0], s.ev_k1[0]);
+  cudaFree(d_out);
+  if (e != cudaSuccess) {
+    ctx->last_error = std::string("microbench: ") + cudaGetErrorString(e);
+    return PTAU_ERR_CUDA;
+  }
+  *ms = t;
+  *ops = o;
+  return PTAU_OK;
+}
+
+}  // extern "C"

@@ -130,13 +130,13 @@ PTAU_HD bool jac_eq_affine(const Jac<F>& p, const F& x, const F& y) {
 #include "consts.inc"
 
 // y^2 == x^3 + 4
-PTAU_HD bool g1_on_curve(const Fq& x, const Fq& y) {
+PTAU_HD_NOINLINE bool g1_on_curve(const Fq& x, const Fq& y) {
   Fq rhs = fq_add(fq_mul(fq_sqr(x), x), k_b1_mont());
   return fq_eq(fq_sqr(y), rhs);
 }
 
 // y^2 == x^3 + 4(1+u)
-PTAU_HD bool g2_on_curve(const Fq2& x, const Fq2& y) {
+PTAU_HD_NOINLINE bool g2_on_curve(const Fq2& x, const Fq2& y) {
   Fq2 b;
   b.c0 = k_b1_mont();
   b.c1 = b.c0;
@@ -145,14 +145,14 @@ PTAU_HD bool g2_on_curve(const Fq2& x, const Fq2& y) {
 }
 
 // phi(P) == -[z^2]P   <=>   [|z|]([|z|]P) == (beta x, -y)
-PTAU_HD bool g1_in_subgroup(const Fq& x, const Fq& y) {
+PTAU_HD_NOINLINE bool g1_in_subgroup(const Fq& x, const Fq& y) {
   Jac<Fq> q = mul_zabs_affine(x, y, fq_one());
   Jac<Fq> q2 = mul_zabs_jac(q);
   return jac_eq_affine(q2, fq_mul(x, k_beta_mont()), fq_neg(y));
 }
 
 // psi(P) == [z]P   <=>   [|z|]P == -psi(P) = (psi_x, -psi_y)
-PTAU_HD bool g2_in_subgroup(const Fq2& x, const Fq2& y) {
+PTAU_HD_NOINLINE bool g2_in_subgroup(const Fq2& x, const Fq2& y) {
   Jac<Fq2> q = mul_zabs_affine(x, y, fq2_one());
   // psi_x = conj(x) * (0, cx1) = (x1*cx1, x0*cx1)
   Fq cx1 = k_psi_cx1_mont();

@@ -17,10 +17,10 @@
 
 #if defined(__CUDACC__)
 #define PTAU_HD __host__ __device__ __forceinline__
-#define PTAU_HD_NOINLINE __host__ __device__ __noinline__
+#define PTAU_HD_NOINLINE static __host__ __device__ __noinline__
 #else
 #define PTAU_HD inline
-#define PTAU_HD_NOINLINE
+#define PTAU_HD_NOINLINE static inline
 #endif
 
 namespace ptau {

@@ -1,0 +1,357 @@
+// CUDA kernels (sm_100a) of the per-point path and their launch wrappers.
+//
+// Data movement: a block of PTAU_BLOCK threads owns PTAU_BLOCK consecutive
+// records.  The packed record stream is read with coalesced 128-bit loads into
+// shared memory, each thread gathers its own record (its 12/24/48 big- or
+// little-endian words) from there, and results go back the same way.  HBM traffic
+// is exactly record_in + record_out bytes per point; everything between is
+// integer multiply-add work on the FMA pipe (IMAD.WIDE chains, see fq.cuh).
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "kernels.h"
+#include "point.cuh"
+
+namespace ptau {
+
+#define PTAU_BLOCK 128
+
+__device__ __forceinline__ uint4 ld_stream(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p));
+  return v;
+}
+
+// global -> shared, nwords u32 words (block-cooperative, 128-bit where possible)
+__device__ __forceinline__ void stage_in(const uint32_t* __restrict__ g, uint32_t* sm, int nwords) {
+  int nvec = nwords >> 2;
+  const uint4* g4 = reinterpret_cast<const uint4*>(g);
+  uint4* s4 = reinterpret_cast<uint4*>(sm);
+  for (int i = threadIdx.x; i < nvec; i += PTAU_BLOCK) s4[i] = ld_stream(g4 + i);
+  for (int i = (nvec << 2) + threadIdx.x; i < nwords; i += PTAU_BLOCK) sm[i] = g[i];
+}
+__device__ __forceinline__ void stage_out(uint32_t* __restrict__ g, const uint32_t* sm, int nwords) {
+  int nvec = nwords >> 2;
+  uint4* g4 = reinterpret_cast<uint4*>(g);
+  const uint4* s4 = reinterpret_cast<const uint4*>(sm);
+  for (int i = threadIdx.x; i < nvec; i += PTAU_BLOCK) g4[i] = s4[i];
+  for (int i = (nvec << 2) + threadIdx.x; i < nwords; i += PTAU_BLOCK) g[i] = sm[i];
+}
+
+template <int G, int INFMT, int OUTFMT>
+__global__ void __launch_bounds__(PTAU_BLOCK)
+    convert_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint64_t n, uint32_t checks,
+                   uint64_t base_index, unsigned long long* __restrict__ status) {
+  constexpr int WIN = record_bytes(G, INFMT) / 4;
+  constexpr int WOUT = record_bytes(G, OUTFMT) / 4;
+  constexpr int WMAX = WIN > WOUT ? WIN : WOUT;
+  __shared__ __align__(16) uint32_t sm[PTAU_BLOCK * WMAX];
+
+  const uint64_t rec0 = (uint64_t)blockIdx.x * PTAU_BLOCK;
+  const int nrec = (int)((n - rec0) < (uint64_t)PTAU_BLOCK ? (n - rec0) : (uint64_t)PTAU_BLOCK);
+  const int tid = threadIdx.x;
+
+  stage_in(in + rec0 * WIN, sm, nrec * WIN);
+  __syncthreads();
+
+  uint32_t win[WIN];
+  if (tid < nrec) {
+    const uint4* s4 = reinterpret_cast<const uint4*>(sm + tid * WIN);
+#pragma unroll
+    for (int j = 0; j < WIN / 4; j++) {
+      uint4 v = s4[j];
+      win[4 * j] = v.x;
+      win[4 * j + 1] = v.y;
+      win[4 * j + 2] = v.z;
+      win[4 * j + 3] = v.w;
+    }
+  }
+  __syncthreads();
+
+  if (tid < nrec) {
+    uint32_t wout[WOUT];
+    uint32_t st = (G == PTAU_G1) ? g1_process<INFMT>(win, OUTFMT, wout, checks)
+                                 : g2_process<INFMT>(win, OUTFMT, wout, checks);
+    uint2* s2 = reinterpret_cast<uint2*>(sm + tid * WOUT);
+#pragma unroll
+    for (int j = 0; j < WOUT / 2; j++) s2[j] = make_uint2(wout[2 * j], wout[2 * j + 1]);
+    if (st != PTAU_OK) atomicMin(status, (unsigned long long)(((base_index + rec0 + tid) << 8) | st));
+  }
+  __syncthreads();
+  stage_out(out + rec0 * WOUT, sm, nrec * WOUT);
+}
+
+template <int G, int INFMT, int OUTFMT>
+static cudaError_t launch_one(const void* d_in, void* d_out, uint64_t n, uint32_t checks, uint64_t base_index,
+                              unsigned long long* d_status, cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  unsigned grid = (unsigned)((n + PTAU_BLOCK - 1) / PTAU_BLOCK);
+  convert_kernel<G, INFMT, OUTFMT><<<grid, PTAU_BLOCK, 0, stream>>>(
+      (const uint32_t*)d_in, (uint32_t*)d_out, n, checks, base_index, d_status);
+  return cudaGetLastError();
+}
+
+template <int G, int INFMT>
+static cudaError_t launch_in(int out_fmt, const void* d_in, void* d_out, uint64_t n, uint32_t checks,
+                             uint64_t base_index, unsigned long long* d_status, cudaStream_t stream) {
+  switch (out_fmt) {
+    case PTAU_FMT_ZCASH_UNCOMPRESSED:
+      return launch_one<G, INFMT, PTAU_FMT_ZCASH_UNCOMPRESSED>(d_in, d_out, n, checks, base_index, d_status, stream);
+    case PTAU_FMT_ARK_UNCOMPRESSED:
+      return launch_one<G, INFMT, PTAU_FMT_ARK_UNCOMPRESSED>(d_in, d_out, n, checks, base_index, d_status, stream);
+    case PTAU_FMT_ARK_MONT_LIMBS:
+      return launch_one<G, INFMT, PTAU_FMT_ARK_MONT_LIMBS>(d_in, d_out, n, checks, base_index, d_status, stream);
+  }
+  return cudaErrorInvalidValue;
+}
+
+template <int G>
+static cudaError_t launch_g(int in_fmt, int out_fmt, const void* d_in, void* d_out, uint64_t n, uint32_t checks,
+                            uint64_t base_index, unsigned long long* d_status, cudaStream_t stream) {
+  switch (in_fmt) {
+    case PTAU_FMT_ZCASH_UNCOMPRESSED:
+      return launch_in<G, PTAU_FMT_ZCASH_UNCOMPRESSED>(out_fmt, d_in, d_out, n, checks, base_index, d_status, stream);
+    case PTAU_FMT_ZCASH_COMPRESSED:
+      return launch_in<G, PTAU_FMT_ZCASH_COMPRESSED>(out_fmt, d_in, d_out, n, checks, base_index, d_status, stream);
+    case PTAU_FMT_ARK_UNCOMPRESSED:
+      return launch_in<G, PTAU_FMT_ARK_UNCOMPRESSED>(out_fmt, d_in, d_out, n, checks, base_index, d_status, stream);
+  }
+  return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_convert(int group, int in_fmt, int out_fmt, const void* d_in, void* d_out, uint64_t n,
+                           uint32_t checks, uint64_t base_index, unsigned long long* d_status,
+                           cudaStream_t stream) {
+  if (group == PTAU_G1) return launch_g<PTAU_G1>(in_fmt, out_fmt, d_in, d_out, n, checks, base_index, d_status, stream);
+  if (group == PTAU_G2) return launch_g<PTAU_G2>(in_fmt, out_fmt, d_in, d_out, n, checks, base_index, d_status, stream);
+  return cudaErrorInvalidValue;
+}
+
+// =============================================================================
+// synthetic Powers-of-Tau generator: out[i] = [k_i] G for host-supplied scalars
+// =============================================================================
+__constant__ uint32_t K_PM2[12] = {0xffffaaa9u, 0xb9feffffu, 0xb153ffffu, 0x1eabfffeu, 0xf6b0f624u, 0x6730d2a0u,
+                                   0xf38512bfu, 0x64774b84u, 0x434bacd7u, 0x4b1ba7b6u, 0x397fe69au, 0x1a0111eau};
+
+// a^(p-2) (Fermat inverse), plain square-and-multiply over the constant exponent
+static __device__ __noinline__ Fq fq_inv(Fq a) {
+  Fq acc = a;  // top bit of p-2 (bit 380)
+#pragma unroll 1
+  for (int i = 379; i >= 0; --i) {
+    acc = fq_sqr(acc);
+    if ((K_PM2[i >> 5] >> (i & 31)) & 1u) acc = fq_mul(acc, a);
+  }
+  return acc;
+}
+
+template <class F>
+__device__ __forceinline__ void select_jac(Jac<F>& dst, const Jac<F>& a, bool take) {
+  uint32_t* d = reinterpret_cast<uint32_t*>(&dst);
+  const uint32_t* s = reinterpret_cast<const uint32_t*>(&a);
+#pragma unroll
+  for (int i = 0; i < (int)(sizeof(Jac<F>) / 4); i++) d[i] = take ? s[i] : d[i];
+}
+
+template <int G, int OUTFMT>
+__global__ void __launch_bounds__(PTAU_BLOCK)
+    generate_kernel(const uint32_t* __restrict__ scalars, uint32_t* __restrict__ out, uint64_t n) {
+  constexpr int WOUT = record_bytes(G, OUTFMT) / 4;
+  __shared__ __align__(16) uint32_t sm[PTAU_BLOCK * WOUT];
+  const uint64_t rec0 = (uint64_t)blockIdx.x * PTAU_BLOCK;
+  const int nrec = (int)((n - rec0) < (uint64_t)PTAU_BLOCK ? (n - rec0) : (uint64_t)PTAU_BLOCK);
+  const int tid = threadIdx.x;
+  if (tid < nrec) {
+    uint32_t k[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) k[j] = scalars[(rec0 + tid) * 8 + j];
+    uint32_t* o = sm + tid * WOUT;
+    if (G == PTAU_G1) {
+      Fq gx = k_g1x_mont(), gy = k_g1y_mont();
+      Jac<Fq> acc;
+      acc.X = gx;
+      acc.Y = gy;
+      acc.Z = fq_one();
+      bool started = false;
+#pragma unroll 1
+      for (int i = 254; i >= 0; --i) {
+        bool bit = (k[i >> 5] >> (i & 31)) & 1u;
+        if (started) {
+          jac_dbl(acc);
+          if (bit) jac_madd(acc, gx, gy);
+        } else if (bit) {
+          started = true;
+        }
+      }
+      // to affine (k != 0 and k < r guarantee a finite result without exceptional cases)
+      Fq zi = fq_inv(acc.Z);
+      Fq zi2 = fq_sqr(zi);
+      Fq xm = fq_mul(acc.X, zi2);
+      Fq ym = fq_mul(acc.Y, fq_mul(zi2, zi));
+      Fq xp = fq_from_mont(xm), yp = fq_from_mont(ym);
+      if (OUTFMT == PTAU_FMT_ZCASH_COMPRESSED) {
+        uint32_t fl = 0x80000000u | (fq_plain_is_largest(yp) ? 0x20000000u : 0u);
+        xp.l[11] |= fl;
+        fq_to_be_words(xp, o);
+      } else {
+        fq_to_be_words(xp, o);
+        fq_to_be_words(yp, o + 12);
+      }
+    } else {
+      Fq2 gx, gy;
+      gx.c0 = k_g2x0_mont();
+      gx.c1 = k_g2x1_mont();
+      gy.c0 = k_g2y0_mont();
+      gy.c1 = k_g2y1_mont();
+      Jac<Fq2> acc;
+      acc.X = gx;
+      acc.Y = gy;
+      acc.Z = fq2_one();
+      bool started = false;
+#pragma unroll 1
+      for (int i = 254; i >= 0; --i) {
+        bool bit = (k[i >> 5] >> (i & 31)) & 1u;
+        if (started) {
+          jac_dbl(acc);
+          if (bit) jac_madd(acc, gx, gy);
+        } else if (bit) {
+          started = true;
+        }
+      }
+      // 1/Z in Fq2 = conj(Z) / norm(Z)
+      Fq nrm = fq_add(fq_sqr(acc.Z.c0), fq_sqr(acc.Z.c1));
+      Fq ni = fq_inv(nrm);
+      Fq2 zi;
+      zi.c0 = fq_mul(acc.Z.c0, ni);
+      zi.c1 = fq_neg(fq_mul(acc.Z.c1, ni));
+      Fq2 zi2 = fq2_sqr(zi);
+      Fq2 xm = fq2_mul(acc.X, zi2);
+      Fq2 ym = fq2_mul(acc.Y, fq2_mul(zi2, zi));
+      Fq2 xp, yp;
+      xp.c0 = fq_from_mont(xm.c0);
+      xp.c1 = fq_from_mont(xm.c1);
+      yp.c0 = fq_from_mont(ym.c0);
+      yp.c1 = fq_from_mont(ym.c1);
+      if (OUTFMT == PTAU_FMT_ZCASH_COMPRESSED) {
+        bool largest = fq_is_zero(yp.c1) ? fq_plain_is_largest(yp.c0) : fq_plain_is_largest(yp.c1);
+        xp.c1.l[11] |= 0x80000000u | (largest ? 0x20000000u : 0u);
+        fq_to_be_words(xp.c1, o);
+        fq_to_be_words(xp.c0, o + 12);
+      } else {
+        fq_to_be_words(xp.c1, o);
+        fq_to_be_words(xp.c0, o + 12);
+        fq_to_be_words(yp.c1, o + 24);
+        fq_to_be_words(yp.c0, o + 36);
+      }
+    }
+  }
+  __syncthreads();
+  stage_out(out + rec0 * WOUT, sm, nrec * WOUT);
+}
+
+cudaError_t launch_generate(int group, int fmt, const uint32_t* d_scalars, void* d_out, uint64_t n,
+                            cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  unsigned grid = (unsigned)((n + PTAU_BLOCK - 1) / PTAU_BLOCK);
+  if (group == PTAU_G1 && fmt == PTAU_FMT_ZCASH_COMPRESSED)
+    generate_kernel<PTAU_G1, PTAU_FMT_ZCASH_COMPRESSED><<<grid, PTAU_BLOCK, 0, stream>>>(d_scalars, (uint32_t*)d_out, n);
+  else if (group == PTAU_G1 && fmt == PTAU_FMT_ZCASH_UNCOMPRESSED)
+    generate_kernel<PTAU_G1, PTAU_FMT_ZCASH_UNCOMPRESSED><<<grid, PTAU_BLOCK, 0, stream>>>(d_scalars, (uint32_t*)d_out, n);
+  else if (group == PTAU_G2 && fmt == PTAU_FMT_ZCASH_COMPRESSED)
+    generate_kernel<PTAU_G2, PTAU_FMT_ZCASH_COMPRESSED><<<grid, PTAU_BLOCK, 0, stream>>>(d_scalars, (uint32_t*)d_out, n);
+  else if (group == PTAU_G2 && fmt == PTAU_FMT_ZCASH_UNCOMPRESSED)
+    generate_kernel<PTAU_G2, PTAU_FMT_ZCASH_UNCOMPRESSED><<<grid, PTAU_BLOCK, 0, stream>>>(d_scalars, (uint32_t*)d_out, n);
+  else
+    return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}
+
+// =============================================================================
+// microbenchmarks: the measured denominators of the IMAD roofline
+// =============================================================================
+// kind 0: 32-bit IMAD, 8 independent dependent-chains per thread
+__global__ void __launch_bounds__(256) mb_imad(uint32_t* out, int iters, uint32_t seed) {
+  uint32_t a0 = seed + threadIdx.x, a1 = a0 * 3, a2 = a0 * 5, a3 = a0 * 7, a4 = a0 * 11, a5 = a0 * 13, a6 = a0 * 17,
+           a7 = a0 * 19;
+  uint32_t m = seed | 1u;
+#pragma unroll 1
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      asm volatile(
+          "mad.lo.u32 %0, %0, %8, %0;\n\tmad.lo.u32 %1, %1, %8, %1;\n\t"
+          "mad.lo.u32 %2, %2, %8, %2;\n\tmad.lo.u32 %3, %3, %8, %3;\n\t"
+          "mad.lo.u32 %4, %4, %8, %4;\n\tmad.lo.u32 %5, %5, %8, %5;\n\t"
+          "mad.lo.u32 %6, %6, %8, %6;\n\tmad.lo.u32 %7, %7, %8, %7;"
+          : "+r"(a0), "+r"(a1), "+r"(a2), "+r"(a3), "+r"(a4), "+r"(a5), "+r"(a6), "+r"(a7)
+          : "r"(m));
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7;
+}
+
+// kind 1: IMAD.WIDE.U32 carry chains shaped like one multiplier row pair:
+// two independent chains of 6 wide MADs (12 wide MADs per inner step)
+__global__ void __launch_bounds__(256) mb_imad_wide(uint32_t* out, int iters, uint32_t seed) {
+  uint32_t E[12], X[12], a[12];
+#pragma unroll
+  for (int i = 0; i < 12; i++) {
+    E[i] = seed + i + threadIdx.x;
+    X[i] = seed * 3 + i + threadIdx.x;
+    a[i] = seed * 7 + i * 5 + threadIdx.x;
+  }
+  uint32_t bi = seed | 1u;
+#pragma unroll 1
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      row_mac_even(E, X[11], a, bi);
+      row_mac_even(X, E[11], a + 1 - 1, bi + u);
+    }
+  }
+  uint32_t r = 0;
+#pragma unroll
+  for (int i = 0; i < 12; i++) r ^= E[i] ^ X[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = r;
+}
+
+// kind 2: dependent Fq Montgomery multiplications through the product's own
+// (non-inlined) fq_mul
+__global__ void __launch_bounds__(256) mb_fqmul(uint32_t* out, int iters, uint32_t seed) {
+  Fq x = fq_one(), y = k_beta_mont();
+  x.l[0] ^= (seed + threadIdx.x) & 0xffu;
+#pragma unroll 1
+  for (int i = 0; i < iters; i++) {
+    x = fq_mul(x, y);
+    y = fq_mul(y, x);
+  }
+  uint32_t r = 0;
+#pragma unroll
+  for (int i = 0; i < 12; i++) r ^= x.l[i] ^ y.l[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = r;
+}
+
+cudaError_t launch_microbench(int kind, int iters, uint32_t* d_out, int grid, int block, double* ops,
+                              cudaStream_t stream) {
+  double threads = (double)grid * block;
+  switch (kind) {
+    case 0:
+      mb_imad<<<grid, block, 0, stream>>>(d_out, iters, 12345u);
+      *ops = threads * iters * 64.0;
+      break;
+    case 1:
+      mb_imad_wide<<<grid, block, 0, stream>>>(d_out, iters, 12345u);
+      *ops = threads * iters * 8.0 * 12.0;
+      break;
+    case 2:
+      mb_fqmul<<<grid, block, 0, stream>>>(d_out, iters, 12345u);
+      *ops = threads * iters * 2.0;
+      break;
+    default:
+      return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace ptau

@@ -1,0 +1,19 @@
+// launch wrappers exported by kernels.cu to the C-ABI host layer (capi.cu)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ptau {
+
+cudaError_t launch_convert(int group, int in_fmt, int out_fmt, const void* d_in, void* d_out, uint64_t n,
+                           uint32_t checks, uint64_t base_index, unsigned long long* d_status,
+                           cudaStream_t stream);
+
+// d_scalars: n x 8 u32 little-endian limbs of the scalars (0 < k < r)
+cudaError_t launch_generate(int group, int fmt, const uint32_t* d_scalars, void* d_out, uint64_t n,
+                            cudaStream_t stream);
+
+cudaError_t launch_microbench(int kind, int iters, uint32_t* d_out, int grid, int block, double* ops,
+                              cudaStream_t stream);
+
+}  // namespace ptau

@@ -61,7 +61,7 @@ __constant__ uint8_t K_P34_CHAIN_D[PTAU_P34_STEPS] = PTAU_P34_CHAIN_INIT;
 static const uint8_t K_P34_CHAIN_H[PTAU_P34_STEPS] = PTAU_P34_CHAIN_INIT;
 
 // a^((p-3)/4): 376 squarings + 85 multiplications
-PTAU_HD Fq fq_pow_p34(const Fq& a) {
+PTAU_HD_NOINLINE Fq fq_pow_p34(const Fq& a) {
 #ifdef __CUDA_ARCH__
   const uint8_t* chain = K_P34_CHAIN_D;
 #else
@@ -96,7 +96,7 @@ PTAU_HD Fq fq_sqrt(const Fq& a, bool& ok) {
 // Algorithm 9 of eprint 2012/685 (two Fq2 exponentiations); the two agree up to
 // sign, and the caller fixes the sign from the encoding's "largest" flag, so the
 // produced bytes are identical (tests/test_oracle_pins.py::test_fq2_sqrt_methods).
-PTAU_HD Fq2 fq2_sqrt(const Fq2& a, bool& ok) {
+PTAU_HD_NOINLINE Fq2 fq2_sqrt(const Fq2& a, bool& ok) {
   Fq n = fq_add(fq_sqr(a.c0), fq_sqr(a.c1));
   Fq s = fq_mul(fq_pow_p34(n), n);  // sqrt(norm) if it exists; verified at the end
   Fq half = k_half_mont();

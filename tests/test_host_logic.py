@@ -1,0 +1,220 @@
+"""CPU-only checks of the product's host side: the limb-level arithmetic the CUDA
+kernels execute (compiled for the host with an emulated carry flag), the C ABI
+surface, and the N>1 sharding logic (gloo, world_size 2)."""
+import ctypes
+import json
+import os
+import random
+import re
+import subprocess
+import sys
+
+import pytest
+
+import ptau_oracle as o
+from conftest import GOLDEN, ROOT, golden
+
+SZ = {1: {1: 96, 2: 48, 3: 96, 4: 104}, 2: {1: 192, 2: 96, 3: 192, 4: 200}}
+
+
+def _conv(lib, group, in_fmt, data, out_fmt, checks):
+    n = len(data) // SZ[group][in_fmt]
+    out = (ctypes.c_uint8 * (n * SZ[group][out_fmt]))()
+    st = (ctypes.c_uint32 * max(n, 1))()
+    assert lib.hostemul_convert(group, in_fmt, bytes(data), out_fmt, out, ctypes.c_size_t(n), checks, st) == 0
+    return bytes(out), list(st)[:n]
+
+
+def test_limb_field_ops_match_bigints(hostemul):
+    P = o.P
+    rinv = pow(o.MONT_R, -1, P)
+
+    def limbs(v):
+        return (ctypes.c_uint32 * 12)(*[(v >> (32 * i)) & 0xFFFFFFFF for i in range(12)])
+
+    def op(k, a, b):
+        out = (ctypes.c_uint32 * 12)()
+        hostemul.hostemul_fq_op(k, limbs(a), limbs(b), out)
+        return sum(int(out[i]) << (32 * i) for i in range(12))
+
+    rnd = random.Random(7)
+    edge = [0, 1, 2, P - 1, P - 2, 1 << 380, o.MONT_R, (1 << 352) - 1, 0xFFFFFFFF, (P - 1) // 2, (P + 1) // 2]
+    cases = [(a, b) for a in edge for b in edge] + [(rnd.randrange(P), rnd.randrange(P)) for _ in range(1500)]
+    for a, b in cases:
+        assert op(0, a, b) == a * b * rinv % P
+        assert op(1, a, b) == (a + b) % P
+        assert op(2, a, b) == (a - b) % P
+        assert op(3, a, b) == (-a) % P
+        assert op(4, a, b) == a * a * rinv % P
+    for _ in range(3):
+        a = rnd.randrange(P)
+        assert op(5, a * o.MONT_R % P, 0) == pow(a, (P - 3) // 4, P) * o.MONT_R % P
+
+
+def test_limb_code_on_golden_files(hostemul):
+    n = 8
+    body = golden("n8_powersoftau.bin")[64:]
+    unc = golden("n8_powersoftau_uncompressed.bin")
+    kgz = golden("n8_kzg_setup_kgz.bin")
+    # fused compressed -> ark of tau_g1, and decompress-only -> zcash uncompressed
+    cnt = 2 * n - 1
+    out, st = _conv(hostemul, 1, 2, body[:cnt * 48], 3, 14)
+    assert not any(st) and out == kgz[:cnt * 96]
+    out, st = _conv(hostemul, 1, 2, body[:cnt * 48], 1, 0)
+    assert not any(st) and out == unc[:cnt * 96]
+    g2c = body[cnt * 48:cnt * 48 + n * 96]
+    out, st = _conv(hostemul, 2, 2, g2c, 1, 0)
+    assert not any(st) and out == unc[cnt * 96:cnt * 96 + n * 192]
+    out, st = _conv(hostemul, 2, 1, out, 3, 14)
+    assert not any(st) and out == golden("n8_kzg_setup_fastkgz.bin")[(3 * n - 1) * 96 + 384:]
+    out, st = _conv(hostemul, 1, 3, kgz[:(3 * n - 1) * 96], 4, 0)
+    assert not any(st) and out == golden("n8_load_kgz_g1.bin")[:(3 * n - 1) * 104]
+    out, st = _conv(hostemul, 2, 3, kgz[-384:], 4, 14)
+    assert not any(st) and out == golden("n8_load_kgz_g2.bin")
+
+
+def test_limb_code_on_edge_cases(hostemul):
+    meta = json.load(open(os.path.join(GOLDEN, "edge_cases.json")))
+    for cs in meta["cases"]:
+        rec = bytes.fromhex(cs["rec"])
+        for mode, checks in (("strict", 14), ("nocheck", 0), ("read", 4)):
+            if mode not in cs:
+                continue
+            _, st = _conv(hostemul, cs["group"], cs["in_fmt"], rec, 3, checks)
+            assert st[0] == cs[mode], (cs["desc"], mode, st[0])
+
+
+def test_limb_code_vs_c_oracle_random(hostemul, cref):
+    rnd = random.Random(21)
+    tau = rnd.randrange(1, o.R_ORDER)
+    zc1 = cref.generate(1, 2, 1, tau, 0, 40, 2)
+    zc2 = cref.generate(2, 2, 1, tau, 0, 16, 2)
+    for g, data in ((1, zc1), (2, zc2)):
+        for out_fmt, checks in ((3, 14), (1, 0), (4, 14)):
+            got, st = _conv(hostemul, g, 2, data, out_fmt, checks)
+            want, st2 = cref.convert(g, 2, data, out_fmt, checks & 4)
+            assert got == want and st == st2 == [0] * len(st)
+
+
+# ---- C ABI surface ---------------------------------------------------------------
+def _header_symbols():
+    text = open(os.path.join(ROOT, "include", "ptau_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(ptau_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from kzg_setup_powersoftau_b200 import _ffi
+
+    lib = _ffi.lib()  # raises if the .so was not built
+    syms = _header_symbols()
+    assert len(syms) >= 20
+    for s in syms:
+        assert hasattr(lib, s), "libptau_b200.so does not export %s" % s
+    assert sorted(_ffi.EXPORTED_SYMBOLS) == syms
+
+
+def test_ffi_constants_match_header():
+    from kzg_setup_powersoftau_b200 import _ffi
+
+    text = open(os.path.join(ROOT, "include", "ptau_b200.h")).read()
+    defs = dict(re.findall(r"#define\s+PTAU_([A-Z0-9_]+)\s+\(?(-?\d+)u?\)?\s", text))
+    for name, val in defs.items():
+        if hasattr(_ffi, name):
+            assert getattr(_ffi, name) == int(val), name
+    assert _ffi.CHECKS_STRICT == 14 and _ffi.CHECKS_READ == 4
+
+
+def test_layout_helpers_and_loud_failure_without_gpu():
+    import torch
+
+    import kzg_setup_powersoftau_b200 as kz
+    from kzg_setup_powersoftau_b200 import _ffi
+
+    L = _ffi.lib()
+    for k in (3, 16, 21, 26):
+        n = 1 << k
+        assert L.ptau_response_size(n) == o.response_size(n)
+        assert L.ptau_uncompressed_size(n) == o.uncompressed_size(n)
+        assert L.ptau_setup_size(kz.VARIANT_KGZ, n) == o.kgz_size(n)
+        assert L.ptau_setup_size(kz.VARIANT_FASTKGZ, n) == o.fastkgz_size(n)
+    for g in (1, 2):
+        for f in (1, 2, 3, 4):
+            assert L.ptau_record_size(g, f) == SZ[g][f]
+    assert kz._n_from_setup_size(kz.VARIANT_KGZ, o.kgz_size(1 << 21)) == 1 << 21
+    assert kz._n_from_setup_size(kz.VARIANT_FASTKGZ, o.fastkgz_size(8)) == 8
+    if not torch.cuda.is_available():
+        # no CPU fallback: creating a context must fail, loudly
+        with pytest.raises(kz.PtauError) as e:
+            kz.Context(1)
+        assert e.value.code == _ffi.ERR_CUDA
+
+
+def test_product_does_not_reference_oracle():
+    """The product path must not import, link or call anything under oracle/."""
+    pkg = os.path.join(ROOT, "kzg_setup_powersoftau_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".inc")) or f == "Makefile":
+                text = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "cpu_ref" not in text and "ptau_oracle" not in text.replace("oracle/ptau_oracle.py constants", "")
+    out = subprocess.run(["nm", "-D", os.path.join(pkg, "libptau_b200.so")], capture_output=True, text=True).stdout
+    assert "oracle_" not in out
+
+
+# ---- N > 1 host logic (gloo, world_size 2) ------------------------------------------
+_WORKER = r"""
+import os, sys
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], "oracle"))
+import torch, torch.distributed as dist
+from kzg_setup_powersoftau_b200 import sharding
+import cpu_ref
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+n = 37
+data = open(os.path.join(sys.argv[1], "tests", "golden", "n8_powersoftau_uncompressed.bin"), "rb").read()[:15 * 96]
+data = bytearray(data * 3)[: n * 96]
+bad = [11, 29]
+for b in bad:
+    data[b * 96 + 95] ^= 1          # corrupt y: off curve
+lo, hi = sharding.shard_range(n, rank, world)
+# stand-in for the GPU leg on this CPU-only box: the checker computes the shard's status
+out, st = cpu_ref.convert(1, 1, bytes(data[lo * 96:hi * 96]), 3, 14)
+local = sharding.STATUS_NONE
+for i, s in enumerate(st):
+    if s:
+        local = ((lo + i) << 8) | s
+        break
+status = sharding.reduce_status(local)
+ms = sharding.reduce_max_ms(10.0 * (rank + 1))
+total = sharding.reduce_sum(hi - lo)
+if rank == 0:
+    print("RESULT", status >> 8, status & 0xff, ms, total, flush=True)
+dist.destroy_process_group()
+"""
+
+
+def test_sharding_ranges():
+    from kzg_setup_powersoftau_b200 import sharding
+
+    for n in (0, 1, 7, 8, 1000, (1 << 28) - 1):
+        for world in (1, 2, 4, 8):
+            rs = [sharding.shard_range(n, r, world) for r in range(world)]
+            assert rs[0][0] == 0 and rs[-1][1] == n
+            for a, b in zip(rs, rs[1:]):
+                assert a[1] == b[0]
+            assert max(h - l for l, h in rs) - min(h - l for l, h in rs) <= 1
+
+
+def test_world_size_2_gloo(cref, tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    p = subprocess.run(
+        [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+         "127.0.0.1", "--master-port", "29531", str(script), ROOT],
+        capture_output=True, text=True, timeout=240, env=env)
+    assert p.returncode == 0, p.stderr[-2000:]
+    line = [l for l in p.stdout.splitlines() if l.startswith("RESULT")][0].split()
+    assert int(line[1]) == 11 and int(line[2]) == 4  # lowest bad index wins, NOT_ON_CURVE
+    assert float(line[3]) == 20.0 and int(line[4]) == 37

@@ -1,0 +1,243 @@
+"""Pins for the oracle (CPU only).  The reference's own tests hold no usable vector
+for this path, so the oracle is pinned on: published BLS12-381
+generator encodings, group-order identities, the endomorphism eigenvalues, the
+known-tau ground truth, the layout arithmetic of SURVEY Appendix B, and agreement of
+the independent C restatement with the Python one."""
+import hashlib
+import json
+import math
+import os
+import random
+
+import pytest
+
+import ptau_oracle as o
+from conftest import GOLDEN, golden
+
+# zcash / IETF pairing-friendly-curves draft serialisation of the generators
+G1_GEN_COMPRESSED = ("97f1d3a73197d7942695638c4fa9ac0fc3688c4f9774b905a14e3a3f171bac586c55e83ff97a1aeffb3af00adb22c6bb")
+G2_GEN_COMPRESSED = (
+    "93e02b6052719f607dacd3a088274f65596bd0d09920b61ab5da61bbdc7f5049334cf11213945d57e5ac7d055d042b7e"
+    "024aa2b2f08f0a91260805272dc51051c6e47ad4fa403b02b4510b647ae3d1770bac0326a805bbefd48056c8c121bdb8")
+G1_INF_COMPRESSED = "c0" + "00" * 47
+
+
+def test_generator_known_answers():
+    assert o.zcash_g1_compressed_encode(o.G1_GEN).hex() == G1_GEN_COMPRESSED
+    assert o.zcash_g2_compressed_encode(o.G2_GEN).hex() == G2_GEN_COMPRESSED
+    assert o.zcash_g1_compressed_encode(None).hex() == G1_INF_COMPRESSED
+    assert o.zcash_g1_compressed_decode(bytes.fromhex(G1_GEN_COMPRESSED)) == o.G1_GEN
+    assert o.zcash_g2_compressed_decode(bytes.fromhex(G2_GEN_COMPRESSED)) == o.G2_GEN
+    # ark uncompressed = byte-reversed zcash uncompressed (src/lib.rs:49-50, :64-76)
+    zu = o.zcash_g1_uncompressed_encode(o.G1_GEN)
+    assert o.ark_g1_serialize_uncompressed(o.G1_GEN) == zu[:48][::-1] + zu[48:][::-1]
+    assert o.read_g1_bytes(zu) == o.ark_g1_serialize_uncompressed(o.G1_GEN)
+    zu2 = o.zcash_g2_uncompressed_encode(o.G2_GEN)
+    assert o.read_g2_bytes(zu2) == o.ark_g2_serialize_uncompressed(o.G2_GEN)
+    inf = o.ark_g1_serialize_uncompressed(None)
+    assert inf == bytes(48) + b"\x01" + bytes(46) + b"\x40"
+
+
+def test_curve_identities():
+    assert o.g1_on_curve(o.G1_GEN) and o.g2_on_curve(o.G2_GEN)
+    assert o.g1_mul(o.G1_GEN, o.R_ORDER) is None and o.g2_mul(o.G2_GEN, o.R_ORDER) is None
+    assert o.R_ORDER == o.Z ** 4 - o.Z ** 2 + 1
+    # phi acts on G1 as -z^2, psi on G2 as z
+    x, y = o.G1_GEN
+    assert o.g1_mul(o.G1_GEN, (-o.Z * o.Z) % o.R_ORDER) == (o.BETA * x % o.P, y)
+    assert o.g2_mul(o.G2_GEN, o.Z % o.R_ORDER) == o.g2_psi(o.G2_GEN)
+    assert pow(o.BETA, 3, o.P) == 1 and o.BETA != 1
+    # soundness of psi(P) = [z]P needs gcd(h1, h2) = 1
+    z = o.Z
+    h1 = (z - 1) ** 2 // 3
+    h2 = (z ** 8 - 4 * z ** 7 + 5 * z ** 6 - 4 * z ** 4 + 6 * z ** 3 - 4 * z ** 2 - 4 * z + 13) // 9
+    assert math.gcd(h1, h2) == 1
+    assert (o.P + 1 - (z + 1)) == h1 * o.R_ORDER  # #E(Fp) = h1 r
+
+
+def test_subgroup_predicates_agree():
+    rnd = random.Random(3)
+    for _ in range(6):
+        k = rnd.randrange(1, o.R_ORDER)
+        q1, q2 = o.g1_mul(o.G1_GEN, k), o.g2_mul(o.G2_GEN, k)
+        assert o.g1_in_subgroup_rmul(q1) and o.g1_in_subgroup_glv(q1)
+        assert o.g2_in_subgroup_rmul(q2) and o.g2_in_subgroup_psi(q2)
+    n = 0
+    while n < 6:
+        x = rnd.randrange(o.P)
+        y = o.fq_sqrt((x ** 3 + 4) % o.P)
+        if y is None:
+            continue
+        n += 1
+        assert not o.g1_in_subgroup_rmul((x, y)) and not o.g1_in_subgroup_glv((x, y))
+    n = 0
+    while n < 4:
+        x = (rnd.randrange(o.P), rnd.randrange(o.P))
+        y = o.fq2_sqrt_alg9(o.fq2_add(o.fq2_mul(o.fq2_sqr(x), x), o.B_G2))
+        if y is None:
+            continue
+        n += 1
+        assert not o.g2_in_subgroup_rmul((x, y)) and not o.g2_in_subgroup_psi((x, y))
+
+
+def test_fq2_sqrt_methods():
+    """Algorithm 9 (reference) and the norm method (kernels) agree up to sign."""
+    rnd = random.Random(9)
+    res = nonres = 0
+    for _ in range(60):
+        a = (rnd.randrange(o.P), rnd.randrange(o.P))
+        s9, sc = o.fq2_sqrt_alg9(a), o.fq2_sqrt_complex(a)
+        assert (s9 is None) == (sc is None)
+        if s9 is None:
+            nonres += 1
+            continue
+        res += 1
+        assert o.fq2_sqr(s9) == a and sc in (s9, o.fq2_neg(s9))
+    assert res > 10 and nonres > 10
+    for a0 in (5, 7, o.P - 3):  # a1 == 0 special case
+        a = (a0, 0)
+        s9, sc = o.fq2_sqrt_alg9(a), o.fq2_sqrt_complex(a)
+        assert s9 is not None and sc in (s9, o.fq2_neg(s9))
+    assert o.fq2_sqrt_complex((0, 0)) == (0, 0)
+
+
+def test_layout_sizes():
+    # SURVEY.md Appendix B (k=21 row = the sizes the reference asserts / produces)
+    assert o.response_size(1 << 21) == 603981040
+    assert o.uncompressed_size(1 << 21) == 1207959648
+    assert o.kgz_size(1 << 21) == 603980256
+    assert o.fastkgz_size(1 << 21) == 1006633248
+    assert o.response_size(1 << 16) == 18875632 and o.kgz_size(1 << 16) == 18874848
+    assert o.response_size(1 << 26) == 19327354096
+
+
+def test_known_tau_ground_truth():
+    """Every point of the golden response equals [tau^i]G etc. computed through the
+    affine (inversion-based) addition law, independent of the Jacobian code."""
+    meta = json.load(open(os.path.join(GOLDEN, "edge_cases.json")))
+    n = meta["n_powers"]
+    tau, alpha, beta = (int(v, 16) for v in meta["scalars"])
+    assert (tau, alpha, beta) == o.derive_scalars(meta["seed"])
+    resp = golden("n8_powersoftau.bin")
+    assert len(resp) == o.response_size(n)
+    off = 64
+    acc = None
+    step = o.g1_mul(o.G1_GEN, 1)
+    # tau_g1[i] = tau * tau_g1[i-1]: check the chain tau_g1[i] == [tau] tau_g1[i-1]
+    prev = None
+    for i in range(2 * n - 1):
+        q = o.zcash_g1_compressed_decode(resp[off:off + 48])
+        off += 48
+        assert o.g1_on_curve(q)
+        if i == 0:
+            assert q == o.G1_GEN
+        else:
+            assert q == o.g1_mul(prev, tau)
+        prev = q
+    prev = None
+    for i in range(n):
+        q = o.zcash_g2_compressed_decode(resp[off:off + 96])
+        off += 96
+        assert q == (o.G2_GEN if i == 0 else o.g2_mul(prev, tau))
+        prev = q
+    for sc in (alpha, beta):
+        prev = None
+        for i in range(n):
+            q = o.zcash_g1_compressed_decode(resp[off:off + 48])
+            off += 48
+            assert q == (o.g1_mul(o.G1_GEN, sc) if i == 0 else o.g1_mul(prev, tau))
+            prev = q
+    assert o.zcash_g2_compressed_decode(resp[off:off + 96]) == o.g2_mul(o.G2_GEN, beta)
+
+
+def test_golden_pipeline_consistency():
+    n = 8
+    resp = golden("n8_powersoftau.bin")
+    unc = o.powersoftau_uncompress(resp, n)
+    assert unc == golden("n8_powersoftau_uncompressed.bin")
+    kgz = o.preprocess_kgz(unc, n)
+    fast = o.preprocess_fastkgz(unc, n)
+    assert kgz == golden("n8_kzg_setup_kgz.bin") and fast == golden("n8_kzg_setup_fastkgz.bin")
+    assert o.preprocess_kgz(unc, n, strict_on_curve=True) == kgz
+    # kgz tail = VerifierKey { g, gamma_g, h, beta_h }
+    assert kgz[-576:-480] == kgz[:96]
+    assert kgz[-480:-384] == kgz[(2 * n - 1) * 96:(2 * n) * 96]
+    assert fast[(3 * n - 1) * 96:(3 * n - 1) * 96 + 384] == fast[(3 * n - 1) * 96 + 384:(3 * n - 1) * 96 + 768]
+    with pytest.raises(ValueError):
+        o.powersoftau_uncompress(resp[:-1], n)
+    # loaders
+    pg, pgg, vk = o.load_kzg_setup(kgz, n)
+    assert len(pg) == 2 * n - 1 and len(pgg) == n and vk[0] == pg[0] and vk[1] == pgg[0]
+    pg2, pgg2, h, bh, bhf, ph = o.load_fastkzg_setup(fast, n)
+    assert pg2 == pg and pgg2 == pgg and h == ph[0] and bh == ph[1] == bhf and vk[2] == h and vk[3] == bh
+
+
+def test_kzg10_sanity_with_known_tau():
+    """Config 4's commit/open sanity check, without pairings: C = [p(tau)]G and the
+    witness W satisfies [p(tau) - v]G = [tau - z]W."""
+    meta = json.load(open(os.path.join(GOLDEN, "edge_cases.json")))
+    tau = int(meta["scalars"][0], 16)
+    pg, _, _ = o.load_kzg_setup(golden("n8_kzg_setup_kgz.bin"), 8)
+    powers = [(x, y) for x, y, inf in pg]
+    rnd = random.Random(4)
+    coeffs = [rnd.randrange(o.R_ORDER) for _ in range(6)]
+    c = o.kzg_commit(powers, coeffs)
+    ptau = sum(cf * pow(tau, i, o.R_ORDER) for i, cf in enumerate(coeffs)) % o.R_ORDER
+    assert c == o.g1_mul(o.G1_GEN, ptau)
+    zpt = rnd.randrange(o.R_ORDER)
+    v, wit = o.kzg_open(powers, coeffs, zpt)
+    assert v == sum(cf * pow(zpt, i, o.R_ORDER) for i, cf in enumerate(coeffs)) % o.R_ORDER
+    assert o.g1_mul(wit, (tau - zpt) % o.R_ORDER) == o.g1_mul(o.G1_GEN, (ptau - v) % o.R_ORDER)
+
+
+def test_blake2b_matches_reference_digest_format():
+    # blake2b_simd default = unkeyed BLAKE2b-512, hex (src/lib.rs:128-131); RFC 7693 "abc" vector
+    assert o.blake2b_hex(b"abc") == (
+        "ba80a53f981c4d0d6a2797b69f12f6e94c212f14685ac4b74b12bb6fdbffa2d17d87c5392aab792dc252d5de4533cc95"
+        "18d38aa8dbf1925ab92386edd4009923")
+    assert len(o.blake2b_hex(b"")) == 128 == len(hashlib.blake2b(b"").hexdigest())
+
+
+# ---- the C restatement against the Python one ---------------------------------
+def test_c_oracle_matches_python_on_golden(cref):
+    n = 8
+    resp = golden("n8_powersoftau.bin")
+    unc = golden("n8_powersoftau_uncompressed.bin")
+    body = resp[64:]
+    secs = [(1, 2 * n - 1), (2, n), (1, n), (1, n), (2, 1)]
+    off_c = off_u = 0
+    for g, cnt in secs:
+        rc, ru = cref.SIZES[g][2], cref.SIZES[g][1]
+        out, st = cref.convert(g, 2, body[off_c:off_c + cnt * rc], 1, 0)
+        assert not any(st) and out == unc[off_u:off_u + cnt * ru]
+        ark, st = cref.convert(g, 1, out, 3, 4, nthreads=2)  # read_g1 / read_g2 semantics
+        assert not any(st)
+        want = b"".join((o.read_g1_bytes if g == 1 else o.read_g2_bytes)(out[i * ru:(i + 1) * ru]) for i in range(cnt))
+        assert ark == want
+        off_c += cnt * rc
+        off_u += cnt * ru
+    g1, st = cref.convert(1, 3, golden("n8_kzg_setup_kgz.bin")[:(3 * n - 1) * 96], 4, 0)
+    assert g1 == golden("n8_load_kgz_g1.bin")[:(3 * n - 1) * 104]
+
+
+def test_c_oracle_matches_python_on_edge_cases(cref):
+    meta = json.load(open(os.path.join(GOLDEN, "edge_cases.json")))
+    for cs in meta["cases"]:
+        rec = bytes.fromhex(cs["rec"])
+        for mode, checks in (("strict", 14), ("nocheck", 0), ("read", 4)):
+            if mode not in cs:
+                continue
+            _, st = cref.convert(cs["group"], cs["in_fmt"], rec, 3, checks)
+            assert st[0] == cs[mode], (cs["desc"], mode)
+
+
+def test_c_oracle_generator(cref):
+    rnd = random.Random(8)
+    tau, a = rnd.randrange(1, o.R_ORDER), rnd.randrange(1, o.R_ORDER)
+    got = cref.generate(1, 2, a, tau, 5, 12, nthreads=2)
+    want = b"".join(o.zcash_g1_compressed_encode(o.g1_mul(o.G1_GEN, a * pow(tau, 5 + i, o.R_ORDER) % o.R_ORDER))
+                    for i in range(12))
+    assert got == want
+    got = cref.generate(2, 1, 1, tau, 0, 5)
+    want = b"".join(o.zcash_g2_uncompressed_encode(o.g2_mul(o.G2_GEN, pow(tau, i, o.R_ORDER))) for i in range(5))
+    assert got == want
