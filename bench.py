@@ -1,0 +1,297 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the Powers-of-Tau -> arkworks path on B200.
+
+Metric (BASELINE.json): G1/G2 points/sec, parse + (decompress) + on-curve + subgroup
+check + arkworks re-encode.  Workload at N=1 = BASELINE configs[1]: 2^20 uncompressed
+G1 tau-powers (known tau) -> canonical + on-curve + subgroup check -> ark LE.  Under
+torchrun every rank owns the next contiguous 2^20-point index range of the same
+tau-power section (weak scaling, no data-path collective).
+
+One "step" = one pass of the hot path over the rank's 2^20 points:
+  value : inputs already in HBM, kernel only, CUDA events on the launch stream
+  e2e   : ptau_convert() on pinned HOST buffers (H2D + kernel + D2H inside the timer)
+Extra legs (reported under "extra", not the headline): G1/G2 compressed (config 3),
+G2 uncompressed, unchecked load, pure re-encode (HBM-bound).
+
+`--impl reference` times the CPU restatement of the reference's algorithms
+(oracle/cpu_ref.c, kind "port": the Rust reference cannot be built here) on a
+bounded sample of the same workload with all host threads.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+LOG2_POINTS = 20
+IMAD_PER_FQMUL = 588  # 12x32-bit CIOS, lo+hi counted separately
+# SURVEY.md 8d algorithmic Fq multiplications per point
+FQMUL = {"g1_unc": 1030, "g2_unc": 1180, "g1_comp": 1500, "g2_comp": 2120}
+METRIC = "G1 points/sec parse+on-curve+subgroup-check+ark re-encode (2^20 uncompressed tau powers per GPU)"
+
+
+def sample_clocks(stop, out):
+    q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    dev = os.environ.get("LOCAL_RANK", "0")
+    while not stop.is_set():
+        try:
+            r = subprocess.run(["nvidia-smi", "-i", dev, "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                               capture_output=True, text=True, timeout=5)
+            f = [x.strip() for x in r.stdout.strip().split(",")]
+            if len(f) >= 7:
+                out.append(f)
+        except Exception:
+            pass
+        stop.wait(0.1)
+
+
+def summarize_clocks(samples):
+    if not samples:
+        return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+    sm = sorted(int(float(s[0])) for s in samples)
+    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    reasons = [n for i, n in enumerate(names) if any(s[3 + i].lower().startswith("active") for s in samples)]
+    return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(float(samples[0][1])), "reasons": reasons,
+            "samples": len(samples), "power_w_max": max(float(s[2]) for s in samples)}
+
+
+def cpu_baseline(n_sample, threads, seed_tau):
+    """The oracle (C restatement of the reference's algorithms) timed on host cores."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import cpu_ref
+
+    zu = cpu_ref.generate(1, 1, 1, seed_tau, 0, n_sample, threads)
+    t0 = time.perf_counter()
+    out, st = cpu_ref.convert(1, 1, zu, 3, 4, threads)  # read_g1 semantics: r-multiplication check
+    dt = time.perf_counter() - t0
+    assert not any(st)
+    return n_sample / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    threads = os.cpu_count() or 1
+    tau = 0x1234567890ABCDEF1234567890ABCDEF
+    n_sample = 1 << 14
+    # size the sample to ~2-4 s per step on this host
+    rate, _ = cpu_baseline(1 << 11, threads, tau)
+    while n_sample / rate > 4.0 and n_sample > (1 << 11):
+        n_sample >>= 1
+    for _ in range(args.warmup):
+        cpu_baseline(min(n_sample, 1 << 11), threads, tau)
+    t_total = 0.0
+    for _ in range(args.steps):
+        r, dt = cpu_baseline(n_sample, threads, tau)
+        t_total += dt
+    value = n_sample * args.steps / t_total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "points/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64 (6x64-bit Montgomery)",
+        "data": "synthetic", "config": {"workload": "2^20 uncompressed G1 tau-powers (configs[1])",
+                                         "sample": "%d points per step" % n_sample},
+        "cpu_baseline": {"value": value, "unit": "points/s", "cores": threads, "kind": "port",
+                         "sample": "%d uncompressed G1 points per step, r-multiplication subgroup check "
+                                   "(ark-ec 0.2 semantics), %d threads" % (n_sample, threads)},
+        "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--log2-points", type=int, default=LOG2_POINTS)
+    ap.add_argument("--no-extra", action="store_true", help="skip the non-headline legs")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    import kzg_setup_powersoftau_b200 as kz
+    from kzg_setup_powersoftau_b200 import sharding
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    ctx = kz.Context(device_ids=[local])
+    N = 1 << args.log2_points
+    tau = 0x1234567890ABCDEF1234567890ABCDEF % 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
+    ZU, ZC, AU, ML = kz.FMT_ZCASH_UNCOMPRESSED, kz.FMT_ZCASH_COMPRESSED, kz.FMT_ARK_UNCOMPRESSED, kz.FMT_ARK_MONT_LIMBS
+    STRICT = kz.CHECKS_STRICT
+    first = rank * N  # this rank's index range of the tau-power section
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- synthetic input, generated on the GPU ([tau^i]G, i in this rank's range) ----
+    d_in = torch.empty(N * 96, dtype=torch.uint8, device=dev)
+    d_out = torch.empty(N * 96, dtype=torch.uint8, device=dev)
+    ctx.generate_device(kz.G1, ZU, 1, tau, first, N, d_in.data_ptr())
+    status = torch.full((1,), -1, dtype=torch.int64, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    stream = torch.cuda.current_stream()
+
+    def timed_steps(group, in_fmt, out_fmt, checks, din, dout, n, steps, warmup):
+        for _ in range(warmup):
+            ctx.convert_device(group, in_fmt, din.data_ptr(), out_fmt, dout.data_ptr(), n, checks, status.data_ptr(),
+                               base_index=first, stream=stream.cuda_stream)
+        barrier()
+        total = 0.0
+        for _ in range(steps):
+            flush.fill_(1)  # evict L2 between timed iterations (outside the timed events)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            ctx.convert_device(group, in_fmt, din.data_ptr(), out_fmt, dout.data_ptr(), n, checks, status.data_ptr(),
+                               base_index=first, stream=stream.cuda_stream)
+            e1.record(stream)
+            e1.synchronize()
+            total += e0.elapsed_time(e1)
+        barrier()
+        return total  # ms for `steps` launches
+
+    clocks, stop = [], threading.Event()
+    th = threading.Thread(target=sample_clocks, args=(stop, clocks), daemon=True)
+    th.start()
+    ms_local = timed_steps(kz.G1, ZU, AU, STRICT, d_in, d_out, N, args.steps, args.warmup)
+    stop.set()
+    th.join()
+    assert int(status.item()) == -1, "synthetic input failed validation"
+    ms = sharding.reduce_max_ms(ms_local)
+    value = world * N * args.steps / (ms / 1e3)
+    launches = args.steps
+
+    # ---- e2e: host buffers through the public C-ABI call ----
+    h_in = kz.PinnedBuffer(N * 96)
+    h_out = kz.PinnedBuffer(N * 96)
+    torch.cuda.synchronize()
+    h_in_t = torch.from_numpy(h_in.array)
+    h_in_t.copy_(d_in.cpu())
+    for _ in range(2):
+        ctx.convert(kz.G1, ZU, h_in, AU, STRICT, out=h_out)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_launches = 0
+    for _ in range(args.steps):
+        ctx.convert(kz.G1, ZU, h_in, AU, STRICT, out=h_out)
+        e2e_launches += ctx.timing()["kernel_launches"]
+    torch.cuda.synchronize()
+    e2e_ms = sharding.reduce_max_ms((time.perf_counter() - t0) * 1e3)
+    barrier()
+    e2e_value = world * N * args.steps / (e2e_ms / 1e3)
+    assert torch.equal(torch.from_numpy(h_out.array), d_out.cpu()), "e2e output differs from device-resident output"
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u32 limbs (12x32-bit Montgomery, IMAD.WIDE carry chains)", "data": "synthetic",
+        "config": {"workload": "2^%d uncompressed G1 tau-powers per GPU (BASELINE configs[1]): canonical + on-curve + "
+                               "GLV subgroup check + ark LE re-encode" % args.log2_points,
+                   "points_per_gpu": N, "sharding": "contiguous index range per rank, no collective",
+                   "l2": "flushed (256 MB fill) between timed iterations", "checks": "strict"},
+        "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": N * 96, "d2h_bytes_per_step": N * 96,
+                "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": launches + e2e_launches,
+    }
+
+    if rank == 0:
+        line["clocks"] = summarize_clocks(clocks)
+        # ---- roofline: measured IMAD peak (microbenchmark, same process) ----
+        mb = {}
+        for kind, name in ((0, "imad32"), (1, "imad_wide"), (2, "fq_mul")):
+            t, ops = ctx.microbench(kind, 4000)
+            mb[name] = ops / (t / 1e3)
+        kernel_s = (ms_local / args.steps) / 1e3
+        achieved = N * FQMUL["g1_unc"] * IMAD_PER_FQMUL / kernel_s
+        line["roofline"] = {
+            "bound": "imad", "achieved": achieved / 1e12, "peak": mb["imad32"] / 1e12, "unit": "TIMAD/s",
+            "frac": achieved / mb["imad32"], "traffic": None,
+            "note": "integer-multiply bound, not hbm/tensor: achieved = %d Fq-mul/point x 588 IMAD (SURVEY 8d) x points / "
+                    "CUDA-event launch time; peak = 32-bit IMAD microbenchmark measured in this run (148 SM x 64/clk). "
+                    "HBM traffic is 192 B/point = %.2f GB/s, <0.1%% of %.0f GB/s" % (
+                        FQMUL["g1_unc"], 192 * N / kernel_s / 1e9, 6552.0),
+            "measured_imad_wide_per_s": mb["imad_wide"], "measured_fq_mul_per_s": mb["fq_mul"],
+        }
+        # ---- other kernels of the path (not the headline) ----
+        extra = {}
+        if not args.no_extra:
+            def leg(name, group, in_fmt, out_fmt, checks, n, key):
+                ri = kz._ffi.lib().ptau_record_size(group, in_fmt)
+                ro = kz._ffi.lib().ptau_record_size(group, out_fmt)
+                gen_fmt = ZU if in_fmt == AU else in_fmt
+                din = torch.empty(n * ri, dtype=torch.uint8, device=dev)
+                dout = torch.empty(n * ro, dtype=torch.uint8, device=dev)
+                ctx.generate_device(group, gen_fmt, 1, tau, 0, n, din.data_ptr())
+                if in_fmt == AU:
+                    tmp = torch.empty_like(din)
+                    ctx.convert_device(group, ZU, din.data_ptr(), AU, tmp.data_ptr(), n, 0, status.data_ptr())
+                    torch.cuda.synchronize()
+                    din = tmp
+                t = timed_steps(group, in_fmt, out_fmt, checks, din, dout, n, 5, 3) / 5
+                r = {"points": n, "ms": t, "points_per_s": n / (t / 1e3), "GBps": n * (ri + ro) / (t / 1e3) / 1e9}
+                if key:
+                    r["imad_frac"] = n * FQMUL[key] * IMAD_PER_FQMUL / (t / 1e3) / mb["imad32"]
+                extra[name] = r
+                del din, dout
+
+            leg("g1_compressed_strict(config3)", kz.G1, ZC, AU, STRICT, 1 << 21, "g1_comp")
+            leg("g2_compressed_strict(config3)", kz.G2, ZC, AU, STRICT, 1 << 21, "g2_comp")
+            leg("g2_uncompressed_strict", kz.G2, ZU, AU, STRICT, 1 << 20, "g2_unc")
+            leg("g1_decompress_only", kz.G1, ZC, ZU, 0, 1 << 21, None)
+            leg("g2_decompress_only", kz.G2, ZC, ZU, 0, 1 << 21, None)
+            leg("g1_load_unchecked(config4)", kz.G1, AU, ML, 0, 1 << 22, None)
+            leg("g1_load_validated(config4)", kz.G1, AU, ML, STRICT, 1 << 22, None)
+            leg("g1_reencode_only(hbm)", kz.G1, ZU, AU, 0, 1 << 23, None)
+            assert int(status.item()) == -1
+            hb = extra["g1_reencode_only(hbm)"]
+            line["roofline_hbm"] = {"bound": "hbm", "kernel": "zcash->ark re-encode only (no checks)",
+                                    "achieved": hb["GBps"], "peak": 6552.0, "unit": "GB/s",
+                                    "frac": hb["GBps"] / 6552.0, "traffic": None}
+        line["extra"] = extra
+        # ---- CPU baseline: the reference's algorithms on this box's host cores ----
+        threads = os.cpu_count() or 1
+        try:
+            rate1, _ = cpu_baseline(1 << 10, 1, tau)
+            n_s = 1 << 15
+            rate, dt = cpu_baseline(n_s, threads, tau)
+            line["cpu_baseline"] = {
+                "value": rate, "unit": "points/s", "cores": threads, "kind": "port",
+                "sample": "first 2^15 points of the workload, C restatement of the reference's algorithms "
+                          "(6x64 Montgomery, r-multiplication subgroup check), %d threads, %.1f s" % (threads, dt),
+                "single_core_value": rate1,
+            }
+        except Exception as e:  # the oracle is optional for the product, never for correctness claims
+            line["cpu_baseline"] = {"value": None, "unit": "points/s", "cores": threads, "kind": "port",
+                                    "sample": "unavailable: %r" % (e,)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,342 @@
+"""GPU parity tests: every call goes through the C ABI (libptau_b200.so) and is
+compared bit-for-bit with the oracle (Python big-int / C restatement of the
+reference's algorithms), the committed golden fixtures, and -- at BASELINE.json's
+full sizes -- size-independent properties."""
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+import ptau_oracle as o
+from conftest import GOLDEN, golden
+
+pytestmark = pytest.mark.gpu
+
+import kzg_setup_powersoftau_b200 as kz  # noqa: E402
+
+SZ = {1: {1: 96, 2: 48, 3: 96, 4: 104}, 2: {1: 192, 2: 96, 3: 192, 4: 200}}
+ZU, ZC, AU, ML = kz.FMT_ZCASH_UNCOMPRESSED, kz.FMT_ZCASH_COMPRESSED, kz.FMT_ARK_UNCOMPRESSED, kz.FMT_ARK_MONT_LIMBS
+STRICT = kz.CHECKS_STRICT
+
+
+def test_native_library_is_the_path():
+    from kzg_setup_powersoftau_b200 import _ffi
+
+    assert os.path.exists(_ffi.LIB_PATH)
+    assert _ffi.lib().ptau_device_count() >= 1
+    maps = open("/proc/self/maps").read()
+    assert "libptau_b200.so" in maps
+
+
+# ---- golden fixtures ----------------------------------------------------------------
+@pytest.mark.parametrize("variant,name", [(kz.VARIANT_KGZ, "kgz"), (kz.VARIANT_FASTKGZ, "fastkgz")])
+def test_preprocess_golden(ctx, variant, name):
+    n = 8
+    resp = golden("n8_powersoftau.bin")
+    want = golden("n8_kzg_setup_%s.bin" % name)
+    # fused path (no intermediate file)
+    got = ctx.preprocess(variant, resp, n, STRICT)
+    assert bytes(got) == want
+    # two-stage path that also emits `powersoftau_uncompressed`
+    got, unc = ctx.preprocess(variant, resp, n, STRICT, emit_uncompressed=True)
+    assert bytes(got) == want and bytes(unc) == golden("n8_powersoftau_uncompressed.bin")
+    # from the uncompressed file (load_powersoftau_accumulator)
+    got = ctx.preprocess_uncompressed(variant, golden("n8_powersoftau_uncompressed.bin"), n, kz.CHECKS_READ)
+    assert bytes(got) == want
+    # wrong size -> the reference panics at preprocess-kgz.rs:83
+    with pytest.raises(kz.PtauError) as e:
+        ctx.preprocess(variant, resp[:-1], n)
+    assert e.value.code == kz._ffi.ERR_SIZE
+
+
+def test_load_golden(ctx):
+    n = 8
+    for checks in (kz.CHECKS_LOAD, STRICT):
+        g1, g2 = ctx.load_setup(kz.VARIANT_KGZ, golden("n8_kzg_setup_kgz.bin"), n, checks)
+        assert g1.tobytes() == golden("n8_load_kgz_g1.bin") and g2.tobytes() == golden("n8_load_kgz_g2.bin")
+        g1, g2 = ctx.load_setup(kz.VARIANT_FASTKGZ, golden("n8_kzg_setup_fastkgz.bin"), n, checks)
+        assert g1.tobytes() == golden("n8_load_fastkgz_g1.bin") and g2.tobytes() == golden("n8_load_fastkgz_g2.bin")
+
+
+def test_loader_api_mirrors_reference(ctx, tmp_path):
+    n = 8
+    (tmp_path / "kzg_setup").write_bytes(golden("n8_kzg_setup_kgz.bin"))
+    powers, vk = kz.load_kzg_setup(str(tmp_path / "kzg_setup"), ctx=ctx)
+    assert powers.powers_of_g.shape == (2 * n - 1, 104) and powers.powers_of_gamma_g.shape == (n, 104)
+    pg, pgg, ovk = o.load_kzg_setup(golden("n8_kzg_setup_kgz.bin"), n)
+    assert powers.powers_of_g[5].tobytes() == o.g1_mont_record(*pg[5])
+    assert vk.g.tobytes() == o.g1_mont_record(*ovk[0]) and vk.beta_h.tobytes() == o.g2_mont_record(*ovk[3])
+    x, y, inf = kz.g1_limbs(vk.gamma_g)
+    assert not inf and int.from_bytes(x.tobytes(), "little") == ovk[1][0] * o.MONT_R % o.P
+    (tmp_path / "kzg_setup").write_bytes(golden("n8_kzg_setup_fastkgz.bin"))
+    params, ph = kz.load_fastkzg_setup(str(tmp_path / "kzg_setup"), ctx=ctx)
+    assert ph.shape == (n, 200) and params.beta_h.tobytes() == ph[1].tobytes() == params.prepared_beta_h_src.tobytes()
+    assert params.neg_powers_of_h == {}
+    # truncated file: the reference's unwrap() panics
+    (tmp_path / "kzg_setup").write_bytes(golden("n8_kzg_setup_kgz.bin")[:-7])
+    with pytest.raises(kz.PtauError):
+        kz.load_kzg_setup(str(tmp_path / "kzg_setup"), ctx=ctx)
+
+
+def test_binaries_file_behaviour(ctx, tmp_path):
+    n = 8
+    (tmp_path / "powersoftau").write_bytes(golden("n8_powersoftau.bin"))
+    kz.preprocess_kgz(str(tmp_path), log2_powers=3, expected_digest=None, ctx=ctx)
+    assert (tmp_path / "kzg_setup").read_bytes() == golden("n8_kzg_setup_kgz.bin")
+    assert (tmp_path / "powersoftau_uncompressed").read_bytes() == golden("n8_powersoftau_uncompressed.bin")
+    # create_new(true): an existing intermediate file is an error (preprocess-kgz.rs:113-118)
+    with pytest.raises(FileExistsError):
+        kz.preprocess_fastkgz(str(tmp_path), log2_powers=3, expected_digest=None, ctx=ctx)
+    os.remove(tmp_path / "powersoftau_uncompressed")
+    kz.preprocess_fastkgz(str(tmp_path), log2_powers=3, expected_digest=None, ctx=ctx)
+    assert (tmp_path / "kzg_setup").read_bytes() == golden("n8_kzg_setup_fastkgz.bin")
+    # digest check (preprocess-kgz.rs:33-47) with the synthetic file's own digest, then a wrong one
+    dg = o.blake2b_hex(golden("n8_powersoftau.bin"))
+    os.remove(tmp_path / "powersoftau_uncompressed")
+    kz.preprocess_kgz(str(tmp_path), log2_powers=3, expected_digest=dg, ctx=ctx)
+    os.remove(tmp_path / "powersoftau_uncompressed")
+    with pytest.raises(IOError):
+        kz.preprocess_kgz(str(tmp_path), log2_powers=3, ctx=ctx)  # real ceremony digest cannot match
+
+
+def test_phase1_and_read_g(ctx, tmp_path):
+    m = 4
+    data = golden("n8_phase1radix2m2.bin")
+    (tmp_path / "phase1radix2m2").write_bytes(data)
+    ph = kz.load_phase1(2, directory=str(tmp_path), ctx=ctx)
+    alpha, beta_g1, beta_g2, c1, c2, ac1, bc1 = o.load_phase1(data, m)
+    assert ph.alpha.tobytes() == o.g1_mont_record(*alpha, False)
+    assert ph.beta_g2.tobytes() == o.g2_mont_record(*beta_g2, False)
+    assert ph.coeffs_g2.tobytes() == b"".join(o.g2_mont_record(*q, False) for q in c2)
+    assert ph.beta_coeffs_g1.tobytes() == b"".join(o.g1_mont_record(*q, False) for q in bc1)
+    with open(tmp_path / "phase1radix2m2", "rb") as f:
+        a = kz.read_g1(f, ctx=ctx)
+        b = kz.read_g1(f, ctx=ctx)
+        c = kz.read_g2(f, ctx=ctx)
+    assert a.tobytes() == ph.alpha.tobytes() and b.tobytes() == ph.beta_g1.tobytes() and c.tobytes() == ph.beta_g2.tobytes()
+    import io
+
+    with pytest.raises(EOFError):
+        kz.read_g1(io.BytesIO(b"\x00" * 95), ctx=ctx)
+
+
+# ---- edge cases ------------------------------------------------------------------------
+def test_edge_cases(ctx):
+    meta = json.load(open(os.path.join(GOLDEN, "edge_cases.json")))
+    for cs in meta["cases"]:
+        rec = bytes.fromhex(cs["rec"])
+        for mode, checks in (("strict", STRICT), ("nocheck", 0), ("read", kz.CHECKS_READ)):
+            if mode not in cs:
+                continue
+            try:
+                ctx.convert(cs["group"], cs["in_fmt"], rec, AU, checks)
+                st = 0
+            except kz.PtauError as e:
+                st = e.code
+                assert e.index == 0
+            assert st == cs[mode], (cs["desc"], mode, st)
+
+
+def test_empty_ragged_and_chunk_boundaries(cref):
+    rnd = random.Random(31)
+    tau = rnd.randrange(1, o.R_ORDER)
+    n = 1000
+    zu = cref.generate(1, 1, 1, tau, 0, n, 8)
+    want = b"".join(o.read_g1_bytes(zu[i * 96:(i + 1) * 96]) for i in range(n))
+    with kz.Context(1, chunk_points=96) as small:  # forces 11 chunks, ragged tail, partial blocks
+        assert small.convert(1, ZU, b"", AU, STRICT).size == 0
+        for cnt in (1, 2, 127, 128, 129, 255, 257, 1000):
+            got = small.convert(1, ZU, zu[:cnt * 96], AU, STRICT)
+            assert got.tobytes() == want[:cnt * 96], cnt
+        assert small.timing()["kernel_launches"] == 11
+        # lowest failing index wins, across chunks, whatever the order of completion
+        bad = bytearray(zu)
+        for i in (977, 403, 404, 612):
+            bad[i * 96 + 95] ^= 0x01
+        with pytest.raises(kz.PtauError) as e:
+            small.convert(1, ZU, bytes(bad), AU, STRICT)
+        assert e.value.index == 403 and e.value.code == kz.BAD_NOT_ON_CURVE
+        with pytest.raises(kz.PtauError):
+            small.convert(1, ZU, zu[:100], AU, STRICT)  # not a whole number of records
+
+
+def test_random_batches_vs_c_oracle(ctx, cref):
+    """Seeded random sections at a size the CPU oracle finishes in seconds; the oracle
+    runs the reference's algorithms (r-multiplication, Algorithm 9)."""
+    rnd = random.Random(77)
+    tau, alpha = rnd.randrange(1, o.R_ORDER), rnd.randrange(1, o.R_ORDER)
+    n1, n2 = 3000, 1200
+    zc1 = cref.generate(1, 2, alpha, tau, 0, n1, 16)
+    zc2 = cref.generate(2, 2, 1, tau, 0, n2, 16)
+    for g, zc in ((1, zc1), (2, zc2)):
+        zu_want, st = cref.convert(g, ZC, zc, ZU, 0, 16)
+        assert not any(st)
+        au_want, st = cref.convert(g, ZU, zu_want, AU, 4, 16)
+        assert not any(st)
+        ml_want, _ = cref.convert(g, AU, au_want, ML, 0, 16)
+        assert ctx.convert(g, ZC, zc, ZU, kz.CHECKS_DECOMPRESS).tobytes() == zu_want
+        assert ctx.convert(g, ZC, zc, AU, STRICT).tobytes() == au_want
+        assert ctx.convert(g, ZU, zu_want, AU, STRICT).tobytes() == au_want
+        assert ctx.convert(g, ZU, zu_want, AU, kz.CHECKS_READ).tobytes() == au_want
+        assert ctx.convert(g, AU, au_want, ML, kz.CHECKS_LOAD).tobytes() == ml_want
+        assert ctx.convert(g, AU, au_want, ML, STRICT).tobytes() == ml_want
+        assert ctx.convert(g, ZU, zu_want, ML, STRICT).tobytes() == ml_want
+        assert ctx.convert(g, AU, au_want, ZU, 0).tobytes() == zu_want
+
+
+def test_generator_vs_oracles(ctx, cref):
+    rnd = random.Random(5)
+    tau, beta = rnd.randrange(1, o.R_ORDER), rnd.randrange(1, o.R_ORDER)
+    got = ctx.generate(1, ZC, beta, tau, 7, 25)
+    want = b"".join(o.zcash_g1_compressed_encode(o.g1_mul(o.G1_GEN, beta * pow(tau, 7 + i, o.R_ORDER) % o.R_ORDER))
+                    for i in range(25))
+    assert got.tobytes() == want
+    for g, fmt in ((1, ZU), (2, ZC), (2, ZU)):
+        assert ctx.generate(g, fmt, 1, tau, 3, 700).tobytes() == cref.generate(g, fmt, 1, tau, 3, 700, 16)
+
+
+def test_pipeline_2pow10_vs_c_oracle(ctx, cref):
+    """Whole preprocess at N = 2^10 against the C oracle assembling the same layout."""
+    n = 1 << 10
+    tau, alpha, beta = o.derive_scalars(0xB200)
+    secs = [(1, 1, 2 * n - 1), (2, 1, n), (1, alpha, n), (1, beta, n), (2, beta, 1)]
+    body = b"".join(cref.generate(g, ZC, s0, tau, 0, cnt, 16) for g, s0, cnt in secs)
+    resp = o.filler_bytes(1, 64, b"hash") + body + o.filler_bytes(1, o.PUBKEY_SIZE, b"pubkey")
+    assert len(resp) == o.response_size(n)
+    off = 0
+    ark = []
+    for g, _, cnt in secs:
+        ln = cnt * SZ[g][ZC]
+        zu, _ = cref.convert(g, ZC, body[off:off + ln], ZU, 0, 16)
+        au, st = cref.convert(g, ZU, zu, AU, 4, 16)
+        assert not any(st)
+        ark.append(au)
+        off += ln
+    kgz = ark[0] + ark[2] + ark[0][:96] + ark[2][:96] + ark[1][:384]
+    fast = ark[0] + ark[2] + ark[1][:384] + ark[1]
+    assert ctx.preprocess(kz.VARIANT_KGZ, resp, n).tobytes() == kgz
+    assert ctx.preprocess(kz.VARIANT_FASTKGZ, resp, n).tobytes() == fast
+    # a corrupted point in alpha_g1 is reported with its section and index
+    bad = bytearray(resp)
+    pos = 64 + (2 * n - 1) * 48 + n * 96 + 17 * 48
+    while True:
+        bad[pos + 47] = (bad[pos + 47] + 1) & 0xFF
+        if o.fq_sqrt((int.from_bytes(bytes([bad[pos] & 0x1F]) + bytes(bad[pos + 1:pos + 48]), "big") ** 3 + 4) % o.P) is not None:
+            break
+    with pytest.raises(kz.PtauError) as e:
+        ctx.preprocess(kz.VARIANT_KGZ, bytes(bad), n)
+    assert e.value.section == 2 and e.value.index == 17 and e.value.code == kz.BAD_NOT_IN_SUBGROUP
+
+
+# ---- full-size properties (BASELINE.json configs 2 and 3) --------------------------------
+def _reverse_fields(a: np.ndarray, nfields: int) -> np.ndarray:
+    return a.reshape(-1, nfields, 48)[:, :, ::-1]
+
+
+@pytest.mark.parametrize("log2n", [20])
+def test_config2_g1_uncompressed_full_size(ctx, log2n):
+    """2^20 uncompressed G1 tau-powers: output must be the byte reversal of each
+    coordinate (src/lib.rs:49-50), every point must pass, and the generator's known-tau
+    chain ties the points to [tau^i]G."""
+    n = 1 << log2n
+    tau = o.derive_scalars(0xB200)[0]
+    zu = ctx.generate(1, ZU, 1, tau, 0, n)
+    au = ctx.convert(1, ZU, zu, AU, STRICT)
+    assert np.array_equal(au.reshape(-1, 2, 48), _reverse_fields(zu, 2))
+    assert zu[:96].tobytes() == o.zcash_g1_uncompressed_encode(o.G1_GEN)
+    for i in (1, 2, n // 3, n - 1):  # spot-check against the big-int oracle
+        assert zu[i * 96:(i + 1) * 96].tobytes() == o.zcash_g1_uncompressed_encode(o.g1_mul(o.G1_GEN, pow(tau, i, o.R_ORDER)))
+    # idempotence / round trip: ark -> zcash -> ark
+    back = ctx.convert(1, AU, au, ZU, 0)
+    assert np.array_equal(back, zu)
+    # one flipped bit anywhere is caught, with its exact index
+    k = 777_777 % n
+    zu[k * 96 + 60] ^= 0x10
+    with pytest.raises(kz.PtauError) as e:
+        ctx.convert(1, ZU, zu, AU, STRICT)
+    assert e.value.index == k
+
+
+def test_config3_compressed_full_size(ctx):
+    """2^21 compressed G1 + 2^21 compressed G2 (reduced to 2^19 G2 under PTAU_TEST_FAST):
+    decompress(compressed) must equal the independently generated uncompressed stream
+    (encode -> decode round trip), and the fused path must equal the two-stage one."""
+    n1 = 1 << 21
+    n2 = 1 << (19 if os.environ.get("PTAU_TEST_FAST") else 21)
+    tau = o.derive_scalars(0xB200)[0]
+    for g, n in ((1, n1), (2, n2)):
+        zc = ctx.generate(g, ZC, 1, tau, 0, n)
+        zu = ctx.generate(g, ZU, 1, tau, 0, n)
+        dec = ctx.convert(g, ZC, zc, ZU, kz.CHECKS_DECOMPRESS)
+        assert np.array_equal(dec, zu)
+        fused = ctx.convert(g, ZC, zc, AU, STRICT)
+        staged = ctx.convert(g, ZU, zu, AU, kz.CHECKS_READ)
+        assert np.array_equal(fused, staged)
+        nf = 2 if g == 1 else 4
+        rev = _reverse_fields(zu, nf)
+        if g == 2:
+            rev = rev[:, [1, 0, 3, 2], :]  # c1|c0 -> c0|c1 (src/lib.rs:64-71)
+        assert np.array_equal(fused.reshape(-1, nf, 48), rev)
+        # both sort flags occur
+        flags = zc.reshape(n, -1)[:, 0] & 0x20
+        assert 0.4 < float((flags != 0).mean()) < 0.6
+
+
+def test_config4_validated_load(ctx):
+    """load of a 2^18-power kgz file (2^22 under PTAU_TEST_FULL): validated and
+    unchecked loads return identical Montgomery limbs; limbs decode back to the file."""
+    k = 22 if os.environ.get("PTAU_TEST_FULL") else 18
+    n = 1 << k
+    tau, alpha, _ = o.derive_scalars(0xB200)
+    g1 = np.concatenate([ctx.generate(1, ZU, 1, tau, 0, 2 * n - 1), ctx.generate(1, ZU, alpha, tau, 0, n)])
+    g2 = ctx.generate(2, ZU, 1, tau, 0, 2)
+    setup = np.concatenate([ctx.convert(1, ZU, g1, AU, 0), ctx.convert(1, ZU, g1[:96], AU, 0),
+                            ctx.convert(1, ZU, g1[(2 * n - 1) * 96:(2 * n) * 96], AU, 0), ctx.convert(2, ZU, g2, AU, 0)])
+    assert setup.size == o.kgz_size(n)
+    a1, a2 = ctx.load_setup(kz.VARIANT_KGZ, setup, n, kz.CHECKS_LOAD)
+    b1, b2 = ctx.load_setup(kz.VARIANT_KGZ, setup, n, STRICT)
+    assert np.array_equal(a1, b1) and np.array_equal(a2, b2)
+    assert not a1[:, 96].any() and not a1[:, 97:].any()
+    for i in (0, 1, n, 3 * n):
+        x, y, inf = o.ark_g1_deserialize_unchecked(setup[i * 96:(i + 1) * 96].tobytes())
+        assert a1[i].tobytes() == o.g1_mont_record(x, y, inf)
+    # KZG10 commit sanity with the known tau: sum c_i [tau^i]G == [p(tau)]G
+    coeffs = [3, 1, 4, 1, 5, 9, 2, 6]
+    pts = []
+    for i in range(len(coeffs)):
+        x, y, _ = o.ark_g1_deserialize_unchecked(setup[i * 96:(i + 1) * 96].tobytes())
+        pts.append((x, y))
+    ptau = sum(c * pow(tau, i, o.R_ORDER) for i, c in enumerate(coeffs)) % o.R_ORDER
+    assert o.kzg_commit(pts, coeffs) == o.g1_mul(o.G1_GEN, ptau)
+    # corrupt one point deep in the file: validated load finds it, unchecked load does not
+    setup[(2 * n + 5) * 96 + 3] ^= 0x04
+    ctx.load_setup(kz.VARIANT_KGZ, setup, n, kz.CHECKS_LOAD)
+    with pytest.raises(kz.PtauError) as e:
+        ctx.load_setup(kz.VARIANT_KGZ, setup, n, STRICT)
+    assert e.value.index == 2 * n + 5
+
+
+def test_multi_gpu_sharding_is_invisible(cref):
+    """Same bytes and same first-bad-index with 1 GPU and with every GPU of the box."""
+    from kzg_setup_powersoftau_b200 import _ffi
+
+    ngpu = _ffi.lib().ptau_device_count()
+    if ngpu < 2:
+        pytest.skip("single-GPU box")
+    tau = o.derive_scalars(7)[0]
+    n = 50_001
+    with kz.Context(1) as c1, kz.Context(ngpu, chunk_points=4096) as cn:
+        zc = c1.generate(2, ZC, 1, tau, 0, n)
+        a = c1.convert(2, ZC, zc, AU, STRICT)
+        b = cn.convert(2, ZC, zc, AU, STRICT)
+        assert np.array_equal(a, b)
+        zc[30_000 * 96 + 40] ^= 1
+        zc[45_000 * 96 + 40] ^= 1
+        codes = []
+        for c in (c1, cn):
+            with pytest.raises(kz.PtauError) as e:
+                c.convert(2, ZC, zc, AU, STRICT)
+            codes.append((e.value.index, e.value.code))
+        assert codes[0] == codes[1] and codes[0][0] == 30_000
