@@ -341,6 +341,114 @@ PTAU_HD Fq fq_mul_inl(const Fq& a, const Fq& b) {
   return r;
 }
 
+// ---------------------------------------------------------------------------
+// single-instruction carry-chain steps (device: one PTX instruction each, the
+// carry lives in CC.CF between them; host: explicit flag `px_cf` in scope)
+// ---------------------------------------------------------------------------
+#ifdef __CUDA_ARCH__
+#define PX_DECL
+#define PX_ADD_CC(r, a, b) asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b))
+#define PX_ADDC_CC(r, a, b) asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b))
+#define PX_ADDC(r, a, b) asm volatile("addc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b))
+#define PX_MAD_LO_CC(r, a, b, c) asm volatile("mad.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c))
+#define PX_MADC_LO_CC(r, a, b, c) asm volatile("madc.lo.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c))
+#define PX_MADC_HI_CC(r, a, b, c) asm volatile("madc.hi.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c))
+#define PX_MADC_HI(r, a, b, c) asm volatile("madc.hi.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c))
+#else
+#define PX_DECL uint32_t px_cf = 0; (void)px_cf
+#define PX_ADD_CC(r, a, b) do { px_cf = 0; r = emu::addc(a, b, px_cf); } while (0)
+#define PX_ADDC_CC(r, a, b) r = emu::addc(a, b, px_cf)
+#define PX_ADDC(r, a, b) do { r = emu::addc(a, b, px_cf); px_cf = 0; } while (0)
+#define PX_MAD_LO_CC(r, a, b, c) do { px_cf = 0; r = emu::madlo(a, b, c, px_cf); } while (0)
+#define PX_MADC_LO_CC(r, a, b, c) r = emu::madlo(a, b, c, px_cf)
+#define PX_MADC_HI_CC(r, a, b, c) r = emu::madhi(a, b, c, px_cf)
+#define PX_MADC_HI(r, a, b, c) do { r = emu::madhi(a, b, c, px_cf); px_cf = 0; } while (0)
+#endif
+
+// Montgomery square a*a/R mod p.  Same row structure as fq_mul_inl, but row i only
+// forms the products with limbs j >= i of the multiplicand
+//     c(i) = a_i W^i + 2 * sum_{j>i} a_j W^j        (a^2 = sum_i a_i W^i c(i)),
+// i.e. 78 wide MADs for the product instead of 144; the 12 reduction rows are
+// unchanged.  Limbs of c(i): j == i -> a_i ; j == i+1 -> a_j << 1 ; j > i+1 ->
+// (a_j << 1) | (a_{j-1} >> 31).  a < 2^381 so nothing is shifted out of limb 11.
+PTAU_HD Fq fq_sqr_inl(const Fq& a) {
+  uint32_t ev[12], od[12];
+  uint32_t c2[12], d1[12];
+  c2[0] = a.l[0];
+  d1[0] = a.l[0];
+#pragma unroll
+  for (int j = 1; j < 12; j++) {
+    d1[j] = a.l[j] << 1;
+    c2[j] = (a.l[j] << 1) | (a.l[j - 1] >> 31);
+  }
+#define SQ_M(i, j) ((j) == (i) ? a.l[j] : ((j) == (i) + 1 ? d1[j] : c2[j]))
+  // row 0: all 12 products, plain
+#pragma unroll
+  for (int j = 0; j < 12; j += 2) {
+    uint64_t t0 = (uint64_t)SQ_M(0, j) * a.l[0];
+    uint64_t t1 = (uint64_t)SQ_M(0, j + 1) * a.l[0];
+    ev[j] = (uint32_t)t0;
+    ev[j + 1] = (uint32_t)(t0 >> 32);
+    od[j] = (uint32_t)t1;
+    od[j + 1] = (uint32_t)(t1 >> 32);
+  }
+  {
+    uint32_t m = ev[0] * PTAU_M0;
+    row_red_odd(od, m);
+    row_red_even(ev, od[11], m);
+  }
+#pragma unroll
+  for (int i = 1; i < 12; i++) {
+    uint32_t* E = (i & 1) ? od : ev;  // even-aligned accumulator of this row
+    uint32_t* X = (i & 1) ? ev : od;  // odd-aligned (holds the previous even accumulator, to be shifted)
+    const uint32_t bi = a.l[i];
+    PX_DECL;
+    // shift X down two limbs, absorb the left-over limb into E[0], add the odd-j products (j >= i)
+    PX_ADD_CC(E[0], E[0], X[1]);
+#pragma unroll
+    for (int k = 0; k < 10; k += 2) {
+      if (k + 1 >= i) {
+        PX_MADC_LO_CC(X[k], SQ_M(i, k + 1), bi, X[k + 2]);
+        PX_MADC_HI_CC(X[k + 1], SQ_M(i, k + 1), bi, X[k + 3]);
+      } else {
+        PX_ADDC_CC(X[k], X[k + 2], 0u);
+        PX_ADDC_CC(X[k + 1], X[k + 3], 0u);
+      }
+    }
+    PX_MADC_LO_CC(X[10], SQ_M(i, 11), bi, 0u);
+    PX_MADC_HI(X[11], SQ_M(i, 11), bi, 0u);
+    // even-j products (j >= i); the chain starts at the first such j
+    const int j0 = (i & 1) ? i + 1 : i;
+    if (j0 <= 10) {
+      PX_MAD_LO_CC(E[j0], SQ_M(i, j0), bi, E[j0]);
+      PX_MADC_HI_CC(E[j0 + 1], SQ_M(i, j0), bi, E[j0 + 1]);
+#pragma unroll
+      for (int j = j0 + 2; j < 12; j += 2) {
+        PX_MADC_LO_CC(E[j], SQ_M(i, j), bi, E[j]);
+        PX_MADC_HI_CC(E[j + 1], SQ_M(i, j), bi, E[j + 1]);
+      }
+      PX_ADDC(X[11], X[11], 0u);
+    }
+    uint32_t m = E[0] * PTAU_M0;
+    row_red_odd(X, m);
+    row_red_even(E, X[11], m);
+  }
+#undef SQ_M
+  // last row (i = 11) had E = od, X = ev: result = ev + (od >> 32)
+  {
+    PX_DECL;
+    PX_ADD_CC(ev[0], ev[0], od[1]);
+#pragma unroll
+    for (int k = 1; k < 11; k++) PX_ADDC_CC(ev[k], ev[k], od[k + 1]);
+    PX_ADDC(ev[11], ev[11], 0u);
+  }
+  fq_cond_sub_p(ev);
+  Fq r;
+#pragma unroll
+  for (int i = 0; i < 12; i++) r.l[i] = ev[i];
+  return r;
+}
+
 // a + b mod p
 PTAU_HD Fq fq_add(const Fq& a, const Fq& b) {
   Fq r;

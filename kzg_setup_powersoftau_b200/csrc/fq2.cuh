@@ -13,10 +13,10 @@ namespace ptau {
 
 #ifdef __CUDA_ARCH__
 __device__ __noinline__ Fq fq_mul(Fq a, Fq b) { return fq_mul_inl(a, b); }
-__device__ __noinline__ Fq fq_sqr(Fq a) { return fq_mul_inl(a, a); }
+__device__ __noinline__ Fq fq_sqr(Fq a) { return fq_sqr_inl(a); }
 #else
 inline Fq fq_mul(const Fq& a, const Fq& b) { return fq_mul_inl(a, b); }
-inline Fq fq_sqr(const Fq& a) { return fq_mul_inl(a, a); }
+inline Fq fq_sqr(const Fq& a) { return fq_sqr_inl(a); }
 #endif
 
 struct Fq2 {

@@ -40,7 +40,7 @@ __device__ __forceinline__ void stage_out(uint32_t* __restrict__ g, const uint32
   for (int i = (nvec << 2) + threadIdx.x; i < nwords; i += PTAU_BLOCK) g[i] = sm[i];
 }
 
-template <int G, int INFMT, int OUTFMT>
+template <int G, int INFMT, int OUTFMT, bool HEAVY>
 __global__ void __launch_bounds__(PTAU_BLOCK)
     convert_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint64_t n, uint32_t checks,
                    uint64_t base_index, unsigned long long* __restrict__ status) {
@@ -72,8 +72,8 @@ __global__ void __launch_bounds__(PTAU_BLOCK)
 
   if (tid < nrec) {
     uint32_t wout[WOUT];
-    uint32_t st = (G == PTAU_G1) ? g1_process<INFMT>(win, OUTFMT, wout, checks)
-                                 : g2_process<INFMT>(win, OUTFMT, wout, checks);
+    uint32_t st = (G == PTAU_G1) ? g1_process<INFMT, HEAVY>(win, OUTFMT, wout, checks)
+                                 : g2_process<INFMT, HEAVY>(win, OUTFMT, wout, checks);
     uint2* s2 = reinterpret_cast<uint2*>(sm + tid * WOUT);
 #pragma unroll
     for (int j = 0; j < WOUT / 2; j++) s2[j] = make_uint2(wout[2 * j], wout[2 * j + 1]);
@@ -88,8 +88,17 @@ static cudaError_t launch_one(const void* d_in, void* d_out, uint64_t n, uint32_
                               unsigned long long* d_status, cudaStream_t stream) {
   if (n == 0) return cudaSuccess;
   unsigned grid = (unsigned)((n + PTAU_BLOCK - 1) / PTAU_BLOCK);
-  convert_kernel<G, INFMT, OUTFMT><<<grid, PTAU_BLOCK, 0, stream>>>(
-      (const uint32_t*)d_in, (uint32_t*)d_out, n, checks, base_index, d_status);
+  // no curve checks requested on an uncompressed input: the lightweight instance
+  // (compressed input is on the curve by construction, so only the subgroup bit matters there)
+  const bool light = INFMT == PTAU_FMT_ZCASH_COMPRESSED
+                         ? !(checks & PTAU_CHECK_SUBGROUP)
+                         : !(checks & (PTAU_CHECK_ON_CURVE | PTAU_CHECK_SUBGROUP));
+  if (light)
+    convert_kernel<G, INFMT, OUTFMT, false><<<grid, PTAU_BLOCK, 0, stream>>>(
+        (const uint32_t*)d_in, (uint32_t*)d_out, n, checks, base_index, d_status);
+  else
+    convert_kernel<G, INFMT, OUTFMT, true><<<grid, PTAU_BLOCK, 0, stream>>>(
+        (const uint32_t*)d_in, (uint32_t*)d_out, n, checks, base_index, d_status);
   return cudaGetLastError();
 }
 

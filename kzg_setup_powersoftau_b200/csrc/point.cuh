@@ -146,8 +146,11 @@ PTAU_HD constexpr int record_bytes(int group, int fmt) {
 // =============================================================================
 // G1
 // =============================================================================
-template <int INFMT>
+// HEAVY = false compiles the curve checks out (used when the caller asked for none
+// of them on an uncompressed input): a small-register kernel that runs at HBM speed.
+template <int INFMT, bool HEAVY = true>
 PTAU_HD uint32_t g1_process(const uint32_t* in, int out_fmt, uint32_t* out, uint32_t checks) {
+  if (!HEAVY) checks &= PTAU_CHECK_REJECT_INFINITY;
   Fq xp, yp, xm, ym;
   uint32_t st = PTAU_OK;
   bool inf = false;
@@ -204,11 +207,11 @@ PTAU_HD uint32_t g1_process(const uint32_t* in, int out_fmt, uint32_t* out, uint
       xm = fq_to_mont(xp);
       ym = fq_to_mont(yp);
       have_mont = true;
-      if (need && (checks & PTAU_CHECK_ON_CURVE) && !g1_on_curve(xm, ym)) st = PTAU_BAD_NOT_ON_CURVE;
+      if (HEAVY && need && (checks & PTAU_CHECK_ON_CURVE) && !g1_on_curve(xm, ym)) st = PTAU_BAD_NOT_ON_CURVE;
     }
   }
   if (st == PTAU_OK && inf && (checks & PTAU_CHECK_REJECT_INFINITY)) st = PTAU_BAD_INFINITY;
-  if (st == PTAU_OK && !inf && (checks & PTAU_CHECK_SUBGROUP)) {
+  if (HEAVY && st == PTAU_OK && !inf && (checks & PTAU_CHECK_SUBGROUP)) {
     if (!g1_in_subgroup(xm, ym)) st = PTAU_BAD_NOT_IN_SUBGROUP;
   }
 
@@ -247,8 +250,9 @@ PTAU_HD uint32_t g1_process(const uint32_t* in, int out_fmt, uint32_t* out, uint
 // =============================================================================
 // G2
 // =============================================================================
-template <int INFMT>
+template <int INFMT, bool HEAVY = true>
 PTAU_HD uint32_t g2_process(const uint32_t* in, int out_fmt, uint32_t* out, uint32_t checks) {
+  if (!HEAVY) checks &= PTAU_CHECK_REJECT_INFINITY;
   Fq2 xp, yp, xm, ym;
   uint32_t st = PTAU_OK;
   bool inf = false;
@@ -322,11 +326,11 @@ PTAU_HD uint32_t g2_process(const uint32_t* in, int out_fmt, uint32_t* out, uint
       ym.c0 = fq_to_mont(yp.c0);
       ym.c1 = fq_to_mont(yp.c1);
       have_mont = true;
-      if (need && !g2_on_curve(xm, ym)) st = PTAU_BAD_NOT_ON_CURVE;
+      if (HEAVY && need && !g2_on_curve(xm, ym)) st = PTAU_BAD_NOT_ON_CURVE;
     }
   }
   if (st == PTAU_OK && inf && (checks & PTAU_CHECK_REJECT_INFINITY)) st = PTAU_BAD_INFINITY;
-  if (st == PTAU_OK && !inf && (checks & PTAU_CHECK_SUBGROUP)) {
+  if (HEAVY && st == PTAU_OK && !inf && (checks & PTAU_CHECK_SUBGROUP)) {
     if (!g2_in_subgroup(xm, ym)) st = PTAU_BAD_NOT_IN_SUBGROUP;
   }
 
