@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libptau_b200.so")
+# PTAU_LIB selects an alternative build of the same library (A/B kernel experiments)
+LIB_PATH = os.environ.get("PTAU_LIB") or os.path.join(_HERE, "libptau_b200.so")
 
 # constants mirrored from include/ptau_b200.h (checked by tests/test_abi.py)
 G1, G2 = 1, 2

@@ -26,18 +26,20 @@ struct Jac {
   F X, Y, Z;
 };
 
-// dbl-2009-l  (2M + 5S)
+// dbl-2009-l  (2M + 5S).  Statement order chosen for register liveness: at most
+// four field elements are live across any multiplication.
 template <class F>
 PTAU_HD void jac_dbl(Jac<F>& p) {
-  F A = fsqr(p.X);
   F B = fsqr(p.Y);
+  p.Z = fdbl(fmul(p.Z, p.Y));  // Y is dead from here
   F C = fsqr(B);
-  F D = fsqr(fadd(p.X, B));
+  F t = fadd(p.X, B);          // B dead
+  F A = fsqr(p.X);             // X dead
+  F D = fsqr(t);
   D = fsub(fsub(D, A), C);
   D = fdbl(D);
-  F E = fadd(fdbl(A), A);
+  F E = fadd(fdbl(A), A);      // A dead
   F Fv = fsqr(E);
-  p.Z = fdbl(fmul(p.Z, p.Y));
   p.X = fsub(Fv, fdbl(D));
   C = fdbl(fdbl(fdbl(C)));
   p.Y = fsub(fmul(fsub(D, p.X), E), C);
