@@ -86,6 +86,8 @@ extern "C" {
 #define PTAU_ERR_SIZE (-3)
 #define PTAU_ERR_NOMEM (-4)
 #define PTAU_ERR_IO (-5)
+#define PTAU_ERR_DIGEST (-6) /* BLAKE2b digest of `powersoftau` differs from the expected one */
+#define PTAU_ERR_EXISTS (-7) /* `powersoftau_uncompressed` already exists (create_new)       */
 
 /* kzg_setup variants */
 #define PTAU_VARIANT_KGZ 1     /* preprocess-kgz / load_kzg_setup         */
@@ -183,6 +185,19 @@ int ptau_load_setup(ptau_ctx* ctx, int variant, const void* setup, uint64_t setu
 int ptau_load_phase1(ptau_ctx* ctx, const void* data, uint64_t len, uint64_t m, unsigned checks, void* g1_out,
                      uint64_t g1_out_len, void* g2_out, uint64_t g2_out_len, uint64_t* bad_index,
                      int* bad_kind);
+
+/* ---- file to file (the two binaries' main()) --------------------------------- */
+#define PTAU_FILE_SKIP_DIGEST 1u     /* do not check the BLAKE2b digest of `powersoftau`           */
+#define PTAU_FILE_NO_UNCOMPRESSED 2u /* fused path: do not write `powersoftau_uncompressed`        */
+/* Streams `response_path` through pinned slabs (memory O(slab), not O(N)): size check
+ * (preprocess-kgz.rs:83), BLAKE2b-512 digest check against expected_digest_hex (NULL = the
+ * ceremony digest of preprocess-kgz.rs:19), `uncompressed_path` created with create_new
+ * semantics (:113-118), `setup_path` written in the variant's layout. */
+int ptau_preprocess_files(ptau_ctx* ctx, int variant, const char* response_path, const char* setup_path,
+                          const char* uncompressed_path, unsigned log2_powers, const char* expected_digest_hex,
+                          unsigned flags, unsigned checks, uint64_t* bad_index, int* bad_kind, int* bad_section);
+/* unkeyed BLAKE2b-512 of a file as 128 hex chars + NUL (blake2b_simd, src/lib.rs:128-131) */
+int ptau_blake2b_file(const char* path, char out_hex[129]);
 
 /* ---- microbenchmarks used by bench.py for the IMAD roofline denominator ------ */
 /* Runs `iters` dependent-chain iterations per thread; returns elapsed ms (CUDA

@@ -463,47 +463,40 @@ def load_fastkzg_setup(path: str = KZG_SETUP_FILE, log2_powers: Optional[int] = 
 # ---- the two binaries (src/bin/preprocess-kgz.rs, preprocess-fastkgz.rs) -------------
 def _preprocess_main(variant: int, directory: str, log2_powers: int, expected_digest: Optional[str],
                      emit_uncompressed: bool, checks: int, ctx: Optional[Context]):
-    n = 1 << log2_powers
+    """Both binaries' main(): everything (size check, BLAKE2b digest check, create_new of
+    the intermediate file, streaming through pinned slabs, section table) happens in
+    ptau_preprocess_files (csrc/files.cu); this wrapper only maps return codes onto the
+    reference's panics/messages."""
     L = _ffi.lib()
+    n = 1 << log2_powers
     src_path = os.path.join(directory, POWERSOFTAU_FILE)
     unc_path = os.path.join(directory, POWERSOFTAU_UNCOMPRESSED_FILE)
     out_path = os.path.join(directory, KZG_SETUP_FILE)
-    # download_parameters(): digest check of the existing file (preprocess-kgz.rs:38-47).
-    # expected_digest=None skips it (synthetic inputs); a mismatch would trigger the
-    # network download in the reference, which is impossible offline -> error.
     if not os.path.exists(src_path):
         raise FileNotFoundError("unable open `%s` in this directory" % POWERSOFTAU_FILE)
-    size = os.path.getsize(src_path)
-    want = L.ptau_response_size(n)
-    if size != want:  # preprocess-kgz.rs:83-90
-        raise PtauError(_ffi.ERR_SIZE, detail="The size of `%s` should be %d, but it's %d, so something isn't right."
-                        % (POWERSOFTAU_FILE, want, size))
-    if emit_uncompressed and os.path.exists(unc_path):  # create_new(true), preprocess-kgz.rs:113-118
-        raise FileExistsError("unable to create `%s`" % POWERSOFTAU_UNCOMPRESSED_FILE)
-    resp = PinnedBuffer(size)
-    with open(src_path, "rb") as f:
-        f.readinto(memoryview(resp.array))
-    if expected_digest is not None:
+    flags = 0
+    if expected_digest is None:
+        flags |= _ffi.FILE_SKIP_DIGEST
+    else:
         print("Checking existing %s file..." % POWERSOFTAU_FILE)
-        if not _check_file_hash(resp.array, expected_digest):
-            raise IOError("failed validation (expected: %s, have %d bytes); download impossible offline"
-                          % (expected_digest, size))
-        print("Checking passed, using existing %s file." % POWERSOFTAU_FILE)
+    if not emit_uncompressed:
+        flags |= _ffi.FILE_NO_UNCOMPRESSED
     ctx = ctx or default_context()
-    out = PinnedBuffer(L.ptau_setup_size(variant, n))
-    unc = PinnedBuffer(L.ptau_uncompressed_size(n)) if emit_uncompressed else None
     print("Started deserializing compressed Powers of Tau...")
-    ctx.preprocess(variant, resp, n, checks, out=out, uncompressed_out=unc)
-    if unc is not None:
-        with open(unc_path, "wb") as f:
-            f.write(memoryview(unc.array))
-    print("Serializing KZG parameters...")
-    with open(out_path, "wb") as f:
-        f.write(memoryview(out.array))
+    bad_i, bad_k, bad_s = C.c_uint64(0), C.c_int(0), C.c_int(-1)
+    rc = L.ptau_preprocess_files(ctx._h, variant, src_path.encode(), out_path.encode(), unc_path.encode(), log2_powers,
+                                 expected_digest.encode() if expected_digest else None, flags, checks,
+                                 C.byref(bad_i), C.byref(bad_k), C.byref(bad_s))
+    if rc == _ffi.ERR_SIZE:  # preprocess-kgz.rs:83-90
+        raise PtauError(rc, detail="The size of `%s` should be %d, but it's %d, so something isn't right."
+                        % (POWERSOFTAU_FILE, L.ptau_response_size(n), os.path.getsize(src_path)))
+    if rc == _ffi.ERR_EXISTS:  # create_new(true), preprocess-kgz.rs:113-118
+        raise FileExistsError("unable to create `%s`" % POWERSOFTAU_UNCOMPRESSED_FILE)
+    if rc == _ffi.ERR_DIGEST:
+        raise IOError("failed validation (expected: %s); download impossible offline" % expected_digest)
+    if rc != 0:
+        ctx._raise(rc, bad_i.value if rc > 0 else None, bad_s.value if rc > 0 else None)
     print("Done serializing. KZG parameters are stored in %s" % KZG_SETUP_FILE)
-    for b in (resp, out, unc):
-        if b is not None:
-            b.free()
     return out_path
 
 

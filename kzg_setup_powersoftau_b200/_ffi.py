@@ -23,7 +23,8 @@ CHECKS_DECOMPRESS = 0
 CHECKS_STRICT = CHECK_ON_CURVE | CHECK_SUBGROUP | CHECK_REJECT_INFINITY
 OK = 0
 BAD_NON_CANONICAL, BAD_FLAGS, BAD_INFINITY, BAD_NOT_ON_CURVE, BAD_NOT_IN_SUBGROUP = 1, 2, 3, 4, 5
-ERR_CUDA, ERR_ARG, ERR_SIZE, ERR_NOMEM, ERR_IO = -1, -2, -3, -4, -5
+ERR_CUDA, ERR_ARG, ERR_SIZE, ERR_NOMEM, ERR_IO, ERR_DIGEST, ERR_EXISTS = -1, -2, -3, -4, -5, -6, -7
+FILE_SKIP_DIGEST, FILE_NO_UNCOMPRESSED = 1, 2
 VARIANT_KGZ, VARIANT_FASTKGZ = 1, 2
 STATUS_NONE = 0xFFFFFFFFFFFFFFFF
 
@@ -103,6 +104,12 @@ _SIGNATURES = {
         [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint, C.c_void_p, C.c_uint64, C.c_void_p,
          C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_int)],
     ),
+    "ptau_preprocess_files": (
+        C.c_int,
+        [C.c_void_p, C.c_int, C.c_char_p, C.c_char_p, C.c_char_p, C.c_uint, C.c_char_p, C.c_uint, C.c_uint,
+         C.POINTER(C.c_uint64), C.POINTER(C.c_int), C.POINTER(C.c_int)],
+    ),
+    "ptau_blake2b_file": (C.c_int, [C.c_char_p, C.c_char_p]),
     "ptau_microbench": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 }
 

@@ -198,6 +198,8 @@ const char* ptau_strerror(int code) {
     case PTAU_ERR_SIZE: return "buffer or file size does not match the layout";
     case PTAU_ERR_NOMEM: return "out of memory";
     case PTAU_ERR_IO: return "I/O error";
+    case PTAU_ERR_DIGEST: return "BLAKE2b digest mismatch";
+    case PTAU_ERR_EXISTS: return "output file already exists";
   }
   return "unknown";
 }

@@ -1,0 +1,258 @@
+// File-to-file pipelines of libptau_b200.so: the two reference binaries' main()
+// (/root/reference/src/bin/preprocess-kgz.rs:162-200,
+//  /root/reference/src/bin/preprocess-fastkgz.rs:180-214) as one streaming pass.
+//
+// The reference holds every section in RAM as Vec<GroupAffine> (O(N) memory, and
+// download_parameters even slurps the whole file to hash it, preprocess-kgz.rs:41-42).
+// Here the `powersoftau` file is streamed slab by slab through pinned host buffers:
+// a reader thread prefetches slab k+1, the GPUs convert slab k (ptau_convert shards it
+// by index range), a writer thread flushes slab k-1.  Memory is O(slab).
+#include <errno.h>
+#include <fcntl.h>
+#include <stdio.h>
+#include <string.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <future>
+#include <string>
+#include <vector>
+
+#include "../../include/ptau_b200.h"
+#include "blake2b.h"
+
+namespace {
+
+const char* kPowersoftauDigest =  // preprocess-kgz.rs:19
+    "88dc1dc6914e44568e8511eace177e6ecd9da9a9bd8f67e4c0c9f215b517db4d1d54a755d051978dbb85ef947918193c"
+    "93cd4cf4c99c0dc5a767d4eeb10047a4";
+
+bool pread_all(int fd, void* buf, size_t len, uint64_t off) {
+  uint8_t* p = (uint8_t*)buf;
+  while (len) {
+    ssize_t r = pread(fd, p, len, (off_t)off);
+    if (r <= 0) {
+      if (r < 0 && errno == EINTR) continue;
+      return false;
+    }
+    p += r;
+    off += (uint64_t)r;
+    len -= (size_t)r;
+  }
+  return true;
+}
+bool pwrite_all(int fd, const void* buf, size_t len, uint64_t off) {
+  const uint8_t* p = (const uint8_t*)buf;
+  while (len) {
+    ssize_t r = pwrite(fd, p, len, (off_t)off);
+    if (r <= 0) {
+      if (r < 0 && errno == EINTR) continue;
+      return false;
+    }
+    p += r;
+    off += (uint64_t)r;
+    len -= (size_t)r;
+  }
+  return true;
+}
+
+struct Pinned {
+  void* p = nullptr;
+  explicit Pinned(size_t n) { p = ptau_host_alloc(n); }
+  ~Pinned() { ptau_host_free(p); }
+  uint8_t* u8() { return (uint8_t*)p; }
+};
+
+}  // namespace
+
+extern "C" {
+
+int ptau_blake2b_file(const char* path, char out_hex[129]) {
+  int fd = open(path, O_RDONLY);
+  if (fd < 0) return PTAU_ERR_IO;
+  ptau::Blake2b h;
+  std::vector<uint8_t> buf(8 << 20);
+  for (;;) {
+    ssize_t r = read(fd, buf.data(), buf.size());
+    if (r < 0) {
+      if (errno == EINTR) continue;
+      close(fd);
+      return PTAU_ERR_IO;
+    }
+    if (r == 0) break;
+    h.update(buf.data(), (size_t)r);
+  }
+  close(fd);
+  std::string s = h.hexdigest();
+  memcpy(out_hex, s.c_str(), 129);
+  return PTAU_OK;
+}
+
+int ptau_preprocess_files(ptau_ctx* ctx, int variant, const char* response_path, const char* setup_path,
+                          const char* uncompressed_path, unsigned log2_powers, const char* expected_digest_hex,
+                          unsigned flags, unsigned checks, uint64_t* bad_index, int* bad_kind, int* bad_section) {
+  if (!ctx || !response_path || !setup_path || log2_powers < 1 || log2_powers > 30) return PTAU_ERR_ARG;
+  if (variant != PTAU_VARIANT_KGZ && variant != PTAU_VARIANT_FASTKGZ) return PTAU_ERR_ARG;
+  const uint64_t n = 1ull << log2_powers;
+  const bool fast = variant == PTAU_VARIANT_FASTKGZ;
+  const bool emit_unc = uncompressed_path && !(flags & PTAU_FILE_NO_UNCOMPRESSED);
+
+  int fd_in = open(response_path, O_RDONLY);
+  if (fd_in < 0) return PTAU_ERR_IO;
+  struct stat st;
+  if (fstat(fd_in, &st) != 0) {
+    close(fd_in);
+    return PTAU_ERR_IO;
+  }
+  // preprocess-kgz.rs:83: size must equal CONTRIBUTION_BYTE_SIZE
+  if ((uint64_t)st.st_size != ptau_response_size(n)) {
+    close(fd_in);
+    return PTAU_ERR_SIZE;
+  }
+  // download_parameters (preprocess-kgz.rs:38-47): digest of the existing file.  A
+  // mismatch sends the reference to the network; offline that is an error.
+  if (!(flags & PTAU_FILE_SKIP_DIGEST)) {
+    char hex[129];
+    int rc = ptau_blake2b_file(response_path, hex);
+    if (rc) {
+      close(fd_in);
+      return rc;
+    }
+    if (strcmp(hex, expected_digest_hex ? expected_digest_hex : kPowersoftauDigest) != 0) {
+      close(fd_in);
+      return PTAU_ERR_DIGEST;
+    }
+  }
+  int fd_unc = -1;
+  if (emit_unc) {
+    // create_new(true): an existing file is an error (preprocess-kgz.rs:113-118)
+    fd_unc = open(uncompressed_path, O_WRONLY | O_CREAT | O_EXCL, 0644);
+    if (fd_unc < 0) {
+      close(fd_in);
+      return errno == EEXIST ? PTAU_ERR_EXISTS : PTAU_ERR_IO;
+    }
+  }
+  int fd_out = open(setup_path, O_WRONLY | O_CREAT | O_TRUNC, 0644);
+  if (fd_out < 0) {
+    close(fd_in);
+    if (fd_unc >= 0) close(fd_unc);
+    return PTAU_ERR_IO;
+  }
+
+  struct Sec {
+    int group;
+    uint64_t count;
+    int64_t out_off;  // offset of the section's ark output in `kzg_setup`, -1 = checked but not written
+    bool process;
+  };
+  const uint64_t g1_all = (2 * n - 1) * 96 + n * 96;
+  const Sec secs[5] = {
+      {PTAU_G1, 2 * n - 1, 0, true},                                             // tau_g1 -> powers_of_g
+      {PTAU_G2, n, fast ? (int64_t)(g1_all + 384) : -1, true},                   // tau_g2 -> powers_of_h (fast)
+      {PTAU_G1, n, (int64_t)((2 * n - 1) * 96), true},                           // alpha_g1 -> powers_of_gamma_g
+      {PTAU_G1, n, -1, fast || emit_unc},  // beta_g1: fastkgz reads+checks+drops it (:156-159); kgz never reads it
+      {PTAU_G2, 1, -1, emit_unc},          // beta_g2: only ever decompressed into `powersoftau_uncompressed`
+  };
+  const size_t slab = (size_t)((2 * n) < (1u << 20) ? (2 * n) : (1u << 20));  // points per slab
+  Pinned in0(slab * 96), in1(slab * 96), unc0(slab * 192), unc1(slab * 192), out0(slab * 192), out1(slab * 192);
+  if (!in0.p || !in1.p || !unc0.p || !unc1.p || !out0.p || !out1.p) {
+    close(fd_in);
+    close(fd_out);
+    if (fd_unc >= 0) close(fd_unc);
+    return PTAU_ERR_NOMEM;
+  }
+  uint8_t* inb[2] = {in0.u8(), in1.u8()};
+  uint8_t* uncb[2] = {unc0.u8(), unc1.u8()};
+  uint8_t* outb[2] = {out0.u8(), out1.u8()};
+  uint8_t first_g1[96], first_alpha[96], first_g2[384];
+  memset(first_g2, 0, sizeof(first_g2));
+
+  int rc = PTAU_OK;
+  uint64_t in_off = 64;  // skip the 64-byte challenge hash (:96-101)
+  uint64_t unc_off = 0;
+  std::future<bool> wr[2], wu[2];
+  for (int s = 0; s < 5 && rc == PTAU_OK; s++) {
+    const Sec& sec = secs[s];
+    const size_t rc_in = ptau_record_size(sec.group, PTAU_FMT_ZCASH_COMPRESSED);
+    const size_t r_unc = ptau_record_size(sec.group, PTAU_FMT_ZCASH_UNCOMPRESSED);
+    const size_t r_out = ptau_record_size(sec.group, PTAU_FMT_ARK_UNCOMPRESSED);
+    const bool only_decompress = (s == 3 && !fast) || s == 4;  // sections the binaries never validate
+    if (sec.process) {
+      const uint64_t nslab = (sec.count + slab - 1) / slab;
+      std::future<bool> rd = std::async(std::launch::async, pread_all, fd_in, inb[0],
+                                        (size_t)((sec.count < slab ? sec.count : slab) * rc_in), in_off);
+      for (uint64_t k = 0; k < nslab && rc == PTAU_OK; k++) {
+        const int b = (int)(k & 1);
+        const uint64_t lo = k * slab;
+        const size_t cnt = (size_t)(sec.count - lo < slab ? sec.count - lo : slab);
+        if (!rd.get()) rc = PTAU_ERR_IO;
+        if (k + 1 < nslab) {
+          const uint64_t lo2 = (k + 1) * slab;
+          const size_t cnt2 = (size_t)(sec.count - lo2 < slab ? sec.count - lo2 : slab);
+          rd = std::async(std::launch::async, pread_all, fd_in, inb[b ^ 1], cnt2 * rc_in, in_off + lo2 * rc_in);
+        }
+        if (wr[b].valid() && !wr[b].get()) rc = PTAU_ERR_IO;  // buffer b is free again
+        if (wu[b].valid() && !wu[b].get()) rc = PTAU_ERR_IO;
+        if (rc != PTAU_OK) break;
+        uint64_t bi = 0;
+        int bk = 0;
+        if (emit_unc) {
+          // stage 1: decompress (CheckForCorrectness::No) -> `powersoftau_uncompressed`
+          rc = ptau_convert(ctx, sec.group, PTAU_FMT_ZCASH_COMPRESSED, inb[b], PTAU_FMT_ZCASH_UNCOMPRESSED, uncb[b], cnt,
+                            PTAU_CHECKS_DECOMPRESS, &bi, &bk);
+          if (rc == PTAU_OK)
+            wu[b] = std::async(std::launch::async, pwrite_all, fd_unc, (const void*)uncb[b], cnt * r_unc,
+                               unc_off + lo * r_unc);
+          // stage 2: read_g1 / read_g2 on the uncompressed bytes
+          if (rc == PTAU_OK && !only_decompress)
+            rc = ptau_convert(ctx, sec.group, PTAU_FMT_ZCASH_UNCOMPRESSED, uncb[b], PTAU_FMT_ARK_UNCOMPRESSED, outb[b], cnt,
+                              checks, &bi, &bk);
+        } else if (!only_decompress) {
+          rc = ptau_convert(ctx, sec.group, PTAU_FMT_ZCASH_COMPRESSED, inb[b], PTAU_FMT_ARK_UNCOMPRESSED, outb[b], cnt, checks,
+                            &bi, &bk);
+        }
+        if (rc > 0) {
+          if (bad_index) *bad_index = lo + bi;
+          if (bad_kind) *bad_kind = bk;
+          if (bad_section) *bad_section = s;
+          break;
+        }
+        if (rc != PTAU_OK) break;
+        if (!only_decompress) {
+          if (k == 0) {
+            if (s == 0) memcpy(first_g1, outb[b], 96);
+            if (s == 2) memcpy(first_alpha, outb[b], 96);
+            if (s == 1) memcpy(first_g2, outb[b], 384);  // n >= 2
+          }
+          if (sec.out_off >= 0)
+            wr[b] = std::async(std::launch::async, pwrite_all, fd_out, (const void*)outb[b], cnt * r_out,
+                               (uint64_t)sec.out_off + lo * r_out);
+        }
+      }
+      if (rd.valid()) rd.wait();
+    }
+    in_off += sec.count * rc_in;
+    unc_off += sec.count * r_unc;
+  }
+  for (int b = 0; b < 2; b++) {
+    if (wr[b].valid() && !wr[b].get() && rc == PTAU_OK) rc = PTAU_ERR_IO;
+    if (wu[b].valid() && !wu[b].get() && rc == PTAU_OK) rc = PTAU_ERR_IO;
+  }
+  if (rc == PTAU_OK) {
+    if (!fast) {  // VerifierKey tail: g, gamma_g, h, beta_h (preprocess-kgz.rs:177-194)
+      uint8_t tail[576];
+      memcpy(tail, first_g1, 96);
+      memcpy(tail + 96, first_alpha, 96);
+      memcpy(tail + 192, first_g2, 384);
+      if (!pwrite_all(fd_out, tail, sizeof(tail), g1_all)) rc = PTAU_ERR_IO;
+    } else {  // h, beta_h in front of powers_of_h (preprocess-fastkgz.rs:199-208)
+      if (!pwrite_all(fd_out, first_g2, 384, g1_all)) rc = PTAU_ERR_IO;
+    }
+  }
+  close(fd_in);
+  if (fd_unc >= 0) close(fd_unc);
+  if (close(fd_out) != 0 && rc == PTAU_OK) rc = PTAU_ERR_IO;
+  return rc;
+}
+
+}  // extern "C"

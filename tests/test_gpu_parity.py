@@ -101,6 +101,71 @@ def test_binaries_file_behaviour(ctx, tmp_path):
         kz.preprocess_kgz(str(tmp_path), log2_powers=3, ctx=ctx)  # real ceremony digest cannot match
 
 
+def test_cli_binaries(tmp_path):
+    """The compiled drop-in binaries (csrc/cli_main.cpp): same files in, same files out."""
+    import subprocess
+
+    from conftest import ROOT
+
+    bindir = os.path.join(ROOT, "kzg_setup_powersoftau_b200", "bin")
+    (tmp_path / "powersoftau").write_bytes(golden("n8_powersoftau.bin"))
+    dg = o.blake2b_hex(golden("n8_powersoftau.bin"))
+    r = subprocess.run([os.path.join(bindir, "preprocess-kgz"), "--dir", str(tmp_path), "--log2-powers", "3",
+                        "--expect-digest", dg], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "Done serializing. KZG parameters are stored in kzg_setup" in r.stdout
+    assert (tmp_path / "kzg_setup").read_bytes() == golden("n8_kzg_setup_kgz.bin")
+    assert (tmp_path / "powersoftau_uncompressed").read_bytes() == golden("n8_powersoftau_uncompressed.bin")
+    # second run: the intermediate file exists -> the reference panics (create_new)
+    r = subprocess.run([os.path.join(bindir, "preprocess-fastkgz"), "--dir", str(tmp_path), "--log2-powers", "3",
+                        "--skip-digest"], capture_output=True, text=True)
+    assert r.returncode != 0 and "unable to create `powersoftau_uncompressed`" in r.stderr
+    r = subprocess.run([os.path.join(bindir, "preprocess-fastkgz"), "--dir", str(tmp_path), "--log2-powers", "3",
+                        "--skip-digest", "--no-uncompressed"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert (tmp_path / "kzg_setup").read_bytes() == golden("n8_kzg_setup_fastkgz.bin")
+    # default digest = the real ceremony file's: a synthetic file fails validation
+    r = subprocess.run([os.path.join(bindir, "preprocess-kgz"), "--dir", str(tmp_path), "--log2-powers", "3",
+                        "--no-uncompressed"], capture_output=True, text=True)
+    assert r.returncode != 0 and "failed validation" in r.stderr
+    # wrong size (preprocess-kgz.rs:83)
+    r = subprocess.run([os.path.join(bindir, "preprocess-kgz"), "--dir", str(tmp_path), "--log2-powers", "4",
+                        "--skip-digest", "--no-uncompressed"], capture_output=True, text=True)
+    assert r.returncode != 0 and "something isn't right" in r.stderr
+    # a corrupted point: reported with section and index, non-zero exit (the reference panics)
+    bad = bytearray(golden("n8_powersoftau.bin"))
+    bad[64 + 15 * 48 + 8 * 96 + 2 * 48 + 20] ^= 0x55  # alpha_tau_powers_g1[2]
+    (tmp_path / "powersoftau").write_bytes(bytes(bad))
+    r = subprocess.run([os.path.join(bindir, "preprocess-kgz"), "--dir", str(tmp_path), "--log2-powers", "3",
+                        "--skip-digest", "--no-uncompressed"], capture_output=True, text=True)
+    assert r.returncode != 0 and "point 2 of alpha_tau_powers_g1" in r.stderr
+
+
+def test_file_pipeline_2pow14_multi_slab(ctx, tmp_path):
+    """2^14-power response through the file pipeline (tau_g1 spans several chunks) against
+    the memory-to-memory pipeline, both variants, and the C++ BLAKE2b against hashlib."""
+    import ctypes
+
+    n = 1 << 14
+    tau, alpha, beta = o.derive_scalars(0xB201)
+    ZCf = kz.FMT_ZCASH_COMPRESSED
+    body = np.concatenate([ctx.generate(1, ZCf, 1, tau, 0, 2 * n - 1), ctx.generate(2, ZCf, 1, tau, 0, n),
+                           ctx.generate(1, ZCf, alpha, tau, 0, n), ctx.generate(1, ZCf, beta, tau, 0, n),
+                           ctx.generate(2, ZCf, beta, tau, 0, 1)])
+    resp = o.filler_bytes(2, 64, b"hash") + body.tobytes() + o.filler_bytes(2, o.PUBKEY_SIZE, b"pubkey")
+    (tmp_path / "powersoftau").write_bytes(resp)
+    hexbuf = ctypes.create_string_buffer(129)
+    assert kz._ffi.lib().ptau_blake2b_file(str(tmp_path / "powersoftau").encode(), hexbuf) == 0
+    assert hexbuf.value.decode() == o.blake2b_hex(resp)
+    want_kgz, want_unc = ctx.preprocess(kz.VARIANT_KGZ, resp, n, emit_uncompressed=True)
+    kz.preprocess_kgz(str(tmp_path), log2_powers=14, expected_digest=o.blake2b_hex(resp), ctx=ctx)
+    assert (tmp_path / "kzg_setup").read_bytes() == want_kgz.tobytes()
+    assert (tmp_path / "powersoftau_uncompressed").read_bytes() == want_unc.tobytes()
+    kz.preprocess_fastkgz(str(tmp_path), log2_powers=14, expected_digest=None, emit_uncompressed=False, ctx=ctx)
+    assert (tmp_path / "kzg_setup").read_bytes() == ctx.preprocess(kz.VARIANT_FASTKGZ, resp, n).tobytes()
+    powers, vk = kz.load_kzg_setup  # noqa: F841 (API presence)
+
+
 def test_phase1_and_read_g(ctx, tmp_path):
     m = 4
     data = golden("n8_phase1radix2m2.bin")
