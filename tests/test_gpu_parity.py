@@ -163,7 +163,8 @@ def test_file_pipeline_2pow14_multi_slab(ctx, tmp_path):
     assert (tmp_path / "powersoftau_uncompressed").read_bytes() == want_unc.tobytes()
     kz.preprocess_fastkgz(str(tmp_path), log2_powers=14, expected_digest=None, emit_uncompressed=False, ctx=ctx)
     assert (tmp_path / "kzg_setup").read_bytes() == ctx.preprocess(kz.VARIANT_FASTKGZ, resp, n).tobytes()
-    powers, vk = kz.load_kzg_setup  # noqa: F841 (API presence)
+    params, ph = kz.load_fastkzg_setup(str(tmp_path / "kzg_setup"), ctx=ctx)  # n inferred from the size
+    assert params.powers_of_g.shape == (2 * n - 1, 104) and ph.shape == (n, 200)
 
 
 def test_phase1_and_read_g(ctx, tmp_path):
