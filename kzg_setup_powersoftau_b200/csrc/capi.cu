@@ -33,6 +33,7 @@ struct GpuSlot {
   unsigned long long* d_status = nullptr;
   cudaEvent_t ev_first = nullptr, ev_last = nullptr;
   cudaEvent_t ev_k0[kBufs] = {nullptr, nullptr}, ev_k1[kBufs] = {nullptr, nullptr};
+  uint32_t* d_tbl[2] = {nullptr, nullptr};  // fixed-base tables of the generator (G1, G2), built lazily
 };
 
 }  // namespace
@@ -255,6 +256,8 @@ void ptau_destroy(ptau_ctx* ctx) {
       if (s.stream[b]) cudaStreamDestroy(s.stream[b]);
     }
     if (s.d_status) cudaFree(s.d_status);
+    for (int t = 0; t < 2; t++)
+      if (s.d_tbl[t]) cudaFree(s.d_tbl[t]);
     if (s.ev_first) cudaEventDestroy(s.ev_first);
     if (s.ev_last) cudaEventDestroy(s.ev_last);
   }
@@ -413,50 +416,77 @@ int ptau_convert(ptau_ctx* ctx, int group, int in_fmt, const void* in, int out_f
 }
 
 // ---- generator -------------------------------------------------------------------
+// fixed-base table T[w][d-1] = [d * 256^w]G (w < 32, d = 1..255) in ARK_MONT_LIMBS records,
+// built once per (context, GPU, group) with the v1 double-and-add kernel
+static int ensure_gen_table(ptau_ctx* ctx, GpuSlot& s, int group, cudaStream_t stream) {
+  const int gi = group == PTAU_G1 ? 0 : 1;
+  if (s.d_tbl[gi]) return PTAU_OK;
+  const size_t cnt = 32 * 255;
+  const int r_zu = rec_size(group, PTAU_FMT_ZCASH_UNCOMPRESSED), r_ml = rec_size(group, PTAU_FMT_ARK_MONT_LIMBS);
+  std::vector<uint32_t> sc(cnt * 8, 0);
+  for (int w = 0; w < 32; w++)
+    for (int d = 1; d <= 255; d++) {
+      uint32_t* k = &sc[(size_t)(w * 255 + d - 1) * 8];
+      if (w == 31 && d > 0x73) {
+        k[0] = 1;  // digits the top window never takes (k < r < 0x74 * 256^31): any valid scalar
+        continue;
+      }
+      k[w >> 2] = (uint32_t)d << ((w & 3) * 8);
+    }
+  uint32_t* d_sc = nullptr;
+  uint8_t* d_zu = nullptr;
+  unsigned long long* d_st = nullptr;
+  CUDA_TRY(ctx, cudaMalloc((void**)&d_sc, cnt * 32));
+  CUDA_TRY(ctx, cudaMalloc((void**)&d_zu, cnt * r_zu));
+  CUDA_TRY(ctx, cudaMalloc((void**)&d_st, 8));
+  CUDA_TRY(ctx, cudaMalloc((void**)&s.d_tbl[gi], cnt * r_ml));
+  const unsigned long long none = PTAU_STATUS_NONE;
+  cudaError_t e = cudaMemcpyAsync(d_sc, sc.data(), cnt * 32, cudaMemcpyHostToDevice, stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_st, &none, 8, cudaMemcpyHostToDevice, stream);
+  if (e == cudaSuccess) e = ptau::launch_generate(group, PTAU_FMT_ZCASH_UNCOMPRESSED, d_sc, d_zu, cnt, stream);
+  if (e == cudaSuccess)
+    e = ptau::launch_convert(group, PTAU_FMT_ZCASH_UNCOMPRESSED, PTAU_FMT_ARK_MONT_LIMBS, d_zu, s.d_tbl[gi], cnt, 0, 0, d_st,
+                             stream);
+  unsigned long long st = 0;
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&st, d_st, 8, cudaMemcpyDeviceToHost, stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+  cudaFree(d_sc);
+  cudaFree(d_zu);
+  cudaFree(d_st);
+  if (e != cudaSuccess || st != PTAU_STATUS_NONE) {
+    cudaFree(s.d_tbl[gi]);
+    s.d_tbl[gi] = nullptr;
+    ctx->last_error = std::string("generator table: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "bad table point");
+    return PTAU_ERR_CUDA;
+  }
+  return PTAU_OK;
+}
+
 int ptau_generate_device(ptau_ctx* ctx, int gpu, int group, int fmt, const uint8_t scalar0[32], const uint8_t step[32],
                          uint64_t first, size_t n_points, void* d_out, void* stream) {
   if (!ctx || gpu < 0 || gpu >= ctx->n_gpus || !scalar0 || !step) return PTAU_ERR_ARG;
   if (fmt != PTAU_FMT_ZCASH_COMPRESSED && fmt != PTAU_FMT_ZCASH_UNCOMPRESSED) return PTAU_ERR_ARG;
   if (!rec_size(group, fmt)) return PTAU_ERR_ARG;
   if (n_points == 0) return PTAU_OK;
-  Fr one_m = fr_to_mont(Fr{{1, 0, 0, 0}});
   Fr s0 = fr_from_le32(scalar0), st = fr_from_le32(step);
   if (fr_ge_mod(s0.l) || fr_ge_mod(st.l)) return PTAU_ERR_ARG;
-  Fr step_m = fr_to_mont(st);
-  Fr cur = fr_mont_mul(fr_to_mont(s0), fr_pow_mont(step_m, first, one_m));
-  CUDA_TRY(ctx, cudaSetDevice(ctx->gpu[gpu].device));
-  // scalars are produced on the host in slabs and shipped as plain LE limbs
-  const size_t slab = (size_t)1 << 20;
-  uint32_t* h_sc = nullptr;
-  uint32_t* d_sc = nullptr;
-  size_t cap = n_points < slab ? n_points : slab;
-  CUDA_TRY(ctx, cudaHostAlloc((void**)&h_sc, cap * 32, cudaHostAllocDefault));
-  if (cudaMalloc((void**)&d_sc, cap * 32) != cudaSuccess) {
-    cudaFreeHost(h_sc);
-    ctx->last_error = "cudaMalloc(scalars)";
-    return PTAU_ERR_CUDA;
+  if ((s0.l[0] | s0.l[1] | s0.l[2] | s0.l[3]) == 0 || (st.l[0] | st.l[1] | st.l[2] | st.l[3]) == 0) return PTAU_ERR_ARG;
+  GpuSlot& slot = ctx->gpu[gpu];
+  CUDA_TRY(ctx, cudaSetDevice(slot.device));
+  int rc = ensure_gen_table(ctx, slot, group, (cudaStream_t)stream);
+  if (rc) return rc;
+  // host side of the scalars: s0 and step^(2^j) in Montgomery form; the per-point
+  // powers are formed on the device
+  Fr s0m = fr_to_mont(s0);
+  uint32_t pw[64][8];
+  Fr p = fr_to_mont(st);
+  for (int j = 0; j < 64; j++) {
+    memcpy(pw[j], p.l, 32);
+    p = fr_mont_mul(p, p);
   }
-  const int ro = rec_size(group, fmt);
-  int rc = PTAU_OK;
-  for (size_t off = 0; off < n_points && rc == PTAU_OK; off += slab) {
-    size_t n = n_points - off < slab ? n_points - off : slab;
-    for (size_t i = 0; i < n; i++) {
-      Fr plain = fr_from_mont(cur);
-      memcpy(h_sc + i * 8, plain.l, 32);
-      cur = fr_mont_mul(cur, step_m);
-    }
-    cudaError_t e = cudaMemcpyAsync(d_sc, h_sc, n * 32, cudaMemcpyHostToDevice, (cudaStream_t)stream);
-    if (e == cudaSuccess)
-      e = ptau::launch_generate(group, fmt, d_sc, (uint8_t*)d_out + off * ro, n, (cudaStream_t)stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);  // h_sc / d_sc are reused
-    if (e != cudaSuccess) {
-      ctx->last_error = std::string("generate: ") + cudaGetErrorString(e);
-      rc = PTAU_ERR_CUDA;
-    }
-  }
-  cudaFree(d_sc);
-  cudaFreeHost(h_sc);
-  return rc;
+  CUDA_TRY(ctx, ptau::launch_generate_win(group, fmt, (const uint32_t*)s0m.l, pw, slot.d_tbl[group == PTAU_G1 ? 0 : 1], d_out,
+                                          first, n_points, (cudaStream_t)stream));
+  return PTAU_OK;
 }
 
 int ptau_generate(ptau_ctx* ctx, int group, int fmt, const uint8_t scalar0[32], const uint8_t step[32], uint64_t first,

@@ -8,6 +8,9 @@
 // integer multiply-add work on the FMA pipe (IMAD.WIDE chains, see fq.cuh).
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
+
+#include <type_traits>
 
 #include "kernels.h"
 #include "point.cuh"
@@ -274,6 +277,255 @@ cudaError_t launch_generate(int group, int fmt, const uint32_t* d_scalars, void*
     generate_kernel<PTAU_G2, PTAU_FMT_ZCASH_COMPRESSED><<<grid, PTAU_BLOCK, 0, stream>>>(d_scalars, (uint32_t*)d_out, n);
   else if (group == PTAU_G2 && fmt == PTAU_FMT_ZCASH_UNCOMPRESSED)
     generate_kernel<PTAU_G2, PTAU_FMT_ZCASH_UNCOMPRESSED><<<grid, PTAU_BLOCK, 0, stream>>>(d_scalars, (uint32_t*)d_out, n);
+  else
+    return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}
+
+// =============================================================================
+// generator v2: fixed-base windowed multiplication, scalars formed
+// on the device, batch inversion to affine.
+//
+//   k_i = scalar0 * step^(first+i) mod r        (8 x u32 Montgomery arithmetic in Fr)
+//   [k_i]G = sum_w T[w][digit_w(k_i)]           (32 windows of 8 bits, 31 mixed additions)
+//   to affine: one field inversion per PTAU_GEN_B points of a thread (Montgomery's
+//   trick: B-1 prefix products, one Fermat inversion, 2(B-1) back-multiplications).
+//
+// T[w][d-1] = [d * 256^w]G as PTAU_FMT_ARK_MONT_LIMBS records, built once per context
+// with the v1 kernel.  No exceptional cases: the partial sums are < 256^w <= d*256^w and
+// k < r, so an addition never meets equal or opposite points.
+// =============================================================================
+#define PTAU_GEN_B 8
+
+struct FrParams {
+  uint32_t s0[8];         // scalar0, Montgomery form
+  uint32_t pw[64][8];     // step^(2^j), Montgomery form
+};
+
+__constant__ uint32_t K_FR_MOD[8] = {0x00000001u, 0xffffffffu, 0xfffe5bfeu, 0x53bda402u,
+                                     0x09a1d805u, 0x3339d808u, 0x299d7d48u, 0x73eda753u};
+#define PTAU_FR_M0 0xffffffffu  // -r^-1 mod 2^32
+
+// Montgomery product in Fr (R = 2^256), plain 64-bit arithmetic: a few dozen calls per point
+static __device__ __noinline__ void fr_mul(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+  uint32_t t[10];
+#pragma unroll
+  for (int i = 0; i < 10; i++) t[i] = 0;
+#pragma unroll 1
+  for (int i = 0; i < 8; i++) {
+    uint64_t c = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      c += (uint64_t)a[j] * b[i] + t[j];
+      t[j] = (uint32_t)c;
+      c >>= 32;
+    }
+    c += t[8];
+    t[8] = (uint32_t)c;
+    t[9] = (uint32_t)(c >> 32);
+    uint32_t m = t[0] * PTAU_FR_M0;
+    c = (uint64_t)m * K_FR_MOD[0] + t[0];
+    c >>= 32;
+#pragma unroll
+    for (int j = 1; j < 8; j++) {
+      c += (uint64_t)m * K_FR_MOD[j] + t[j];
+      t[j - 1] = (uint32_t)c;
+      c >>= 32;
+    }
+    c += t[8];
+    t[7] = (uint32_t)c;
+    t[8] = t[9] + (uint32_t)(c >> 32);
+  }
+  // conditional subtraction
+  uint32_t d[8];
+  uint32_t bw = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    uint64_t x = (uint64_t)t[i] - K_FR_MOD[i] - bw;
+    d[i] = (uint32_t)x;
+    bw = (uint32_t)(x >> 63);
+  }
+  bool ge = t[8] != 0 || bw == 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r[i] = ge ? d[i] : t[i];
+}
+
+template <class F>
+struct FieldInv;
+template <>
+struct FieldInv<Fq> {
+  static __device__ __forceinline__ Fq inv(const Fq& a) { return fq_inv(a); }
+};
+template <>
+struct FieldInv<Fq2> {
+  static __device__ __forceinline__ Fq2 inv(const Fq2& a) {
+    Fq ni = fq_inv(fq_add(fq_sqr(a.c0), fq_sqr(a.c1)));
+    Fq2 r;
+    r.c0 = fq_mul(a.c0, ni);
+    r.c1 = fq_neg(fq_mul(a.c1, ni));
+    return r;
+  }
+};
+
+template <class F>
+__device__ __forceinline__ F load_tbl_field(const uint32_t* p);
+template <>
+__device__ __forceinline__ Fq load_tbl_field<Fq>(const uint32_t* p) {
+  Fq r;
+  const uint2* q = reinterpret_cast<const uint2*>(p);
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+    uint2 v = __ldg(q + i);
+    r.l[2 * i] = v.x;
+    r.l[2 * i + 1] = v.y;
+  }
+  return r;
+}
+template <>
+__device__ __forceinline__ Fq2 load_tbl_field<Fq2>(const uint32_t* p) {
+  Fq2 r;
+  r.c0 = load_tbl_field<Fq>(p);
+  r.c1 = load_tbl_field<Fq>(p + 12);
+  return r;
+}
+
+template <class F>
+__device__ __forceinline__ F field_one();
+template <>
+__device__ __forceinline__ Fq field_one<Fq>() { return fq_one(); }
+template <>
+__device__ __forceinline__ Fq2 field_one<Fq2>() { return fq2_one(); }
+
+template <int G, int OUTFMT>
+__global__ void __launch_bounds__(PTAU_BLOCK)
+    generate_win_kernel(FrParams fp, const uint32_t* __restrict__ tbl, uint32_t* __restrict__ out, uint64_t first,
+                        uint64_t n) {
+  using F = typename std::conditional<G == PTAU_G1, Fq, Fq2>::type;
+  constexpr int WOUT = record_bytes(G, OUTFMT) / 4;
+  constexpr int WTBL = record_bytes(G, PTAU_FMT_ARK_MONT_LIMBS) / 4;
+  constexpr int WF = sizeof(F) / 4;
+  __shared__ __align__(16) uint32_t sm[PTAU_BLOCK * WOUT];
+  const int tid = threadIdx.x;
+  // the block owns PTAU_BLOCK * B consecutive points; thread t owns t + j * PTAU_BLOCK
+  const uint64_t blk0 = (uint64_t)blockIdx.x * (PTAU_BLOCK * PTAU_GEN_B);
+
+  // ---- scalar of this thread's first point: s0 * step^(first + blk0 + tid) ----
+  uint32_t cur[8];
+  {
+#pragma unroll
+    for (int i = 0; i < 8; i++) cur[i] = fp.s0[i];
+    uint64_t e = first + blk0 + tid;
+#pragma unroll 1
+    for (int j = 0; j < 64; j++)
+      if ((e >> j) & 1ull) fr_mul(cur, cur, fp.pw[j]);
+  }
+
+  Jac<F> pts[PTAU_GEN_B];
+  F pre[PTAU_GEN_B];
+#pragma unroll 1
+  for (int j = 0; j < PTAU_GEN_B; j++) {
+    const uint64_t idx = blk0 + (uint64_t)j * PTAU_BLOCK + tid;
+    Jac<F> acc;
+    acc.X = field_one<F>();
+    acc.Y = field_one<F>();
+    acc.Z = field_one<F>();
+    if (idx < n) {
+      uint32_t k[8];
+      {
+        uint32_t one[8] = {1, 0, 0, 0, 0, 0, 0, 0};
+        fr_mul(k, cur, one);  // out of Montgomery form
+      }
+      bool started = false;
+#pragma unroll 1
+      for (int w = 0; w < 32; w++) {
+        uint32_t d = (k[w >> 2] >> ((w & 3) * 8)) & 0xffu;
+        if (d) {
+          const uint32_t* e = tbl + (size_t)(w * 255 + (d - 1)) * WTBL;
+          F x = load_tbl_field<F>(e);
+          F y = load_tbl_field<F>(e + WF);
+          if (started) {
+            jac_madd(acc, x, y);
+          } else {
+            acc.X = x;
+            acc.Y = y;
+            started = true;
+          }
+        }
+      }
+      fr_mul(cur, cur, fp.pw[7]);  // next point of this thread is PTAU_BLOCK = 2^7 further
+    }
+    pts[j] = acc;
+    pre[j] = (j == 0) ? acc.Z : fmul(pre[j - 1], acc.Z);
+  }
+  // ---- batch inversion (Montgomery's trick) ----
+  F inv = FieldInv<F>::inv(pre[PTAU_GEN_B - 1]);
+#pragma unroll 1
+  for (int j = PTAU_GEN_B - 1; j >= 0; j--) {
+    F zi = (j == 0) ? inv : fmul(inv, pre[j - 1]);
+    if (j) inv = fmul(inv, pts[j].Z);
+    F zi2 = fsqr(zi);
+    F xm = fmul(pts[j].X, zi2);
+    F ym = fmul(pts[j].Y, fmul(zi2, zi));
+    const uint64_t rec0 = blk0 + (uint64_t)j * PTAU_BLOCK;
+    uint32_t* o = sm + tid * WOUT;
+    if (rec0 + tid < n) {
+      if (G == PTAU_G1) {
+        const Fq& xq = reinterpret_cast<const Fq&>(xm);
+        const Fq& yq = reinterpret_cast<const Fq&>(ym);
+        Fq xp = fq_from_mont(xq), yp = fq_from_mont(yq);
+        if (OUTFMT == PTAU_FMT_ZCASH_COMPRESSED) {
+          xp.l[11] |= 0x80000000u | (fq_plain_is_largest(yp) ? 0x20000000u : 0u);
+          fq_to_be_words(xp, o);
+        } else {
+          fq_to_be_words(xp, o);
+          fq_to_be_words(yp, o + 12);
+        }
+      } else {
+        const Fq2& xq = reinterpret_cast<const Fq2&>(xm);
+        const Fq2& yq = reinterpret_cast<const Fq2&>(ym);
+        Fq2 xp, yp;
+        xp.c0 = fq_from_mont(xq.c0);
+        xp.c1 = fq_from_mont(xq.c1);
+        yp.c0 = fq_from_mont(yq.c0);
+        yp.c1 = fq_from_mont(yq.c1);
+        if (OUTFMT == PTAU_FMT_ZCASH_COMPRESSED) {
+          bool largest = fq_is_zero(yp.c1) ? fq_plain_is_largest(yp.c0) : fq_plain_is_largest(yp.c1);
+          xp.c1.l[11] |= 0x80000000u | (largest ? 0x20000000u : 0u);
+          fq_to_be_words(xp.c1, o);
+          fq_to_be_words(xp.c0, o + 12);
+        } else {
+          fq_to_be_words(xp.c1, o);
+          fq_to_be_words(xp.c0, o + 12);
+          fq_to_be_words(yp.c1, o + 24);
+          fq_to_be_words(yp.c0, o + 36);
+        }
+      }
+    }
+    __syncthreads();
+    if (rec0 < n) {
+      const int nrec = (int)((n - rec0) < (uint64_t)PTAU_BLOCK ? (n - rec0) : (uint64_t)PTAU_BLOCK);
+      stage_out(out + rec0 * WOUT, sm, nrec * WOUT);
+    }
+    __syncthreads();
+  }
+}
+
+cudaError_t launch_generate_win(int group, int fmt, const uint32_t* s0_mont, const uint32_t (*pw_mont)[8],
+                                const uint32_t* d_tbl, void* d_out, uint64_t first, uint64_t n, cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  FrParams fp;
+  memcpy(fp.s0, s0_mont, 32);
+  memcpy(fp.pw, pw_mont, sizeof(fp.pw));
+  const uint64_t per_block = (uint64_t)PTAU_BLOCK * PTAU_GEN_B;
+  unsigned grid = (unsigned)((n + per_block - 1) / per_block);
+  if (group == PTAU_G1 && fmt == PTAU_FMT_ZCASH_COMPRESSED)
+    generate_win_kernel<PTAU_G1, PTAU_FMT_ZCASH_COMPRESSED><<<grid, PTAU_BLOCK, 0, stream>>>(fp, d_tbl, (uint32_t*)d_out, first, n);
+  else if (group == PTAU_G1 && fmt == PTAU_FMT_ZCASH_UNCOMPRESSED)
+    generate_win_kernel<PTAU_G1, PTAU_FMT_ZCASH_UNCOMPRESSED><<<grid, PTAU_BLOCK, 0, stream>>>(fp, d_tbl, (uint32_t*)d_out, first, n);
+  else if (group == PTAU_G2 && fmt == PTAU_FMT_ZCASH_COMPRESSED)
+    generate_win_kernel<PTAU_G2, PTAU_FMT_ZCASH_COMPRESSED><<<grid, PTAU_BLOCK, 0, stream>>>(fp, d_tbl, (uint32_t*)d_out, first, n);
+  else if (group == PTAU_G2 && fmt == PTAU_FMT_ZCASH_UNCOMPRESSED)
+    generate_win_kernel<PTAU_G2, PTAU_FMT_ZCASH_UNCOMPRESSED><<<grid, PTAU_BLOCK, 0, stream>>>(fp, d_tbl, (uint32_t*)d_out, first, n);
   else
     return cudaErrorInvalidValue;
   return cudaGetLastError();

@@ -13,6 +13,11 @@ cudaError_t launch_convert(int group, int in_fmt, int out_fmt, const void* d_in,
 cudaError_t launch_generate(int group, int fmt, const uint32_t* d_scalars, void* d_out, uint64_t n,
                             cudaStream_t stream);
 
+// generator v2: scalars formed on the device from s0 (Montgomery Fr) and pw[j] = step^(2^j)
+// (Montgomery Fr); d_tbl = 32 x 255 ARK_MONT_LIMBS records of [d * 256^w]G
+cudaError_t launch_generate_win(int group, int fmt, const uint32_t* s0_mont, const uint32_t (*pw_mont)[8],
+                                const uint32_t* d_tbl, void* d_out, uint64_t first, uint64_t n, cudaStream_t stream);
+
 cudaError_t launch_microbench(int kind, int iters, uint32_t* d_out, int grid, int block, double* ops,
                               cudaStream_t stream);
 
