@@ -108,6 +108,82 @@ def run_reference(args):
     return 0
 
 
+def run_config5(args, kz, sharding, torch, dist, ctx, rank, world, dev):
+    """BASELINE configs[4]: a 2^K-power synthetic setup (known tau) sharded by contiguous
+    index ranges over the ranks.  Per rank: for each section of the kgz pipeline, its index
+    range is generated on the GPU slab by slab (compressed zcash encoding, [s*tau^i]G) and
+    pushed through the fused compressed -> strict checks -> ark kernel.  Only the convert
+    kernels are timed (CUDA events); strong scaling: the total work is fixed."""
+    n = 1 << args.log2_powers
+    tau, alpha, beta = 0x1234567890ABCDEF1234567890ABCDEF, 0x0FEDCBA987654321, 0x13579BDF02468ACE
+    secs = [("tau_g1", kz.G1, 1, 2 * n - 1), ("tau_g2", kz.G2, 1, n), ("alpha_g1", kz.G1, alpha, n),
+            ("beta_g1", kz.G1, beta, n)]
+    slab = 1 << 22
+    d_in = torch.empty(slab * 96, dtype=torch.uint8, device=dev)
+    d_out = torch.empty(slab * 192, dtype=torch.uint8, device=dev)
+    status = torch.full((1,), -1, dtype=torch.int64, device=dev)
+    stream = torch.cuda.current_stream()
+    ZC, AU = kz.FMT_ZCASH_COMPRESSED, kz.FMT_ARK_UNCOMPRESSED
+    # warm-up (also builds the generator tables)
+    for g in (kz.G1, kz.G2):
+        ctx.generate_device(g, ZC, 1, tau, 0, 4096, d_in.data_ptr(), stream=stream.cuda_stream)
+        for _ in range(3):
+            ctx.convert_device(g, ZC, d_in.data_ptr(), AU, d_out.data_ptr(), 4096, kz.CHECKS_STRICT, status.data_ptr(),
+                               stream=stream.cuda_stream)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks, stop = [], threading.Event()
+    th = threading.Thread(target=sample_clocks, args=(stop, clocks), daemon=True)
+    th.start()
+    t_wall = time.perf_counter()
+    ms = {"G1": 0.0, "G2": 0.0}
+    pts = {"G1": 0, "G2": 0}
+    launches = 0
+    for name, g, s0, cnt in secs:
+        lo, hi = sharding.shard_range(cnt, rank, world)
+        for a in range(lo, hi, slab):
+            c = min(slab, hi - a)
+            ctx.generate_device(g, ZC, s0, tau, a, c, d_in.data_ptr(), stream=stream.cuda_stream)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            ctx.convert_device(g, ZC, d_in.data_ptr(), AU, d_out.data_ptr(), c, kz.CHECKS_STRICT, status.data_ptr(),
+                               base_index=a, stream=stream.cuda_stream)
+            e1.record(stream)
+            e1.synchronize()
+            key = "G1" if g == kz.G1 else "G2"
+            ms[key] += e0.elapsed_time(e1)
+            pts[key] += c
+            launches += 1
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t_wall
+    stop.set()
+    th.join()
+    assert int(status.item()) == -1, "synthetic setup failed validation"
+    if world > 1:
+        dist.barrier()
+    t_max = sharding.reduce_max_ms(ms["G1"] + ms["G2"])
+    g1_ms, g2_ms = sharding.reduce_max_ms(ms["G1"]), sharding.reduce_max_ms(ms["G2"])
+    tot_g1, tot_g2 = int(sharding.reduce_sum(pts["G1"])), int(sharding.reduce_sum(pts["G2"]))
+    wall_max = sharding.reduce_max_ms(wall * 1e3)
+    if rank == 0:
+        line = {
+            "metric": "G1+G2 points/sec, compressed parse + sqrt decompress + subgroup check + ark re-encode "
+                      "(2^%d-power setup, index-range sharded)" % args.log2_powers,
+            "value": (tot_g1 + tot_g2) / (t_max / 1e3), "unit": "points/s", "n_gpus": world, "steps": 1, "warmup": 3,
+            "ms_per_step": t_max, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u32 limbs (12x32-bit Montgomery, IMAD.WIDE carry chains)", "data": "synthetic",
+            "config": {"workload": "BASELINE configs[4]: 2^%d powers, sections tau_g1 (2N-1), tau_g2 (N), alpha_g1 (N), "
+                                   "beta_g1 (N), compressed input generated on the GPU per slab" % args.log2_powers,
+                       "g1_points": tot_g1, "g2_points": tot_g2, "g1_points_per_s": tot_g1 / (g1_ms / 1e3),
+                       "g2_points_per_s": tot_g2 / (g2_ms / 1e3), "kernel_ms_g1_max_rank": g1_ms,
+                       "kernel_ms_g2_max_rank": g2_ms, "wall_s_incl_generation": wall_max / 1e3,
+                       "l2": "inputs larger than L2 (slabs of 2^22 points, 200-400 MB)"},
+            "e2e": None, "gpu_launches": launches, "clocks": summarize_clocks(clocks),
+        }
+        print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -116,6 +192,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--log2-points", type=int, default=LOG2_POINTS)
     ap.add_argument("--no-extra", action="store_true", help="skip the non-headline legs")
+    ap.add_argument("--workload", default="config2", choices=["config2", "config5"],
+                    help="config2 = headline (2^20 uncompressed G1 per GPU); config5 = 2^K-power compressed setup "
+                         "sharded by index range over all ranks (strong scaling, device-resident)")
+    ap.add_argument("--log2-powers", type=int, default=26, help="powers of the config5 setup")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -135,6 +215,12 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     ctx = kz.Context(device_ids=[local])
+    if args.workload == "config5":
+        run_config5(args, kz, sharding, torch, dist, ctx, rank, world, dev)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return 0
     N = 1 << args.log2_points
     tau = 0x1234567890ABCDEF1234567890ABCDEF % 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
     ZU, ZC, AU, ML = kz.FMT_ZCASH_UNCOMPRESSED, kz.FMT_ZCASH_COMPRESSED, kz.FMT_ARK_UNCOMPRESSED, kz.FMT_ARK_MONT_LIMBS
@@ -266,6 +352,30 @@ def main():
             leg("g1_load_validated(config4)", kz.G1, AU, ML, STRICT, 1 << 22, None)
             leg("g1_reencode_only(hbm)", kz.G1, ZU, AU, 0, 1 << 23, None)
             assert int(status.item()) == -1
+            # whole preprocess-kgz job at the ceremony's real size (2^21 powers, 604 MB response), host to host
+            try:
+                k = 21
+                n21 = 1 << k
+                L = kz._ffi.lib()
+                resp = kz.PinnedBuffer(L.ptau_response_size(n21))
+                setup = kz.PinnedBuffer(L.ptau_setup_size(kz.VARIANT_KGZ, n21))
+                off = 64
+                for g, s0, cnt in ((kz.G1, 1, 2 * n21 - 1), (kz.G2, 1, n21), (kz.G1, 7, n21), (kz.G1, 11, n21), (kz.G2, 11, 1)):
+                    ln = cnt * L.ptau_record_size(g, ZC)
+                    ctx.generate(g, ZC, s0, tau, 0, cnt, out=resp.array[off:off + ln])
+                    off += ln
+                ctx.preprocess(kz.VARIANT_KGZ, resp, n21, STRICT, out=setup)  # warm
+                t0 = time.perf_counter()
+                ctx.preprocess(kz.VARIANT_KGZ, resp, n21, STRICT, out=setup)
+                dt = time.perf_counter() - t0
+                npts = (2 * n21 - 1) + n21 + n21
+                extra["preprocess_kgz_2^21_fused(host->host)"] = {
+                    "points": npts, "ms": dt * 1e3, "points_per_s": npts / dt,
+                    "note": "ptau_preprocess on pinned host buffers: 4.2M+2.1M compressed G1, 2.1M compressed G2, all checks"}
+                resp.free()
+                setup.free()
+            except Exception as e:  # pinned allocation of 1.2 GB may be refused on small hosts
+                extra["preprocess_kgz_2^21_fused(host->host)"] = {"error": repr(e)}
             hb = extra["g1_reencode_only(hbm)"]
             line["roofline_hbm"] = {"bound": "hbm", "kernel": "zcash->ark re-encode only (no checks)",
                                     "achieved": hb["GBps"], "peak": 6552.0, "unit": "GB/s",

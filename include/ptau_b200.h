@@ -130,7 +130,8 @@ uint64_t ptau_setup_size(int variant, uint64_t n_powers); /* `kzg_setup`        
 /* Host buffers in, host buffers out.  Points [0, n_points) are split into
  * contiguous index ranges, one per GPU of the context; each GPU streams its range
  * through double-buffered H2D -> kernel -> D2H and writes its disjoint slice of
- * `out`.  No collective.  `in`/`out` should be pinned for full PCIe speed. */
+ * `out`.  No collective.  `in`/`out` should be pinned for full PCIe speed.  out == NULL
+ * validates only: the kernels run, nothing is copied back. */
 int ptau_convert(ptau_ctx* ctx, int group, int in_fmt, const void* in, int out_fmt, void* out,
                  size_t n_points, unsigned checks, uint64_t* bad_index, int* bad_kind);
 

@@ -318,7 +318,7 @@ int ptau_convert_device(ptau_ctx* ctx, int gpu, int group, int in_fmt, const voi
 
 int ptau_convert(ptau_ctx* ctx, int group, int in_fmt, const void* in, int out_fmt, void* out, size_t n_points,
                  unsigned checks, uint64_t* bad_index, int* bad_kind) {
-  if (!ctx || (!in && n_points) || (!out && n_points)) return PTAU_ERR_ARG;
+  if (!ctx || (!in && n_points)) return PTAU_ERR_ARG;  // out == NULL: validate only, nothing is copied back
   const int ri = rec_size(group, in_fmt), ro = rec_size(group, out_fmt);
   if (!ri || !ro || in_fmt == PTAU_FMT_ARK_MONT_LIMBS || out_fmt == PTAU_FMT_ZCASH_COMPRESSED) return PTAU_ERR_ARG;
   auto t0 = std::chrono::steady_clock::now();
@@ -368,15 +368,17 @@ int ptau_convert(ptau_ctx* ctx, int group, int in_fmt, const void* in, int out_f
         tm.kernel_ms[g] += ms;
       }
       const uint8_t* src = (const uint8_t*)in + r.next * (size_t)ri;
-      uint8_t* dst = (uint8_t*)out + r.next * (size_t)ro;
+      uint8_t* dst = out ? (uint8_t*)out + r.next * (size_t)ro : nullptr;
       CUDA_TRY(ctx, cudaMemcpyAsync(s.d_in[b], src, npts * ri, cudaMemcpyHostToDevice, s.stream[b]));
       CUDA_TRY(ctx, cudaEventRecord(s.ev_k0[b], s.stream[b]));
       CUDA_TRY(ctx, ptau::launch_convert(group, in_fmt, out_fmt, s.d_in[b], s.d_out[b], npts, checks, r.next,
                                          s.d_status, s.stream[b]));
       CUDA_TRY(ctx, cudaEventRecord(s.ev_k1[b], s.stream[b]));
-      CUDA_TRY(ctx, cudaMemcpyAsync(dst, s.d_out[b], npts * ro, cudaMemcpyDeviceToHost, s.stream[b]));
+      if (out) {
+        CUDA_TRY(ctx, cudaMemcpyAsync(dst, s.d_out[b], npts * ro, cudaMemcpyDeviceToHost, s.stream[b]));
+        tm.d2h_bytes[g] += npts * ro;
+      }
       tm.h2d_bytes[g] += npts * ri;
-      tm.d2h_bytes[g] += npts * ro;
       tm.kernel_launches++;
       r.next += npts;
       r.issued++;
@@ -511,9 +513,10 @@ int ptau_generate(ptau_ctx* ctx, int group, int fmt, const uint8_t scalar0[32], 
 }
 
 // ---- whole-file pipelines ----------------------------------------------------------
+// out[s] == NULL with process[s] set: the section is validated but nothing is copied back
 static int run_sections(ptau_ctx* ctx, const Section* secs, int nsec, int in_fmt, const uint8_t* in,
                         const int* out_fmt, uint8_t* const* out, unsigned checks, uint64_t* bad_index, int* bad_kind,
-                        int* bad_section) {
+                        int* bad_section, const bool* process = nullptr) {
   // Sections are processed in file order and the first failing section wins, so
   // the reported (section, index) is the first bad point in file order.
   ptau_timing total;
@@ -522,7 +525,7 @@ static int run_sections(ptau_ctx* ctx, const Section* secs, int nsec, int in_fmt
   size_t off = 0;
   for (int s = 0; s < nsec; s++) {
     const int ri = rec_size(secs[s].group, in_fmt);
-    if (out[s]) {
+    if (out[s] || (process && process[s])) {
       int rc = ptau_convert(ctx, secs[s].group, in_fmt, in + off, out_fmt[s], out[s], secs[s].count, checks,
                             bad_index, bad_kind);
       total.wall_ms += ctx->timing.wall_ms;
@@ -569,26 +572,34 @@ static int preprocess_common(ptau_ctx* ctx, int variant, int in_fmt, const uint8
   const bool fast = variant == PTAU_VARIANT_FASTKGZ;
   const Section secs[5] = {{PTAU_G1, 2 * n - 1}, {PTAU_G2, n}, {PTAU_G1, n}, {PTAU_G1, n}, {PTAU_G2, 1}};
   // tau_g2: kgz needs only [0], [1] in the output but the reference checks all n
-  // (preprocess-kgz.rs:146-148), so all n are converted; kgz keeps them in a
-  // scratch buffer, fastkgz writes them in place as powers_of_h.
+  // (preprocess-kgz.rs:146-148): all n are validated on the GPU without copying the
+  // results back, and the first two are converted again for the VerifierKey; fastkgz
+  // writes all n in place as powers_of_h.  beta_tau_powers_g1 is read, checked and
+  // dropped by fastkgz (preprocess-fastkgz.rs:156-159) and never read by kgz; beta_g2
+  // (section 4) is never read by either binary (preprocess-fastkgz.rs:161).
   const uint64_t g1_all = (2 * n - 1) * 96 + n * 96;
-  std::vector<uint8_t> scratch_g2;
-  uint8_t* tau_g2_out;
-  if (fast) {
-    tau_g2_out = setup + g1_all + 384;
-  } else {
-    scratch_g2.resize(n * 192);
-    tau_g2_out = scratch_g2.data();
-  }
-  std::vector<uint8_t> scratch_beta;
-  if (fast) scratch_beta.resize(n * 96);  // beta_tau_powers_g1: read, checked, dropped (preprocess-fastkgz.rs:156-159)
+  uint8_t first_g2[384];
   int fmts[5] = {PTAU_FMT_ARK_UNCOMPRESSED, PTAU_FMT_ARK_UNCOMPRESSED, PTAU_FMT_ARK_UNCOMPRESSED,
                  PTAU_FMT_ARK_UNCOMPRESSED, PTAU_FMT_ARK_UNCOMPRESSED};
-  // beta_g2 (section 4) is never read by either binary (preprocess-fastkgz.rs:161)
-  uint8_t* outs[5] = {setup, tau_g2_out, setup + (2 * n - 1) * 96, fast ? scratch_beta.data() : nullptr, nullptr};
-  int rc = run_sections(ctx, secs, 5, in_fmt, body, fmts, outs, checks, bad_index, bad_kind, bad_section);
+  uint8_t* outs[5] = {setup, fast ? setup + g1_all + 384 : nullptr, setup + (2 * n - 1) * 96, nullptr, nullptr};
+  const bool process[5] = {true, true, true, fast, false};
+  int rc = run_sections(ctx, secs, 5, in_fmt, body, fmts, outs, checks, bad_index, bad_kind, bad_section, process);
   if (rc) return rc;
-  return assemble_setup(variant, n, setup, tau_g2_out);
+  const uint8_t* tau_g2_ark = setup + g1_all + 384;
+  if (!fast) {
+    const size_t g2_off = (2 * n - 1) * (size_t)rec_size(PTAU_G1, in_fmt);
+    ptau_timing keep = ctx->timing;
+    rc = ptau_convert(ctx, PTAU_G2, in_fmt, body + g2_off, PTAU_FMT_ARK_UNCOMPRESSED, first_g2, 2, checks, bad_index,
+                      bad_kind);
+    keep.kernel_launches += ctx->timing.kernel_launches;
+    ctx->timing = keep;
+    if (rc) {
+      if (bad_section) *bad_section = 1;
+      return rc;
+    }
+    tau_g2_ark = first_g2;
+  }
+  return assemble_setup(variant, n, setup, tau_g2_ark);
 }
 
 int ptau_preprocess(ptau_ctx* ctx, int variant, const void* response, uint64_t response_len, uint64_t n_powers,

@@ -196,6 +196,9 @@ int ptau_preprocess_files(ptau_ctx* ctx, int variant, const char* response_path,
         if (rc != PTAU_OK) break;
         uint64_t bi = 0;
         int bk = 0;
+        // sections that are checked but not written (kgz: tau_g2 beyond its first slab;
+        // fastkgz: beta_g1) are validated on the GPU without copying results back
+        uint8_t* dst = (sec.out_off >= 0 || k == 0) ? outb[b] : nullptr;
         if (emit_unc) {
           // stage 1: decompress (CheckForCorrectness::No) -> `powersoftau_uncompressed`
           rc = ptau_convert(ctx, sec.group, PTAU_FMT_ZCASH_COMPRESSED, inb[b], PTAU_FMT_ZCASH_UNCOMPRESSED, uncb[b], cnt,
@@ -205,10 +208,10 @@ int ptau_preprocess_files(ptau_ctx* ctx, int variant, const char* response_path,
                                unc_off + lo * r_unc);
           // stage 2: read_g1 / read_g2 on the uncompressed bytes
           if (rc == PTAU_OK && !only_decompress)
-            rc = ptau_convert(ctx, sec.group, PTAU_FMT_ZCASH_UNCOMPRESSED, uncb[b], PTAU_FMT_ARK_UNCOMPRESSED, outb[b], cnt,
+            rc = ptau_convert(ctx, sec.group, PTAU_FMT_ZCASH_UNCOMPRESSED, uncb[b], PTAU_FMT_ARK_UNCOMPRESSED, dst, cnt,
                               checks, &bi, &bk);
         } else if (!only_decompress) {
-          rc = ptau_convert(ctx, sec.group, PTAU_FMT_ZCASH_COMPRESSED, inb[b], PTAU_FMT_ARK_UNCOMPRESSED, outb[b], cnt, checks,
+          rc = ptau_convert(ctx, sec.group, PTAU_FMT_ZCASH_COMPRESSED, inb[b], PTAU_FMT_ARK_UNCOMPRESSED, dst, cnt, checks,
                             &bi, &bk);
         }
         if (rc > 0) {
