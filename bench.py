@@ -61,14 +61,16 @@ def summarize_clocks(samples):
             "samples": len(samples), "power_w_max": max(float(s[2]) for s in samples)}
 
 
-def cpu_baseline(n_sample, threads, seed_tau):
-    """The oracle (C restatement of the reference's algorithms) timed on host cores."""
+def cpu_baseline(n_sample, threads, seed_tau, fast_predicates=False):
+    """The oracle (C restatement of the reference's algorithms) timed on host cores.
+    fast_predicates=True runs the same C code with the GPU's GLV check instead of the
+    reference's multiplication by r (separates algorithmic from hardware speed-up)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import cpu_ref
 
     zu = cpu_ref.generate(1, 1, 1, seed_tau, 0, n_sample, threads)
     t0 = time.perf_counter()
-    out, st = cpu_ref.convert(1, 1, zu, 3, 4, threads)  # read_g1 semantics: r-multiplication check
+    out, st = cpu_ref.convert(1, 1, zu, 3, 4 | (16 if fast_predicates else 0), threads)  # read_g1 semantics
     dt = time.perf_counter() - t0
     assert not any(st)
     return n_sample / dt, dt
@@ -392,6 +394,7 @@ def main():
                 "sample": "first 2^15 points of the workload, C restatement of the reference's algorithms "
                           "(6x64 Montgomery, r-multiplication subgroup check), %d threads, %.1f s" % (threads, dt),
                 "single_core_value": rate1,
+                "same_code_with_gpu_predicates_value": cpu_baseline(n_s, threads, tau, True)[0],
             }
         except Exception as e:  # the oracle is optional for the product, never for correctness claims
             line["cpu_baseline"] = {"value": None, "unit": "points/s", "cores": threads, "kind": "port",

@@ -201,6 +201,8 @@ DEFINE_CURVE(fq, g1)
 DEFINE_CURVE(fq2, g2)
 
 static fq FQ_B1; /* 4 in Montgomery form, set by init */
+static fq K_BETA, K_PSI_CX1, K_HALF; /* constants of the fast predicates (baseline row 3 only) */
+static fq2 K_PSI_CY;
 static fq2 FQ2_ONE, FQ2_B2;
 static fq G1X, G1Y; static fq2 G2X, G2Y;
 static int g_init = 0;
@@ -219,13 +221,62 @@ static void init_consts(void) {
   fq_from_hex_limbs(&G1X, g1x); fq_from_hex_limbs(&G1Y, g1y);
   fq_from_hex_limbs(&G2X.c0, g2x0); fq_from_hex_limbs(&G2X.c1, g2x1);
   fq_from_hex_limbs(&G2Y.c0, g2y0); fq_from_hex_limbs(&G2Y.c1, g2y1);
+  static const uint64_t beta[6] = {0x2e01fffffffefffeull, 0xde17d813620a0002ull, 0xddb3a93be6f89688ull, 0xba69c6076a0f77eaull, 0x5f19672fdf76ce51ull, 0};
+  static const uint64_t cx1[6] = {0x8bfd00000000aaadull, 0x409427eb4f49fffdull, 0x897d29650fb85f9bull, 0xaa0d857d89759ad4ull, 0xec02408663d4de85ull, 0x1a0111ea397fe699ull};
+  static const uint64_t cy0[6] = {0xf1ee7b04121bdea2ull, 0x304466cf3e67fa0aull, 0xef396489f61eb45eull, 0x1c3dedd930b1cf60ull, 0xe2e9c448d77a2cd9ull, 0x135203e60180a68eull};
+  static const uint64_t cy1[6] = {0xc81084fbede3cc09ull, 0xee67992f72ec05f4ull, 0x77f76e17009241c5ull, 0x48395dabc2d3435eull, 0x6831e36d6bd17ffeull, 0x06af0e0437ff400bull};
+  static const uint64_t half[6] = {0xdcff7fffffffd556ull, 0x0f55ffff58a9ffffull, 0xb39869507b587b12ull, 0xb23ba5c279c2895full, 0x258dd3db21a5d66bull, 0x0d0088f51cbff34dull};
+  fq_from_hex_limbs(&K_BETA, beta); fq_from_hex_limbs(&K_PSI_CX1, cx1); fq_from_hex_limbs(&K_PSI_CY.c0, cy0);
+  fq_from_hex_limbs(&K_PSI_CY.c1, cy1); fq_from_hex_limbs(&K_HALF, half);
   g_init = 1;
+}
+
+/* ---------------- the GPU's predicates, on the CPU ----------------
+ * Only used for the third baseline row of BASELINE.md (same C code, endomorphism checks and
+ * norm-method square root) so that the algorithmic and the hardware speed-up can be told
+ * apart.  Selected with CHK_FAST_PREDICATES; never the default, never the parity oracle. */
+static const uint64_t Z_ABS[1] = {0xd201000000010000ull};
+static void g1_add_jac(g1_jac* p, const g1_jac* q) { /* add-2007-bl, no special cases needed on the ladders */
+  fq Z1Z1, Z2Z2, U1, U2, S1, S2, H, I, J, rr, V, t, X3, Y3, Z3;
+  fq_sqr(&Z1Z1, &p->Z); fq_sqr(&Z2Z2, &q->Z); fq_mul(&U1, &p->X, &Z2Z2); fq_mul(&U2, &q->X, &Z1Z1);
+  fq_mul(&S1, &p->Y, &q->Z); fq_mul(&S1, &S1, &Z2Z2); fq_mul(&S2, &q->Y, &p->Z); fq_mul(&S2, &S2, &Z1Z1);
+  fq_sub(&H, &U2, &U1); fq_dbl(&I, &H); fq_sqr(&I, &I); fq_mul(&J, &H, &I); fq_sub(&rr, &S2, &S1); fq_dbl(&rr, &rr);
+  fq_mul(&V, &U1, &I); fq_sqr(&X3, &rr); fq_sub(&X3, &X3, &J); fq_dbl(&t, &V); fq_sub(&X3, &X3, &t);
+  fq_sub(&t, &V, &X3); fq_mul(&Y3, &rr, &t); fq_mul(&t, &S1, &J); fq_dbl(&t, &t); fq_sub(&Y3, &Y3, &t);
+  fq_mul(&Z3, &p->Z, &q->Z); fq_dbl(&Z3, &Z3); fq_mul(&Z3, &Z3, &H);
+  p->X = X3; p->Y = Y3; p->Z = Z3;
+}
+static int g1_in_subgroup_glv(const fq* x, const fq* y) {
+  g1_jac q, acc; g1_mul_bits(&q, x, y, &FQ_ONE, Z_ABS, 1);
+  if (fq_is_zero(&q.Z)) return 0;
+  acc = q;
+  for (int i = 62; i >= 0; --i) { g1_double(&acc); if ((Z_ABS[0] >> i) & 1) g1_add_jac(&acc, &q); }
+  if (fq_is_zero(&acc.Z)) return 0;
+  fq zz, zzz, bx, ny, l, r2; fq_sqr(&zz, &acc.Z); fq_mul(&zzz, &zz, &acc.Z); fq_mul(&bx, x, &K_BETA); fq_neg(&ny, y);
+  fq_mul(&l, &bx, &zz); fq_mul(&r2, &ny, &zzz);
+  return fq_eq(&acc.X, &l) && fq_eq(&acc.Y, &r2);
+}
+static int g2_in_subgroup_psi(const fq2* x, const fq2* y) {
+  g2_jac q; g2_mul_bits(&q, x, y, &FQ2_ONE, Z_ABS, 1);
+  if (fq2_is_zero(&q.Z)) return 0;
+  fq2 px, py, cy, zz, zzz, l, r2; fq_mul(&px.c0, &x->c1, &K_PSI_CX1); fq_mul(&px.c1, &x->c0, &K_PSI_CX1);
+  fq2_conj(&cy, y); fq2_mul(&py, &cy, &K_PSI_CY); fq2_neg(&py, &py);
+  fq2_sqr(&zz, &q.Z); fq2_mul(&zzz, &zz, &q.Z); fq2_mul(&l, &px, &zz); fq2_mul(&r2, &py, &zzz);
+  return fq2_eq(&q.X, &l) && fq2_eq(&q.Y, &r2);
+}
+static int fq2_sqrt_norm(fq2* r, const fq2* a) {
+  fq n, t0, s, d, t, x0, chi, w, nx0; fq_sqr(&n, &a->c0); fq_sqr(&t0, &a->c1); fq_add(&n, &n, &t0);
+  fq_pow(&s, &n, E_P1_4, 6); fq_add(&d, &a->c0, &s); fq_mul(&d, &d, &K_HALF);
+  if (fq_is_zero(&d)) { fq_sub(&d, &a->c0, &s); fq_mul(&d, &d, &K_HALF); }
+  fq_pow(&t, &d, E_P3_4, 6); fq_mul(&x0, &d, &t); fq_mul(&chi, &x0, &t); fq_mul(&w, &a->c1, &t); fq_mul(&w, &w, &K_HALF);
+  if (fq_eq(&chi, &FQ_ONE) || fq_is_zero(&d)) { r->c0 = x0; r->c1 = w; } else { fq_neg(&nx0, &x0); r->c0 = w; r->c1 = nx0; }
+  fq2 chk; fq2_sqr(&chk, r); return fq2_eq(&chk, a);
 }
 
 /* ---------------- encodings ---------------- */
 enum { FMT_ZU = 1, FMT_ZC = 2, FMT_AU = 3, FMT_ML = 4 };
 enum { G1 = 1, G2 = 2 };
-enum { CHK_ON_CURVE = 2, CHK_SUBGROUP = 4, CHK_REJECT_INF = 8 };
+enum { CHK_ON_CURVE = 2, CHK_SUBGROUP = 4, CHK_REJECT_INF = 8, CHK_FAST_PREDICATES = 16 };
 enum { OK = 0, BAD_NON_CANONICAL = 1, BAD_FLAGS = 2, BAD_INFINITY = 3, BAD_NOT_ON_CURVE = 4, BAD_NOT_IN_SUBGROUP = 5 };
 
 static void be48_to_limbs(fq* r, const uint8_t* b) {
@@ -280,8 +331,8 @@ static int g1_one(int in_fmt, const uint8_t* in, int out_fmt, uint8_t* out, unsi
   }
   if (st == OK && inf && (checks & CHK_REJECT_INF)) st = BAD_INFINITY;
   if (st == OK && !inf && (checks & CHK_SUBGROUP)) {
-    g1_jac t; g1_mul_bits(&t, &xm, &ym, &FQ_ONE, R_ORDER, 4);
-    if (!fq_is_zero(&t.Z)) st = BAD_NOT_IN_SUBGROUP;
+    if (checks & CHK_FAST_PREDICATES) { if (!g1_in_subgroup_glv(&xm, &ym)) st = BAD_NOT_IN_SUBGROUP; }
+    else { g1_jac t; g1_mul_bits(&t, &xm, &ym, &FQ_ONE, R_ORDER, 4); if (!fq_is_zero(&t.Z)) st = BAD_NOT_IN_SUBGROUP; }
   }
   if (out_fmt == FMT_AU) { limbs_to_le48(out, &xp); limbs_to_le48(out + 48, &yp); if (inf) out[95] |= 0x40; }
   else if (out_fmt == FMT_ZU) {
@@ -308,7 +359,8 @@ static int g2_one(int in_fmt, const uint8_t* in, int out_fmt, uint8_t* out, unsi
     if (st == OK && !inf) {
       fq2 rhs; fq_to_mont(&xm.c0, &xp.c0); fq_to_mont(&xm.c1, &xp.c1);
       fq2_sqr(&rhs, &xm); fq2_mul(&rhs, &rhs, &xm); fq2_add(&rhs, &rhs, &FQ2_B2);
-      if (!fq2_sqrt(&ym, &rhs)) st = BAD_NOT_ON_CURVE;
+      if (checks & CHK_FAST_PREDICATES) { if (!fq2_sqrt_norm(&ym, &rhs)) st = BAD_NOT_ON_CURVE; }
+      else if (!fq2_sqrt(&ym, &rhs)) st = BAD_NOT_ON_CURVE;
       else { fq2 chk; fq2_sqr(&chk, &ym); if (!fq2_eq(&chk, &rhs)) st = BAD_NOT_ON_CURVE; }
       fq_from_mont(&yp.c0, &ym.c0); fq_from_mont(&yp.c1, &ym.c1);
       if (fq2_plain_largest(&yp) != (fl & 1)) { fq2_neg(&ym, &ym); fq_plain_neg(&yp.c0, &yp.c0); fq_plain_neg(&yp.c1, &yp.c1); }
@@ -329,8 +381,8 @@ static int g2_one(int in_fmt, const uint8_t* in, int out_fmt, uint8_t* out, unsi
   }
   if (st == OK && inf && (checks & CHK_REJECT_INF)) st = BAD_INFINITY;
   if (st == OK && !inf && (checks & CHK_SUBGROUP)) {
-    g2_jac t; g2_mul_bits(&t, &xm, &ym, &FQ2_ONE, R_ORDER, 4);
-    if (!fq2_is_zero(&t.Z)) st = BAD_NOT_IN_SUBGROUP;
+    if (checks & CHK_FAST_PREDICATES) { if (!g2_in_subgroup_psi(&xm, &ym)) st = BAD_NOT_IN_SUBGROUP; }
+    else { g2_jac t; g2_mul_bits(&t, &xm, &ym, &FQ2_ONE, R_ORDER, 4); if (!fq2_is_zero(&t.Z)) st = BAD_NOT_IN_SUBGROUP; }
   }
   if (out_fmt == FMT_AU) {
     limbs_to_le48(out, &xp.c0); limbs_to_le48(out + 48, &xp.c1); limbs_to_le48(out + 96, &yp.c0); limbs_to_le48(out + 144, &yp.c1);
