@@ -693,9 +693,9 @@ int ptau_microbench(ptau_ctx* ctx, int gpu, int kind, int iters, double* ms, dou
   cudaDeviceProp prop;
   CUDA_TRY(ctx, cudaGetDeviceProperties(&prop, s.device));
   const int block = 256;
-  const int grid = prop.multiProcessorCount * (kind == 2 ? 2 : 4);
+  const int grid = prop.multiProcessorCount * (kind == 2 ? 2 : (kind >= 3 ? 1 : 4));
   uint32_t* d_out = nullptr;
-  CUDA_TRY(ctx, cudaMalloc((void**)&d_out, (size_t)grid * block * 4));
+  CUDA_TRY(ctx, cudaMalloc((void**)&d_out, (size_t)grid * block * 4 * 4));
   double o = 0;
   cudaError_t e = ptau::launch_microbench(kind, iters > 16 ? 16 : iters, d_out, grid, block, &o, s.stream[0]);  // warm-up
   if (e == cudaSuccess) e = cudaEventRecord(s.ev_k0[0], s.stream[0]);

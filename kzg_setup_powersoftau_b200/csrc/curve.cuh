@@ -90,6 +90,30 @@ PTAU_HD void jac_add(Jac<F>& p, const Jac<F>& q) {
 // |z| = 0xd201000000010000 = 2^63 + 2^62 + 2^60 + 2^57 + 2^48 + 2^16
 #define PTAU_Z_ABS 0xd201000000010000ull
 
+// The doubling of the ladders.  PTAU_G1_DBL_INLINE (device, Fq only) expands the seven
+// field multiplications in place instead of calling fq_mul / fq_sqr: no argument shuffles,
+// at the price of a ~40 KB loop body.
+#if defined(__CUDA_ARCH__) && defined(PTAU_G1_DBL_INLINE)
+PTAU_HD void jac_dbl_ladder(Jac<Fq>& p) {
+  Fq B = fq_sqr_inl(p.Y);
+  p.Z = fq_dbl(fq_mul_inl(p.Z, p.Y));
+  Fq C = fq_sqr_inl(B);
+  Fq t = fq_add(p.X, B);
+  Fq A = fq_sqr_inl(p.X);
+  Fq D = fq_sqr_inl(t);
+  D = fq_sub(fq_sub(D, A), C);
+  D = fq_dbl(D);
+  Fq E = fq_add(fq_dbl(A), A);
+  Fq Fv = fq_sqr_inl(E);
+  p.X = fq_sub(Fv, fq_dbl(D));
+  C = fq_dbl(fq_dbl(fq_dbl(C)));
+  p.Y = fq_sub(fq_mul_inl(fq_sub(D, p.X), E), C);
+}
+#else
+PTAU_HD void jac_dbl_ladder(Jac<Fq>& p) { jac_dbl(p); }
+#endif
+PTAU_HD void jac_dbl_ladder(Jac<Fq2>& p) { jac_dbl(p); }
+
 // acc = [|z|] (x, y), affine base, mixed additions
 template <class F>
 PTAU_HD Jac<F> mul_zabs_affine(const F& x, const F& y, const F& one) {
@@ -99,7 +123,7 @@ PTAU_HD Jac<F> mul_zabs_affine(const F& x, const F& y, const F& one) {
   acc.Z = one;
 #pragma unroll 1
   for (int i = 62; i >= 0; --i) {
-    jac_dbl(acc);
+    jac_dbl_ladder(acc);
     if ((PTAU_Z_ABS >> i) & 1ull) jac_madd(acc, x, y);
   }
   return acc;
@@ -111,7 +135,7 @@ PTAU_HD Jac<F> mul_zabs_jac(const Jac<F>& q) {
   Jac<F> acc = q;
 #pragma unroll 1
   for (int i = 62; i >= 0; --i) {
-    jac_dbl(acc);
+    jac_dbl_ladder(acc);
     if ((PTAU_Z_ABS >> i) & 1ull) jac_add(acc, q);
   }
   return acc;

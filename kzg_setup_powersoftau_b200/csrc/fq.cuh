@@ -171,7 +171,7 @@ PTAU_HD void row_mac_odd_shift(uint32_t* X, uint32_t& E0, const uint32_t* a, uin
       "madc.lo.cc.u32 %8, %17, %19, %10;\n\t"
       "madc.hi.cc.u32 %9, %17, %19, %11;\n\t"
       "madc.lo.cc.u32 %10, %18, %19, 0;\n\t"
-      "madc.hi.u32 %11, %18, %19, 0;"
+      "madc.hi.cc.u32 %11, %18, %19, 0;"
       : "+r"(X[0]), "+r"(X[1]), "+r"(X[2]), "+r"(X[3]), "+r"(X[4]), "+r"(X[5]), "+r"(X[6]), "+r"(X[7]),
         "+r"(X[8]), "+r"(X[9]), "+r"(X[10]), "+r"(X[11]), "+r"(E0)
       : "r"(a[1]), "r"(a[3]), "r"(a[5]), "r"(a[7]), "r"(a[9]), "r"(a[11]), "r"(bi));
@@ -201,7 +201,7 @@ PTAU_HD void row_red_odd(uint32_t* X, uint32_t m) {
       "madc.lo.cc.u32 %8, %12, " P9S ", %8;\n\t"
       "madc.hi.cc.u32 %9, %12, " P9S ", %9;\n\t"
       "madc.lo.cc.u32 %10, %12, " P11S ", %10;\n\t"
-      "madc.hi.u32 %11, %12, " P11S ", %11;"
+      "madc.hi.cc.u32 %11, %12, " P11S ", %11;"
       : "+r"(X[0]), "+r"(X[1]), "+r"(X[2]), "+r"(X[3]), "+r"(X[4]), "+r"(X[5]), "+r"(X[6]), "+r"(X[7]),
         "+r"(X[8]), "+r"(X[9]), "+r"(X[10]), "+r"(X[11])
       : "r"(m));
@@ -416,7 +416,7 @@ PTAU_HD Fq fq_sqr_inl(const Fq& a) {
       }
     }
     PX_MADC_LO_CC(X[10], SQ_M(i, 11), bi, 0u);
-    PX_MADC_HI(X[11], SQ_M(i, 11), bi, 0u);
+    PX_MADC_HI_CC(X[11], SQ_M(i, 11), bi, 0u);  // carry-out is 0 by the bound; .cc lets lo/hi fuse into one IMAD.WIDE
     // even-j products (j >= i); the chain starts at the first such j
     const int j0 = (i & 1) ? i + 1 : i;
     if (j0 <= 10) {

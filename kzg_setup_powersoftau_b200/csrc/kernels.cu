@@ -18,8 +18,11 @@
 namespace ptau {
 
 #define PTAU_BLOCK 128
+// A/B-measured on B200 (tools/ab_bench.py): G1 ladders with the doubling expanded in place
+// (PTAU_G1_DBL_INLINE) run best at 2 blocks/SM (30.1 M pts/s); with calls, 3-4 blocks/SM
+// (29.1-29.4 M pts/s).
 #ifndef PTAU_MINBLOCKS_G1
-#define PTAU_MINBLOCKS_G1 3
+#define PTAU_MINBLOCKS_G1 2
 #endif
 
 __device__ __forceinline__ uint4 ld_stream(const uint4* p) {
@@ -596,6 +599,44 @@ __global__ void __launch_bounds__(256) mb_fqmul(uint32_t* out, int iters, uint32
   out[blockIdx.x * blockDim.x + threadIdx.x] = r;
 }
 
+// kind 3 / 4: the G1 doubling loop of the subgroup ladders, with the product's non-inlined
+// fq_mul/fq_sqr (3) and with everything inlined (4): bounds the cost of the call ABI
+template <bool INL>
+__device__ __forceinline__ void mb_dbl_step(Jac<Fq>& p) {
+  auto MUL = [](const Fq& a, const Fq& b) { return INL ? fq_mul_inl(a, b) : fq_mul(a, b); };
+  auto SQR = [](const Fq& a) { return INL ? fq_sqr_inl(a) : fq_sqr(a); };
+  Fq B = SQR(p.Y);
+  p.Z = fq_dbl(MUL(p.Z, p.Y));
+  Fq C = SQR(B);
+  Fq t = fq_add(p.X, B);
+  Fq A = SQR(p.X);
+  Fq D = SQR(t);
+  D = fq_sub(fq_sub(D, A), C);
+  D = fq_dbl(D);
+  Fq E = fq_add(fq_dbl(A), A);
+  Fq Fv = SQR(E);
+  p.X = fq_sub(Fv, fq_dbl(D));
+  C = fq_dbl(fq_dbl(fq_dbl(C)));
+  p.Y = fq_sub(MUL(fq_sub(D, p.X), E), C);
+}
+#ifndef PTAU_MB_MINB
+#define PTAU_MB_MINB 3
+#endif
+template <bool INL>
+__global__ void __launch_bounds__(128, PTAU_MB_MINB) mb_dbl(uint32_t* out, int iters, uint32_t seed) {
+  Jac<Fq> p;
+  p.X = k_g1x_mont();
+  p.Y = k_g1y_mont();
+  p.Z = fq_one();
+  p.X.l[0] ^= (seed + threadIdx.x) & 0xffu;
+#pragma unroll 1
+  for (int i = 0; i < iters; i++) mb_dbl_step<INL>(p);
+  uint32_t r = 0;
+#pragma unroll
+  for (int i = 0; i < 12; i++) r ^= p.X.l[i] ^ p.Y.l[i] ^ p.Z.l[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = r;
+}
+
 cudaError_t launch_microbench(int kind, int iters, uint32_t* d_out, int grid, int block, double* ops,
                               cudaStream_t stream) {
   double threads = (double)grid * block;
@@ -611,6 +652,14 @@ cudaError_t launch_microbench(int kind, int iters, uint32_t* d_out, int grid, in
     case 2:
       mb_fqmul<<<grid, block, 0, stream>>>(d_out, iters, 12345u);
       *ops = threads * iters * 2.0;
+      break;
+    case 3:
+      mb_dbl<false><<<grid * PTAU_MB_MINB, 128, 0, stream>>>(d_out, iters, 12345u);
+      *ops = (double)grid * PTAU_MB_MINB * 128 * iters;
+      break;
+    case 4:
+      mb_dbl<true><<<grid * PTAU_MB_MINB, 128, 0, stream>>>(d_out, iters, 12345u);
+      *ops = (double)grid * PTAU_MB_MINB * 128 * iters;
       break;
     default:
       return cudaErrorInvalidValue;

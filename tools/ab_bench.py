@@ -30,3 +30,5 @@ bench(kz.G1, 2, 1, 0, "g1_decompress")
 bench(kz.G2, 2, 1, 0, "g2_decompress")
 for kind, name in ((0, "imad"), (1, "imad_wide"), (2, "fq_mul")):
     ms, ops = ctx.microbench(kind, 2000); print(name, ops / ms / 1e6, "G/s")
+for kind, name in ((3, "g1 dbl loop, calls"), (4, "g1 dbl loop, inlined")):
+    ms, ops = ctx.microbench(kind, 500); print(name, "%.2f G dbl/s  (%.1f Mpts/s-equivalent at 126 dbl/pt)" % (ops / ms / 1e6, ops / ms / 1e3 / 126))
