@@ -68,11 +68,19 @@ PTAU_HD Fq2 fq2_conj(const Fq2& a) {
 PTAU_HD bool fq2_is_zero(const Fq2& a) { return fq_is_zero(a.c0) && fq_is_zero(a.c1); }
 PTAU_HD bool fq2_eq(const Fq2& a, const Fq2& b) { return fq_eq(a.c0, b.c0) && fq_eq(a.c1, b.c1); }
 
+// PTAU_FQ2_LEAF (device): expand the Fq multiplications inside fq2_mul / fq2_sqr so that
+// they are leaf functions (one call level, no nested argument shuffles).
+#if defined(__CUDA_ARCH__) && defined(PTAU_FQ2_LEAF)
+#define PTAU_FQ2_M(a, b) fq_mul_inl(a, b)
+#else
+#define PTAU_FQ2_M(a, b) fq_mul(a, b)
+#endif
+
 // Karatsuba: 3 Fq multiplications
 PTAU_HD Fq2 fq2_mul_inl(const Fq2& a, const Fq2& b) {
-  Fq v0 = fq_mul(a.c0, b.c0);
-  Fq v1 = fq_mul(a.c1, b.c1);
-  Fq s = fq_mul(fq_add(a.c0, a.c1), fq_add(b.c0, b.c1));
+  Fq v0 = PTAU_FQ2_M(a.c0, b.c0);
+  Fq v1 = PTAU_FQ2_M(a.c1, b.c1);
+  Fq s = PTAU_FQ2_M(fq_add(a.c0, a.c1), fq_add(b.c0, b.c1));
   Fq2 r;
   r.c0 = fq_sub(v0, v1);
   r.c1 = fq_sub(fq_sub(s, v0), v1);
@@ -80,9 +88,9 @@ PTAU_HD Fq2 fq2_mul_inl(const Fq2& a, const Fq2& b) {
 }
 // complex squaring: 2 Fq multiplications
 PTAU_HD Fq2 fq2_sqr_inl(const Fq2& a) {
-  Fq t = fq_mul(a.c0, a.c1);
+  Fq t = PTAU_FQ2_M(a.c0, a.c1);
   Fq2 r;
-  r.c0 = fq_mul(fq_add(a.c0, a.c1), fq_sub(a.c0, a.c1));
+  r.c0 = PTAU_FQ2_M(fq_add(a.c0, a.c1), fq_sub(a.c0, a.c1));
   r.c1 = fq_dbl(t);
   return r;
 }

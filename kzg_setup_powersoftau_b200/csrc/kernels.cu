@@ -24,6 +24,9 @@ namespace ptau {
 #ifndef PTAU_MINBLOCKS_G1
 #define PTAU_MINBLOCKS_G1 2
 #endif
+#ifndef PTAU_MINBLOCKS_G2
+#define PTAU_MINBLOCKS_G2 2
+#endif
 
 __device__ __forceinline__ uint4 ld_stream(const uint4* p) {
   uint4 v;
@@ -50,7 +53,7 @@ __device__ __forceinline__ void stage_out(uint32_t* __restrict__ g, const uint32
 }
 
 template <int G, int INFMT, int OUTFMT, bool HEAVY>
-__global__ void __launch_bounds__(PTAU_BLOCK, (G == PTAU_G1 ? PTAU_MINBLOCKS_G1 : 1))
+__global__ void __launch_bounds__(PTAU_BLOCK, (G == PTAU_G1 ? PTAU_MINBLOCKS_G1 : PTAU_MINBLOCKS_G2))
     convert_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint64_t n, uint32_t checks,
                    uint64_t base_index, unsigned long long* __restrict__ status) {
   constexpr int WIN = record_bytes(G, INFMT) / 4;
