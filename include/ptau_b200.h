@@ -197,6 +197,13 @@ int ptau_load_phase1(ptau_ctx* ctx, const void* data, uint64_t len, uint64_t m, 
 int ptau_preprocess_files(ptau_ctx* ctx, int variant, const char* response_path, const char* setup_path,
                           const char* uncompressed_path, unsigned log2_powers, const char* expected_digest_hex,
                           unsigned flags, unsigned checks, uint64_t* bad_index, int* bad_kind, int* bad_section);
+/* load_kzg_setup / load_fastkzg_setup from the file itself (src/lib.rs:174-228), streamed
+ * through pinned slabs.  n_powers = 0 infers n from the file size (*n_powers_out receives it).
+ * Call once with g1_out = g2_out = NULL and zero lengths to learn n, then with buffers of
+ * n_g1*104 and n_g2*200 bytes (kgz: n_g1 = 3n+1, n_g2 = 2; fastkgz: n_g1 = 3n-1, n_g2 = n+2). */
+int ptau_load_setup_file(ptau_ctx* ctx, int variant, const char* setup_path, uint64_t n_powers, unsigned checks,
+                         void* g1_out, uint64_t g1_out_len, void* g2_out, uint64_t g2_out_len, uint64_t* n_powers_out,
+                         uint64_t* bad_index, int* bad_kind);
 /* unkeyed BLAKE2b-512 of a file as 128 hex chars + NUL (blake2b_simd, src/lib.rs:128-131) */
 int ptau_blake2b_file(const char* path, char out_hex[129]);
 

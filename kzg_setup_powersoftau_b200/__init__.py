@@ -73,30 +73,32 @@ class PtauError(Exception):
 
 # ---- pinned host buffers ---------------------------------------------------------
 class PinnedBuffer:
-    """Page-locked host memory from ptau_host_alloc, exposed as a numpy u8 array."""
+    """Page-locked host memory from ptau_host_alloc, exposed as a numpy u8 array.  The
+    memory is returned with ptau_host_free when the last numpy view of it is gone (the
+    finalizer hangs on the ctypes object every view keeps alive), so slices handed to
+    callers stay valid after the PinnedBuffer itself is dropped."""
 
     def __init__(self, nbytes: int):
+        import weakref
+
         self.nbytes = int(nbytes)
-        self._ptr = _ffi.lib().ptau_host_alloc(max(self.nbytes, 1))
-        if not self._ptr:
+        L = _ffi.lib()
+        ptr = L.ptau_host_alloc(max(self.nbytes, 1))
+        if not ptr:
             raise PtauError(_ffi.ERR_NOMEM, detail="ptau_host_alloc(%d)" % nbytes)
-        self.array = np.ctypeslib.as_array((C.c_uint8 * max(self.nbytes, 1)).from_address(self._ptr))[: self.nbytes]
+        self._ptr = ptr
+        cobj = (C.c_uint8 * max(self.nbytes, 1)).from_address(ptr)
+        weakref.finalize(cobj, L.ptau_host_free, ptr)
+        self.array = np.ctypeslib.as_array(cobj)[: self.nbytes]
 
     @property
     def ptr(self) -> int:
         return self._ptr
 
     def free(self):
-        if self._ptr:
-            self.array = None
-            _ffi.lib().ptau_host_free(self._ptr)
-            self._ptr = None
-
-    def __del__(self):
-        try:
-            self.free()
-        except Exception:
-            pass
+        """Drop this object's reference; the memory goes away with the last view."""
+        self.array = None
+        self._ptr = None
 
 
 def _as_u8(data) -> np.ndarray:
@@ -432,14 +434,35 @@ def _n_from_setup_size(variant: int, size: int) -> int:
     return q
 
 
+def _load_setup_file(variant: int, path: str, log2_powers: Optional[int], ctx: Optional["Context"], checks: int):
+    """ptau_load_setup_file: the file is streamed through pinned slabs in C++; the records
+    land in pinned buffers owned by the returned arrays."""
+    L = _ffi.lib()
+    ctx = ctx or default_context()
+    if not os.path.exists(path):
+        raise FileNotFoundError(path)  # File::open(KZG_SETUP_FILE).unwrap()
+    n_in = (1 << log2_powers) if log2_powers is not None else 0
+    n_out, bad_i, bad_k = C.c_uint64(0), C.c_uint64(0), C.c_int(0)
+    rc = L.ptau_load_setup_file(ctx._h, variant, path.encode(), n_in, checks, None, 0, None, 0, C.byref(n_out),
+                                C.byref(bad_i), C.byref(bad_k))
+    if rc != 0:
+        raise PtauError(rc, detail="%s: %d bytes is not a kzg_setup of this variant/size" % (path, os.path.getsize(path)))
+    n = n_out.value
+    fast = variant == VARIANT_FASTKGZ
+    n_g1, n_g2 = 3 * n - 1 + (0 if fast else 2), (n + 2 if fast else 2)
+    b1, b2 = PinnedBuffer(n_g1 * 104), PinnedBuffer(n_g2 * 200)
+    rc = L.ptau_load_setup_file(ctx._h, variant, path.encode(), n, checks, b1.ptr, b1.nbytes, b2.ptr, b2.nbytes,
+                                C.byref(n_out), C.byref(bad_i), C.byref(bad_k))
+    if rc != 0:
+        ctx._raise(rc, bad_i.value if rc > 0 else None)
+    return n, b1.array.reshape(n_g1, 104), b2.array.reshape(n_g2, 200)  # views keep the pinned memory alive
+
+
 def load_kzg_setup(path: str = KZG_SETUP_FILE, log2_powers: Optional[int] = None, ctx: Optional[Context] = None,
                    checks: int = CHECKS_LOAD) -> Tuple[Powers, VerifierKey]:
     """src/lib.rs:174-195.  log2_powers None infers n from the file size (the
     reference hard-codes 21).  checks=CHECKS_STRICT gives the validated load."""
-    data = np.fromfile(path, dtype=np.uint8)
-    n = (1 << log2_powers) if log2_powers is not None else _n_from_setup_size(VARIANT_KGZ, data.size)
-    ctx = ctx or default_context()
-    g1, g2 = ctx.load_setup(VARIANT_KGZ, data, n, checks)
+    n, g1, g2 = _load_setup_file(VARIANT_KGZ, path, log2_powers, ctx, checks)
     powers = Powers(powers_of_g=g1[: 2 * n - 1], powers_of_gamma_g=g1[2 * n - 1: 3 * n - 1])
     vk = VerifierKey(g=g1[3 * n - 1], gamma_g=g1[3 * n], h=g2[0], beta_h=g2[1])
     return powers, vk
@@ -448,10 +471,7 @@ def load_kzg_setup(path: str = KZG_SETUP_FILE, log2_powers: Optional[int] = None
 def load_fastkzg_setup(path: str = KZG_SETUP_FILE, log2_powers: Optional[int] = None, ctx: Optional[Context] = None,
                        checks: int = CHECKS_LOAD) -> Tuple[UniversalParams, np.ndarray]:
     """src/lib.rs:197-228."""
-    data = np.fromfile(path, dtype=np.uint8)
-    n = (1 << log2_powers) if log2_powers is not None else _n_from_setup_size(VARIANT_FASTKGZ, data.size)
-    ctx = ctx or default_context()
-    g1, g2 = ctx.load_setup(VARIANT_FASTKGZ, data, n, checks)
+    n, g1, g2 = _load_setup_file(VARIANT_FASTKGZ, path, log2_powers, ctx, checks)
     powers_of_h = g2[2:]
     params = UniversalParams(
         powers_of_g=g1[: 2 * n - 1], powers_of_gamma_g=g1[2 * n - 1: 3 * n - 1], h=g2[0], beta_h=powers_of_h[1],

@@ -109,6 +109,11 @@ _SIGNATURES = {
         [C.c_void_p, C.c_int, C.c_char_p, C.c_char_p, C.c_char_p, C.c_uint, C.c_char_p, C.c_uint, C.c_uint,
          C.POINTER(C.c_uint64), C.POINTER(C.c_int), C.POINTER(C.c_int)],
     ),
+    "ptau_load_setup_file": (
+        C.c_int,
+        [C.c_void_p, C.c_int, C.c_char_p, C.c_uint64, C.c_uint, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64,
+         C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_int)],
+    ),
     "ptau_blake2b_file": (C.c_int, [C.c_char_p, C.c_char_p]),
     "ptau_microbench": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 }

@@ -258,4 +258,92 @@ int ptau_preprocess_files(ptau_ctx* ctx, int variant, const char* response_path,
   return rc;
 }
 
+// load_kzg_setup / load_fastkzg_setup (/root/reference/src/lib.rs:174-228) from the file:
+// `kzg_setup` is streamed through pinned slabs; records land in the caller's buffers
+// (pin them with ptau_host_alloc for full PCIe speed).  n_powers == 0 infers n from the file
+// size (the reference hard-codes 2^21).
+int ptau_load_setup_file(ptau_ctx* ctx, int variant, const char* setup_path, uint64_t n_powers, unsigned checks,
+                         void* g1_out, uint64_t g1_out_len, void* g2_out, uint64_t g2_out_len, uint64_t* n_powers_out,
+                         uint64_t* bad_index, int* bad_kind) {
+  if (!ctx || !setup_path) return PTAU_ERR_ARG;
+  if (variant != PTAU_VARIANT_KGZ && variant != PTAU_VARIANT_FASTKGZ) return PTAU_ERR_ARG;
+  const bool fast = variant == PTAU_VARIANT_FASTKGZ;
+  int fd = open(setup_path, O_RDONLY);
+  if (fd < 0) return PTAU_ERR_IO;
+  struct stat st;
+  if (fstat(fd, &st) != 0) {
+    close(fd);
+    return PTAU_ERR_IO;
+  }
+  uint64_t n = n_powers;
+  if (n == 0) {  // kgz: (3n-1)*96 + 576 ; fastkgz: (3n-1)*96 + 384 + n*192
+    const uint64_t sz = (uint64_t)st.st_size;
+    const uint64_t num = fast ? sz + 96 - 384 : sz + 96 - 576, den = fast ? 480 : 288;
+    if (sz < 1000 || num % den) {
+      close(fd);
+      return PTAU_ERR_SIZE;
+    }
+    n = num / den;
+  }
+  if (n_powers_out) *n_powers_out = n;
+  if ((uint64_t)st.st_size != ptau_setup_size(variant, n)) {  // the reference's unwrap() panics on a short file
+    close(fd);
+    return PTAU_ERR_SIZE;
+  }
+  const uint64_t n_g1 = 3 * n - 1 + (fast ? 0 : 2), n_g2 = fast ? n + 2 : 2;
+  if (!g1_out || !g2_out) {  // size query
+    close(fd);
+    return (g1_out_len == 0 && g2_out_len == 0) ? PTAU_OK : PTAU_ERR_ARG;
+  }
+  if (g1_out_len != n_g1 * 104 || g2_out_len != n_g2 * 200) {
+    close(fd);
+    return PTAU_ERR_SIZE;
+  }
+  const size_t slab = (size_t)((2 * n) < (1u << 20) ? (2 * n) : (1u << 20));
+  Pinned b0(slab * 192), b1(slab * 192);
+  if (!b0.p || !b1.p) {
+    close(fd);
+    return PTAU_ERR_NOMEM;
+  }
+  uint8_t* buf[2] = {b0.u8(), b1.u8()};
+  const struct {
+    int group;
+    uint64_t count;
+    uint8_t* out;
+  } secs[2] = {{PTAU_G1, n_g1, (uint8_t*)g1_out}, {PTAU_G2, n_g2, (uint8_t*)g2_out}};
+  int rc = PTAU_OK;
+  uint64_t off = 0, base = 0;
+  for (int s = 0; s < 2 && rc == PTAU_OK; s++) {
+    const size_t ri = ptau_record_size(secs[s].group, PTAU_FMT_ARK_UNCOMPRESSED);
+    const size_t ro = ptau_record_size(secs[s].group, PTAU_FMT_ARK_MONT_LIMBS);
+    const uint64_t cnt = secs[s].count, nslab = (cnt + slab - 1) / slab;
+    std::future<bool> rd = std::async(std::launch::async, pread_all, fd, buf[0], (size_t)((cnt < slab ? cnt : slab) * ri), off);
+    for (uint64_t k = 0; k < nslab && rc == PTAU_OK; k++) {
+      const int b = (int)(k & 1);
+      const uint64_t lo = k * slab;
+      const size_t c = (size_t)(cnt - lo < slab ? cnt - lo : slab);
+      if (!rd.get()) rc = PTAU_ERR_IO;
+      if (k + 1 < nslab) {
+        const uint64_t lo2 = (k + 1) * slab;
+        rd = std::async(std::launch::async, pread_all, fd, buf[b ^ 1], (size_t)((cnt - lo2 < slab ? cnt - lo2 : slab) * ri),
+                        off + lo2 * ri);
+      }
+      if (rc != PTAU_OK) break;
+      uint64_t bi = 0;
+      int bk = 0;
+      rc = ptau_convert(ctx, secs[s].group, PTAU_FMT_ARK_UNCOMPRESSED, buf[b], PTAU_FMT_ARK_MONT_LIMBS, secs[s].out + lo * ro, c,
+                        checks, &bi, &bk);
+      if (rc > 0) {
+        if (bad_index) *bad_index = base + lo + bi;  // index over all points in file order
+        if (bad_kind) *bad_kind = bk;
+      }
+    }
+    if (rd.valid()) rd.wait();
+    off += cnt * ri;
+    base += cnt;
+  }
+  close(fd);
+  return rc;
+}
+
 }  // extern "C"

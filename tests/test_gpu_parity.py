@@ -74,6 +74,16 @@ def test_loader_api_mirrors_reference(ctx, tmp_path):
     params, ph = kz.load_fastkzg_setup(str(tmp_path / "kzg_setup"), ctx=ctx)
     assert ph.shape == (n, 200) and params.beta_h.tobytes() == ph[1].tobytes() == params.prepared_beta_h_src.tobytes()
     assert params.neg_powers_of_h == {}
+    # the returned arrays own their pinned memory: still valid after a garbage collection
+    import gc
+
+    keep = params.powers_of_g[3].copy()
+    del params
+    gc.collect()
+    assert ph[1].tobytes() == o.g2_mont_record(*o.load_fastkzg_setup(golden("n8_kzg_setup_fastkgz.bin"), n)[5][1])
+    assert keep.tobytes() == o.g1_mont_record(*pg[3])
+    # validated load of the same file
+    kz.load_fastkzg_setup(str(tmp_path / "kzg_setup"), ctx=ctx, checks=STRICT)
     # truncated file: the reference's unwrap() panics
     (tmp_path / "kzg_setup").write_bytes(golden("n8_kzg_setup_kgz.bin")[:-7])
     with pytest.raises(kz.PtauError):
