@@ -64,7 +64,9 @@ extern "C" {
 /* checks bitmask.  Encoding canonicity (coordinates < p, legal flag bits) is
  * always enforced -- the reference has no path that skips it. */
 #define PTAU_CHECK_ON_CURVE 2u        /* y^2 = x^3 + 4 (G2: + 4(1+u)); stricter than ark 0.2   */
-#define PTAU_CHECK_SUBGROUP 4u        /* G1: phi(P) = -[z^2]P ; G2: on-curve and psi(P) = [z]P  */
+#define PTAU_CHECK_SUBGROUP 4u        /* same boolean as ark's multiplication by r on EVERY input: */
+                                      /* G1 phi(P) = -[z^2]P; G2 psi(P) = [z]P on the twist, and   */
+                                      /* the r-multiplication itself for off-curve G2 points       */
 #define PTAU_CHECK_REJECT_INFINITY 8u /* point at infinity is an error                          */
 /* reference-exact presets */
 #define PTAU_CHECKS_LOAD 0u                     /* deserialize_unchecked, src/lib.rs:180        */

@@ -192,4 +192,54 @@ PTAU_HD_NOINLINE bool g2_in_subgroup(const Fq2& x, const Fq2& y) {
   return jac_eq_affine(q, px, fq2_neg(py));
 }
 
+// ---------------------------------------------------------------------------
+// Reference-exact fallback for G2 points that are NOT on the twist (only reachable
+// with PTAU_CHECKS_READ, i.e. when the caller asks for the reference's behaviour and
+// not for the on-curve test).  ark-ec 0.2.0 does not test the curve equation in
+// deserialize_uncompressed; it multiplies by r with formulas that never use b, so an
+// off-curve (x, y) is accepted iff it is r-torsion on the curve y^2 = x^3 + b' it
+// happens to lie on.  psi is not an endomorphism of those curves, so the only way to
+// reproduce that boolean is the multiplication by r itself:
+//   res = 0; for each bit of r, MSB first: res = 2 res; if bit: res = res + P
+// with the special cases of add_assign_mixed (res == 0 -> P; res == P -> double).
+// ---------------------------------------------------------------------------
+#ifdef __CUDACC__
+__constant__ uint32_t K_R_ORDER_D[8] = {0x00000001u, 0xffffffffu, 0xfffe5bfeu, 0x53bda402u,
+                                        0x09a1d805u, 0x3339d808u, 0x299d7d48u, 0x73eda753u};
+#endif
+static const uint32_t K_R_ORDER_H[8] = {0x00000001u, 0xffffffffu, 0xfffe5bfeu, 0x53bda402u,
+                                        0x09a1d805u, 0x3339d808u, 0x299d7d48u, 0x73eda753u};
+
+PTAU_HD_NOINLINE bool g2_rmul_is_zero(const Fq2& x, const Fq2& y) {
+#ifdef __CUDA_ARCH__
+  const uint32_t* r = K_R_ORDER_D;
+#else
+  const uint32_t* r = K_R_ORDER_H;
+#endif
+  Jac<Fq2> acc;
+  acc.X = fq2_zero();
+  acc.Y = fq2_one();
+  acc.Z = fq2_zero();
+#pragma unroll 1
+  for (int i = 254; i >= 0; --i) {
+    if (!fq2_is_zero(acc.Z)) jac_dbl(acc);  // doubling of zero is zero; a point with Y = 0 doubles to Z = 0
+    if ((r[i >> 5] >> (i & 31)) & 1u) {
+      if (fq2_is_zero(acc.Z)) {
+        acc.X = x;
+        acc.Y = y;
+        acc.Z = fq2_one();
+      } else {
+        Fq2 zz = fq2_sqr(acc.Z);
+        Fq2 u2 = fq2_mul(x, zz);
+        Fq2 s2 = fq2_mul(fq2_mul(y, acc.Z), zz);
+        if (fq2_eq(u2, acc.X) && fq2_eq(s2, acc.Y))
+          jac_dbl(acc);
+        else
+          jac_madd(acc, x, y);  // opposite points: H = 0 gives Z3 = 0, i.e. zero
+      }
+    }
+  }
+  return fq2_is_zero(acc.Z);
+}
+
 }  // namespace ptau

@@ -257,6 +257,7 @@ PTAU_HD uint32_t g2_process(const uint32_t* in, int out_fmt, uint32_t* out, uint
   uint32_t st = PTAU_OK;
   bool inf = false;
   bool have_mont = false;
+  bool off_curve = false;
 
   if (INFMT == PTAU_FMT_ZCASH_COMPRESSED) {
     xp.c1 = fq_from_be_words(in);
@@ -317,8 +318,9 @@ PTAU_HD uint32_t g2_process(const uint32_t* in, int out_fmt, uint32_t* out, uint
       st = PTAU_BAD_NON_CANONICAL;
     }
     inf = (fl == 1u);
-    // psi is an endomorphism of the twist only: the G2 subgroup test implies the
-    // on-curve test.
+    // psi is an endomorphism of the twist only, so the psi test is used on points of the
+    // twist; an off-curve point is an error under PTAU_CHECK_ON_CURVE and otherwise takes
+    // the reference's own multiplication by r (curve.cuh: g2_rmul_is_zero).
     bool need = (checks & (PTAU_CHECK_ON_CURVE | PTAU_CHECK_SUBGROUP)) && !inf;
     if (st == PTAU_OK && (need || out_fmt == PTAU_FMT_ARK_MONT_LIMBS)) {
       xm.c0 = fq_to_mont(xp.c0);
@@ -326,11 +328,18 @@ PTAU_HD uint32_t g2_process(const uint32_t* in, int out_fmt, uint32_t* out, uint
       ym.c0 = fq_to_mont(yp.c0);
       ym.c1 = fq_to_mont(yp.c1);
       have_mont = true;
-      if (HEAVY && need && !g2_on_curve(xm, ym)) st = PTAU_BAD_NOT_ON_CURVE;
+      if (HEAVY && need && !g2_on_curve(xm, ym)) {
+        if (checks & PTAU_CHECK_ON_CURVE) {
+          st = PTAU_BAD_NOT_ON_CURVE;
+        } else {
+          off_curve = true;
+          if (!g2_rmul_is_zero(xm, ym)) st = PTAU_BAD_NOT_IN_SUBGROUP;
+        }
+      }
     }
   }
   if (st == PTAU_OK && inf && (checks & PTAU_CHECK_REJECT_INFINITY)) st = PTAU_BAD_INFINITY;
-  if (HEAVY && st == PTAU_OK && !inf && (checks & PTAU_CHECK_SUBGROUP)) {
+  if (HEAVY && st == PTAU_OK && !inf && !off_curve && (checks & PTAU_CHECK_SUBGROUP)) {
     if (!g2_in_subgroup(xm, ym)) st = PTAU_BAD_NOT_IN_SUBGROUP;
   }
 

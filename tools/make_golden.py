@@ -109,8 +109,9 @@ def add(desc, group, in_fmt, rec):
 
     entry = {"desc": desc, "group": group, "in_fmt": in_fmt, "rec": rec.hex(), "strict": status_of(strict),
              "nocheck": status_of(lambda: un(rec))}
-    if group == 1:  # G1 subgroup-only mode is reference-exact on every input
-        entry["read"] = status_of(lambda: rd(rec, False))
+    # subgroup-only mode is reference-exact on every input (G1: the GLV test is; G2: off-curve
+    # points fall back to the multiplication by r)
+    entry["read"] = status_of(lambda: rd(rec, False))
     cases.append(entry)
 
 
@@ -183,6 +184,13 @@ k = 7
 tw = (k * k * q1[0] % P, k ** 3 * q1[1] % P)
 add("r-torsion point of the isomorphic curve y^2=x^3+4*7^6 (ark 0.2 accepts; strict rejects)", 1, 1,
     o.zcash_g1_uncompressed_encode(tw))
+kk = (5, 3)  # same for G2 with k in Fq2
+k2, k3 = o.fq2_sqr(kk), o.fq2_mul(o.fq2_sqr(kk), kk)
+tw2 = (o.fq2_mul(k2, q2[0]), o.fq2_mul(k3, q2[1]))
+assert not o.g2_on_curve(tw2) and o.g2_in_subgroup_rmul(tw2)
+add("r-torsion point of the isomorphic twist y^2=x^3+4(1+u)(5+3u)^6 (ark 0.2 accepts; strict rejects)", 2, 1,
+    o.zcash_g2_uncompressed_encode(tw2))
+add("same, ark encoding", 2, 3, o.ark_g2_serialize_uncompressed(tw2))
 # on curve, outside the subgroup
 cnt = 0
 while cnt < 4:
