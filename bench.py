@@ -316,7 +316,11 @@ def main():
         achieved = N * FQMUL["g1_unc"] * IMAD_PER_FQMUL / kernel_s
         line["roofline"] = {
             "bound": "imad", "achieved": achieved / 1e12, "peak": mb["imad32"] / 1e12, "unit": "TIMAD/s",
-            "frac": achieved / mb["imad32"], "traffic": None,
+            "frac": achieved / mb["imad32"],
+            # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel at 2^20 points, from the
+            # ncu --set full capture in profiles/r01_final_ncu_full_headline_g1unc.csv (104.1 MB + 52.9 MB;
+            # algorithmic 201.3 MB -- part of the output is still in L2 when the kernel ends)
+            "traffic": 157.0e6 * (N / float(1 << 20)),
             "note": "integer-multiply bound, not hbm/tensor: achieved = %d Fq-mul/point x 588 IMAD (SURVEY 8d) x points / "
                     "CUDA-event launch time; peak = 32-bit IMAD microbenchmark measured in this run (148 SM x 64/clk). "
                     "HBM traffic is 192 B/point = %.2f GB/s, <0.1%% of %.0f GB/s" % (

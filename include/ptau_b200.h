@@ -209,6 +209,12 @@ int ptau_load_setup_file(ptau_ctx* ctx, int variant, const char* setup_path, uin
 /* unkeyed BLAKE2b-512 of a file as 128 hex chars + NUL (blake2b_simd, src/lib.rs:128-131) */
 int ptau_blake2b_file(const char* path, char out_hex[129]);
 
+/* ---- self-test hook --------------------------------------------------------------- */
+/* Raw Fq operations on n pairs of 48-byte Montgomery-limb values (host pointers), computed by
+ * the kernels' own field code on the GPU: op 0 mul, 1 add, 2 sub, 3 neg, 4 sqr, 5 a^((p-3)/4),
+ * 6 inverse.  Lets tests drive the PTX carry chains with chosen limb patterns. */
+int ptau_selftest_fq_op(ptau_ctx* ctx, int gpu, int op, const void* a, const void* b, void* out, size_t n);
+
 /* ---- microbenchmarks used by bench.py for the IMAD roofline denominator ------ */
 /* Runs `iters` dependent-chain iterations per thread; returns elapsed ms (CUDA
  * events) in *ms and the number of instructions of the class issued in *ops.

@@ -686,6 +686,29 @@ int ptau_load_phase1(ptau_ctx* ctx, const void* data, uint64_t len, uint64_t m, 
                       bad_kind, &sec);
 }
 
+int ptau_selftest_fq_op(ptau_ctx* ctx, int gpu, int op, const void* a, const void* b, void* out, size_t n) {
+  if (!ctx || gpu < 0 || gpu >= ctx->n_gpus || !a || !b || !out) return PTAU_ERR_ARG;
+  GpuSlot& s = ctx->gpu[gpu];
+  CUDA_TRY(ctx, cudaSetDevice(s.device));
+  void *da = nullptr, *db = nullptr, *dout = nullptr;
+  CUDA_TRY(ctx, cudaMalloc(&da, n * 48 + 16));
+  CUDA_TRY(ctx, cudaMalloc(&db, n * 48 + 16));
+  CUDA_TRY(ctx, cudaMalloc(&dout, n * 48 + 16));
+  cudaError_t e = cudaMemcpyAsync(da, a, n * 48, cudaMemcpyHostToDevice, s.stream[0]);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(db, b, n * 48, cudaMemcpyHostToDevice, s.stream[0]);
+  if (e == cudaSuccess) e = ptau::launch_fq_op(op, da, db, dout, n, s.stream[0]);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(out, dout, n * 48, cudaMemcpyDeviceToHost, s.stream[0]);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s.stream[0]);
+  cudaFree(da);
+  cudaFree(db);
+  cudaFree(dout);
+  if (e != cudaSuccess) {
+    ctx->last_error = std::string("selftest: ") + cudaGetErrorString(e);
+    return PTAU_ERR_CUDA;
+  }
+  return PTAU_OK;
+}
+
 int ptau_microbench(ptau_ctx* ctx, int gpu, int kind, int iters, double* ms, double* ops) {
   if (!ctx || gpu < 0 || gpu >= ctx->n_gpus || !ms || !ops || iters < 1) return PTAU_ERR_ARG;
   GpuSlot& s = ctx->gpu[gpu];

@@ -538,6 +538,34 @@ cudaError_t launch_generate_win(int group, int fmt, const uint32_t* s0_mont, con
 }
 
 // =============================================================================
+// self-test hook: raw field operations on caller-supplied Montgomery limbs, so that the
+// PTX carry chains themselves (not only their host emulation) can be checked against big
+// integers on carry-propagation stress patterns.  op: 0 mul, 1 add, 2 sub, 3 neg, 4 sqr,
+// 5 a^((p-3)/4), 6 inverse
+// =============================================================================
+__global__ void fq_op_kernel(int op, const Fq* __restrict__ a, const Fq* __restrict__ b, Fq* __restrict__ out, uint64_t n) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fq x = a[i], y = b[i], r;
+  switch (op) {
+    case 0: r = fq_mul(x, y); break;
+    case 1: r = fq_add(x, y); break;
+    case 2: r = fq_sub(x, y); break;
+    case 3: r = fq_neg(x); break;
+    case 4: r = fq_sqr(x); break;
+    case 5: r = fq_pow_p34(x); break;
+    case 6: r = fq_inv(x); break;
+    default: r = fq_zero();
+  }
+  out[i] = r;
+}
+cudaError_t launch_fq_op(int op, const void* d_a, const void* d_b, void* d_out, uint64_t n, cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  fq_op_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(op, (const Fq*)d_a, (const Fq*)d_b, (Fq*)d_out, n);
+  return cudaGetLastError();
+}
+
+// =============================================================================
 // microbenchmarks: the measured denominators of the IMAD roofline
 // =============================================================================
 // kind 0: 32-bit IMAD, 8 independent dependent-chains per thread

@@ -18,6 +18,8 @@ cudaError_t launch_generate(int group, int fmt, const uint32_t* d_scalars, void*
 cudaError_t launch_generate_win(int group, int fmt, const uint32_t* s0_mont, const uint32_t (*pw_mont)[8],
                                 const uint32_t* d_tbl, void* d_out, uint64_t first, uint64_t n, cudaStream_t stream);
 
+cudaError_t launch_fq_op(int op, const void* d_a, const void* d_b, void* d_out, uint64_t n, cudaStream_t stream);
+
 cudaError_t launch_microbench(int kind, int iters, uint32_t* d_out, int grid, int block, double* ops,
                               cudaStream_t stream);
 

@@ -30,6 +30,54 @@ def test_native_library_is_the_path():
     assert "libptau_b200.so" in maps
 
 
+def test_field_ops_on_gpu_carry_stress(ctx):
+    """The PTX carry chains themselves (IMAD.WIDE rows, dedicated squaring, add/sub) on limb
+    patterns that force every carry path, against Python big integers."""
+    import ctypes
+
+    P = o.P
+    rinv = pow(o.MONT_R, -1, P)
+    rnd = random.Random(2026)
+    pats = [0, 1, 2, 0x7FFFFFFF, 0x80000000, 0xFFFFFFFE, 0xFFFFFFFF, 0xFFFF0000, 0x0000FFFF, 0xAAAAAAAA, 0x55555555]
+    vals = []
+    for _ in range(3000):
+        v = 0
+        for i in range(12):
+            v |= rnd.choice(pats) << (32 * i)
+        vals.append((v & ((1 << 381) - 1)) % P)
+    for k in range(1, 12):
+        vals += [(1 << (32 * k)) - 1, 1 << (32 * k), (1 << (32 * k)) + 1, P - (1 << (32 * k)), P - (1 << (32 * k)) - 1]
+    vals += [0, 1, P - 1, P - 2, o.MONT_R, (P - 1) // 2, (P + 1) // 2] + [rnd.randrange(P) for _ in range(2000)]
+    vals = [v % P for v in vals]
+    n = len(vals)
+    a = vals
+    b = [vals[(7 * i + 3) % n] for i in range(n)]
+    abuf = b"".join(v.to_bytes(48, "little") for v in a)
+    bbuf = b"".join(v.to_bytes(48, "little") for v in b)
+    L = kz._ffi.lib()
+
+    def run(op):
+        out = ctypes.create_string_buffer(n * 48)
+        assert L.ptau_selftest_fq_op(ctx._h, 0, op, abuf, bbuf, out, n) == 0
+        return [int.from_bytes(out.raw[i * 48:(i + 1) * 48], "little") for i in range(n)]
+
+    assert run(0) == [x * y * rinv % P for x, y in zip(a, b)]
+    assert run(4) == [x * x * rinv % P for x in a]
+    assert run(1) == [(x + y) % P for x, y in zip(a, b)]
+    assert run(2) == [(x - y) % P for x, y in zip(a, b)]
+    assert run(3) == [(-x) % P for x in a]
+    # exponentiation chain and Fermat inverse on Montgomery-form inputs
+    am = [x * o.MONT_R % P for x in a[:200]]
+    abuf2 = b"".join(v.to_bytes(48, "little") for v in am)
+    out = ctypes.create_string_buffer(200 * 48)
+    assert L.ptau_selftest_fq_op(ctx._h, 0, 5, abuf2, abuf2, out, 200) == 0
+    got = [int.from_bytes(out.raw[i * 48:(i + 1) * 48], "little") for i in range(200)]
+    assert got == [pow(x, (P - 3) // 4, P) * o.MONT_R % P for x in a[:200]]
+    assert L.ptau_selftest_fq_op(ctx._h, 0, 6, abuf2, abuf2, out, 200) == 0
+    got = [int.from_bytes(out.raw[i * 48:(i + 1) * 48], "little") for i in range(200)]
+    assert got == [(pow(x, -1, P) if x else 0) * o.MONT_R % P for x in a[:200]]
+
+
 # ---- golden fixtures ----------------------------------------------------------------
 @pytest.mark.parametrize("variant,name", [(kz.VARIANT_KGZ, "kgz"), (kz.VARIANT_FASTKGZ, "fastkgz")])
 def test_preprocess_golden(ctx, variant, name):

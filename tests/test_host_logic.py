@@ -51,6 +51,41 @@ def test_limb_field_ops_match_bigints(hostemul):
         assert op(5, a * o.MONT_R % P, 0) == pow(a, (P - 3) // 4, P) * o.MONT_R % P
 
 
+def test_limb_field_ops_carry_stress(hostemul):
+    """Values built from extreme 32-bit limbs (0, 1, 2^31, 2^32-1, ...) exercise every
+    carry-propagation path of the even/odd multiplier rows and of the dedicated squaring."""
+    P = o.P
+    rinv = pow(o.MONT_R, -1, P)
+
+    def limbs(v):
+        return (ctypes.c_uint32 * 12)(*[(v >> (32 * i)) & 0xFFFFFFFF for i in range(12)])
+
+    def op(k, a, b):
+        out = (ctypes.c_uint32 * 12)()
+        hostemul.hostemul_fq_op(k, limbs(a), limbs(b), out)
+        return sum(int(out[i]) << (32 * i) for i in range(12))
+
+    rnd = random.Random(99)
+    pats = [0, 1, 2, 0x7FFFFFFF, 0x80000000, 0xFFFFFFFE, 0xFFFFFFFF, 0xFFFF0000, 0x0000FFFF, 0xAAAAAAAA, 0x55555555]
+    vals = []
+    for _ in range(400):
+        v = 0
+        for i in range(12):
+            v |= rnd.choice(pats) << (32 * i)
+        v &= (1 << 381) - 1
+        vals.append(v % P)
+    # neighbours of multiples of p-structure and of limb boundaries
+    for k in range(1, 12):
+        vals += [(1 << (32 * k)) - 1, 1 << (32 * k), (1 << (32 * k)) + 1, P - (1 << (32 * k)), P - (1 << (32 * k)) - 1]
+    vals = [v % P for v in vals]
+    for i, a in enumerate(vals):
+        b = vals[(7 * i + 3) % len(vals)]
+        assert op(0, a, b) == a * b * rinv % P
+        assert op(4, a, 0) == a * a * rinv % P
+        assert op(1, a, b) == (a + b) % P
+        assert op(2, a, b) == (a - b) % P
+
+
 def test_limb_code_on_golden_files(hostemul):
     n = 8
     body = golden("n8_powersoftau.bin")[64:]
