@@ -306,9 +306,7 @@ int ptau_status_decode(uint64_t status, uint64_t* bad_index) {
 int ptau_convert_device(ptau_ctx* ctx, int gpu, int group, int in_fmt, const void* d_in, int out_fmt, void* d_out,
                         size_t n_points, unsigned checks, uint64_t base_index, uint64_t* d_status, void* stream) {
   if (!ctx || gpu < 0 || gpu >= ctx->n_gpus || !d_status) return PTAU_ERR_ARG;
-  if (!rec_size(group, in_fmt) || !rec_size(group, out_fmt) || in_fmt == PTAU_FMT_ARK_MONT_LIMBS ||
-      out_fmt == PTAU_FMT_ZCASH_COMPRESSED)
-    return PTAU_ERR_ARG;
+  if (!rec_size(group, in_fmt) || !rec_size(group, out_fmt) || out_fmt == PTAU_FMT_ZCASH_COMPRESSED) return PTAU_ERR_ARG;
   if (((uintptr_t)d_in | (uintptr_t)d_out) & 15) return PTAU_ERR_ARG;
   CUDA_TRY(ctx, cudaSetDevice(ctx->gpu[gpu].device));
   CUDA_TRY(ctx, ptau::launch_convert(group, in_fmt, out_fmt, d_in, d_out, n_points, checks, base_index,
@@ -320,7 +318,7 @@ int ptau_convert(ptau_ctx* ctx, int group, int in_fmt, const void* in, int out_f
                  unsigned checks, uint64_t* bad_index, int* bad_kind) {
   if (!ctx || (!in && n_points)) return PTAU_ERR_ARG;  // out == NULL: validate only, nothing is copied back
   const int ri = rec_size(group, in_fmt), ro = rec_size(group, out_fmt);
-  if (!ri || !ro || in_fmt == PTAU_FMT_ARK_MONT_LIMBS || out_fmt == PTAU_FMT_ZCASH_COMPRESSED) return PTAU_ERR_ARG;
+  if (!ri || !ro || out_fmt == PTAU_FMT_ZCASH_COMPRESSED) return PTAU_ERR_ARG;
   auto t0 = std::chrono::steady_clock::now();
   const int G = ctx->n_gpus;
   const size_t chunk = ctx->chunk_points;

@@ -70,14 +70,24 @@ __global__ void __launch_bounds__(PTAU_BLOCK, (G == PTAU_G1 ? PTAU_MINBLOCKS_G1 
 
   uint32_t win[WIN];
   if (tid < nrec) {
-    const uint4* s4 = reinterpret_cast<const uint4*>(sm + tid * WIN);
+    if (WIN % 4 == 0) {
+      const uint4* s4 = reinterpret_cast<const uint4*>(sm + tid * WIN);
 #pragma unroll
-    for (int j = 0; j < WIN / 4; j++) {
-      uint4 v = s4[j];
-      win[4 * j] = v.x;
-      win[4 * j + 1] = v.y;
-      win[4 * j + 2] = v.z;
-      win[4 * j + 3] = v.w;
+      for (int j = 0; j < WIN / 4; j++) {
+        uint4 v = s4[j];
+        win[4 * j] = v.x;
+        win[4 * j + 1] = v.y;
+        win[4 * j + 2] = v.z;
+        win[4 * j + 3] = v.w;
+      }
+    } else {  // Montgomery-limb records: 104 / 200 bytes, 8-byte granular
+      const uint2* s2 = reinterpret_cast<const uint2*>(sm + tid * WIN);
+#pragma unroll
+      for (int j = 0; j < WIN / 2; j++) {
+        uint2 v = s2[j];
+        win[2 * j] = v.x;
+        win[2 * j + 1] = v.y;
+      }
     }
   }
   __syncthreads();
@@ -138,6 +148,8 @@ static cudaError_t launch_g(int in_fmt, int out_fmt, const void* d_in, void* d_o
       return launch_in<G, PTAU_FMT_ZCASH_COMPRESSED>(out_fmt, d_in, d_out, n, checks, base_index, d_status, stream);
     case PTAU_FMT_ARK_UNCOMPRESSED:
       return launch_in<G, PTAU_FMT_ARK_UNCOMPRESSED>(out_fmt, d_in, d_out, n, checks, base_index, d_status, stream);
+    case PTAU_FMT_ARK_MONT_LIMBS:
+      return launch_in<G, PTAU_FMT_ARK_MONT_LIMBS>(out_fmt, d_in, d_out, n, checks, base_index, d_status, stream);
   }
   return cudaErrorInvalidValue;
 }

@@ -184,6 +184,21 @@ PTAU_HD uint32_t g1_process(const uint32_t* in, int out_fmt, uint32_t* out, uint
       }
       have_mont = true;
     }
+  } else if (INFMT == PTAU_FMT_ARK_MONT_LIMBS) {
+    // in-memory GroupAffine (ark-ff Montgomery limbs + infinity byte) -> the serialize
+    // direction, preprocess-kgz.rs:188-194.  Limbs must be < p (ark's invariant).
+    xm = fq_from_le_words(in);
+    ym = fq_from_le_words(in + 12);
+    inf = (in[24] & 0xffu) != 0;
+    if (fq_plain_ge_p(xm) || fq_plain_ge_p(ym)) {
+      st = PTAU_BAD_NON_CANONICAL;
+      xm = fq_zero();
+      ym = fq_zero();
+    }
+    have_mont = true;
+    xp = fq_from_mont(xm);
+    yp = fq_from_mont(ym);
+    if (HEAVY && st == PTAU_OK && !inf && (checks & PTAU_CHECK_ON_CURVE) && !g1_on_curve(xm, ym)) st = PTAU_BAD_NOT_ON_CURVE;
   } else {
     if (INFMT == PTAU_FMT_ZCASH_UNCOMPRESSED) {
       xp = fq_from_be_words(in);
@@ -295,6 +310,30 @@ PTAU_HD uint32_t g2_process(const uint32_t* in, int out_fmt, uint32_t* out, uint
         yp.c1 = fq_plain_neg(yp.c1);
       }
       have_mont = true;
+    }
+  } else if (INFMT == PTAU_FMT_ARK_MONT_LIMBS) {
+    xm.c0 = fq_from_le_words(in);
+    xm.c1 = fq_from_le_words(in + 12);
+    ym.c0 = fq_from_le_words(in + 24);
+    ym.c1 = fq_from_le_words(in + 36);
+    inf = (in[48] & 0xffu) != 0;
+    if (fq_plain_ge_p(xm.c0) || fq_plain_ge_p(xm.c1) || fq_plain_ge_p(ym.c0) || fq_plain_ge_p(ym.c1)) {
+      st = PTAU_BAD_NON_CANONICAL;
+      xm = fq2_zero();
+      ym = fq2_zero();
+    }
+    have_mont = true;
+    xp.c0 = fq_from_mont(xm.c0);
+    xp.c1 = fq_from_mont(xm.c1);
+    yp.c0 = fq_from_mont(ym.c0);
+    yp.c1 = fq_from_mont(ym.c1);
+    if (HEAVY && st == PTAU_OK && !inf && (checks & (PTAU_CHECK_ON_CURVE | PTAU_CHECK_SUBGROUP)) && !g2_on_curve(xm, ym)) {
+      if (checks & PTAU_CHECK_ON_CURVE) {
+        st = PTAU_BAD_NOT_ON_CURVE;
+      } else {
+        off_curve = true;
+        if (!g2_rmul_is_zero(xm, ym)) st = PTAU_BAD_NOT_IN_SUBGROUP;
+      }
     }
   } else {
     if (INFMT == PTAU_FMT_ZCASH_UNCOMPRESSED) {

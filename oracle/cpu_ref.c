@@ -317,6 +317,14 @@ static int g1_one(int in_fmt, const uint8_t* in, int out_fmt, uint8_t* out, unsi
       if (fq_plain_largest(&yp) != (fl & 1)) { fq_neg(&ym, &ym); fq_plain_neg(&yp, &yp); }
       have_m = 1;
     }
+  } else if (in_fmt == FMT_ML) { /* in-memory GroupAffine -> serialize direction (preprocess-kgz.rs:188-194) */
+    le48_to_limbs(&xm, in); le48_to_limbs(&ym, in + 48); inf = in[96] != 0;
+    if (limbs_ge_p(xm.l) || limbs_ge_p(ym.l)) { st = BAD_NON_CANONICAL; memset(&xm, 0, sizeof xm); memset(&ym, 0, sizeof ym); }
+    have_m = 1; fq_from_mont(&xp, &xm); fq_from_mont(&yp, &ym);
+    if (st == OK && !inf && (checks & CHK_ON_CURVE)) {
+      fq l, r; fq_sqr(&l, &ym); fq_sqr(&r, &xm); fq_mul(&r, &r, &xm); fq_add(&r, &r, &FQ_B1);
+      if (!fq_eq(&l, &r)) st = BAD_NOT_ON_CURVE;
+    }
   } else {
     if (in_fmt == FMT_ZU) { be48_to_limbs(&xp, in); be48_to_limbs(&yp, in + 48); }
     else { le48_to_limbs(&xp, in); le48_to_limbs(&yp, in + 48); }
@@ -365,6 +373,15 @@ static int g2_one(int in_fmt, const uint8_t* in, int out_fmt, uint8_t* out, unsi
       fq_from_mont(&yp.c0, &ym.c0); fq_from_mont(&yp.c1, &ym.c1);
       if (fq2_plain_largest(&yp) != (fl & 1)) { fq2_neg(&ym, &ym); fq_plain_neg(&yp.c0, &yp.c0); fq_plain_neg(&yp.c1, &yp.c1); }
       have_m = 1;
+    }
+  } else if (in_fmt == FMT_ML) {
+    le48_to_limbs(&xm.c0, in); le48_to_limbs(&xm.c1, in + 48); le48_to_limbs(&ym.c0, in + 96); le48_to_limbs(&ym.c1, in + 144);
+    inf = in[192] != 0;
+    if (limbs_ge_p(xm.c0.l) || limbs_ge_p(xm.c1.l) || limbs_ge_p(ym.c0.l) || limbs_ge_p(ym.c1.l)) { st = BAD_NON_CANONICAL; memset(&xm, 0, sizeof xm); memset(&ym, 0, sizeof ym); }
+    have_m = 1; fq_from_mont(&xp.c0, &xm.c0); fq_from_mont(&xp.c1, &xm.c1); fq_from_mont(&yp.c0, &ym.c0); fq_from_mont(&yp.c1, &ym.c1);
+    if (st == OK && !inf && (checks & CHK_ON_CURVE)) {
+      fq2 l, r; fq2_sqr(&l, &ym); fq2_sqr(&r, &xm); fq2_mul(&r, &r, &xm); fq2_add(&r, &r, &FQ2_B2);
+      if (!fq2_eq(&l, &r)) st = BAD_NOT_ON_CURVE;
     }
   } else {
     if (in_fmt == FMT_ZU) { be48_to_limbs(&xp.c1, in); be48_to_limbs(&xp.c0, in + 48); be48_to_limbs(&yp.c1, in + 96); be48_to_limbs(&yp.c0, in + 144); }
@@ -417,7 +434,7 @@ static void* worker(void* arg) {
 int oracle_convert(int group, int in_fmt, const uint8_t* in, int out_fmt, uint8_t* out, size_t n, unsigned checks,
                    uint8_t* status, int nthreads) {
   init_consts();
-  if (!rec_size(group, in_fmt) || !rec_size(group, out_fmt) || in_fmt == FMT_ML || out_fmt == FMT_ZC) return -2;
+  if (!rec_size(group, in_fmt) || !rec_size(group, out_fmt) || out_fmt == FMT_ZC) return -2;
   if (nthreads <= 1) { job_t j = {group, in_fmt, out_fmt, checks, in, out, status, 0, n}; worker(&j); return 0; }
   if (nthreads > 256) nthreads = 256;
   pthread_t th[256]; job_t jobs[256];

@@ -29,11 +29,13 @@ extern "C" int hostemul_convert(int group, int in_fmt, const uint8_t* in, int ou
       if (in_fmt == PTAU_FMT_ZCASH_UNCOMPRESSED) st = one<PTAU_G1, PTAU_FMT_ZCASH_UNCOMPRESSED>(p, out_fmt, q, checks);
       else if (in_fmt == PTAU_FMT_ZCASH_COMPRESSED) st = one<PTAU_G1, PTAU_FMT_ZCASH_COMPRESSED>(p, out_fmt, q, checks);
       else if (in_fmt == PTAU_FMT_ARK_UNCOMPRESSED) st = one<PTAU_G1, PTAU_FMT_ARK_UNCOMPRESSED>(p, out_fmt, q, checks);
+      else if (in_fmt == PTAU_FMT_ARK_MONT_LIMBS) st = one<PTAU_G1, PTAU_FMT_ARK_MONT_LIMBS>(p, out_fmt, q, checks);
       else return -2;
     } else {
       if (in_fmt == PTAU_FMT_ZCASH_UNCOMPRESSED) st = one<PTAU_G2, PTAU_FMT_ZCASH_UNCOMPRESSED>(p, out_fmt, q, checks);
       else if (in_fmt == PTAU_FMT_ZCASH_COMPRESSED) st = one<PTAU_G2, PTAU_FMT_ZCASH_COMPRESSED>(p, out_fmt, q, checks);
       else if (in_fmt == PTAU_FMT_ARK_UNCOMPRESSED) st = one<PTAU_G2, PTAU_FMT_ARK_UNCOMPRESSED>(p, out_fmt, q, checks);
+      else if (in_fmt == PTAU_FMT_ARK_MONT_LIMBS) st = one<PTAU_G2, PTAU_FMT_ARK_MONT_LIMBS>(p, out_fmt, q, checks);
       else return -2;
     }
     status[i] = st;

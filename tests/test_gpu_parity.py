@@ -263,6 +263,57 @@ def test_edge_cases(ctx):
             assert st == cs[mode], (cs["desc"], mode, st)
 
 
+def test_mont_limb_input_and_differential_fuzz(ctx, cref):
+    """ARK_MONT_LIMBS input (serialize direction) round trips, and mutated / random records of
+    every input format in every check mode agree with the C oracle, record by record."""
+    n = 8
+    kgz = golden("n8_kzg_setup_kgz.bin")
+    assert ctx.convert(1, ML, golden("n8_load_kgz_g1.bin"), AU, STRICT).tobytes() == kgz[:(3 * n - 1) * 96] + kgz[-576:-384]
+    assert ctx.convert(2, ML, golden("n8_load_kgz_g2.bin"), AU, STRICT).tobytes() == kgz[-384:]
+    rnd = random.Random(777)
+    P = o.P
+    base = []
+    for _ in range(4):
+        q1 = o.g1_mul(o.G1_GEN, rnd.randrange(1, o.R_ORDER))
+        q2 = o.g2_mul(o.G2_GEN, rnd.randrange(1, o.R_ORDER))
+        base += [(1, ZU, o.zcash_g1_uncompressed_encode(q1)), (1, ZC, o.zcash_g1_compressed_encode(q1)),
+                 (1, AU, o.ark_g1_serialize_uncompressed(q1)), (1, ML, o.g1_mont_record(q1[0], q1[1], False)),
+                 (2, ZU, o.zcash_g2_uncompressed_encode(q2)), (2, ZC, o.zcash_g2_compressed_encode(q2)),
+                 (2, AU, o.ark_g2_serialize_uncompressed(q2)), (2, ML, o.g2_mont_record(q2[0], q2[1], False))]
+
+    def mutate(rec):
+        b = bytearray(rec)
+        k = rnd.randrange(4)
+        if k == 0:
+            b[rnd.randrange(len(b))] ^= 1 << rnd.randrange(8)
+        elif k == 1:
+            b[0] ^= rnd.choice([0x80, 0x40, 0x20, 0xC0, 0xE0])
+        elif k == 2:
+            pos = rnd.choice(range(0, len(b) - 47, 48))
+            b[pos:pos + 48] = rnd.choice([P, P - 1, P + 1, 0, 1, (1 << 381) - 1, (1 << 384) - 1]).to_bytes(48, "big")
+        else:
+            b[48 * rnd.randrange(len(b) // 48)] ^= rnd.choice([0x80, 0x40, 0xC0])
+        return bytes(b)
+
+    n_bad = 0
+    for g, f, rec in base:
+        recs = [rec] + [mutate(rec) for _ in range(5)] + [bytes(rnd.randrange(256) for _ in range(len(rec)))]
+        for r in recs:
+            for checks in (0, kz.CHECKS_READ, STRICT):
+                want, st = cref.convert(g, f, r, AU, checks)
+                try:
+                    got = ctx.convert(g, f, r, AU, checks).tobytes()
+                    code = 0
+                except kz.PtauError as e:
+                    code = e.code
+                assert code == st[0], (g, f, checks, r.hex())
+                if code == 0:
+                    assert got == want
+                else:
+                    n_bad += 1
+    assert n_bad > 100
+
+
 def test_empty_ragged_and_chunk_boundaries(cref):
     rnd = random.Random(31)
     tau = rnd.randrange(1, o.R_ORDER)

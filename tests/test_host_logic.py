@@ -131,6 +131,85 @@ def test_limb_code_vs_c_oracle_random(hostemul, cref):
             assert got == want and st == st2 == [0] * len(st)
 
 
+def test_mont_limb_input_round_trip(hostemul, cref):
+    """ARK_MONT_LIMBS as *input* (the serialize direction, preprocess-kgz.rs:188-194):
+    load -> serialize reproduces the file bytes; non-canonical limbs are rejected."""
+    n = 8
+    kgz = golden("n8_kzg_setup_kgz.bin")
+    g1_ml = golden("n8_load_kgz_g1.bin")
+    g2_ml = golden("n8_load_kgz_g2.bin")
+    for conv in (lambda g, i, d, of, c: _conv(hostemul, g, i, d, of, c), lambda g, i, d, of, c: cref.convert(g, i, d, of, c)):
+        out, st = conv(1, 4, g1_ml, 3, 14)
+        assert not any(st) and out == kgz[:(3 * n - 1) * 96] + kgz[-576:-384]
+        out, st = conv(2, 4, g2_ml, 3, 14)
+        assert not any(st) and out == kgz[-384:]
+        out, st = conv(2, 4, g2_ml, 1, 0)
+        assert not any(st) and o.read_g2_bytes(out[:192]) == kgz[-384:-192]
+        out, st = conv(1, 4, g1_ml[:104], 4, 0)
+        assert out == g1_ml[:104]
+        bad = bytearray(g1_ml[:208])
+        bad[104:152] = o.P.to_bytes(48, "little")  # x limbs = p: not a valid Fp384
+        out, st = conv(1, 4, bytes(bad), 3, 0)
+        assert list(st) == [0, 1]
+        inf = bytearray(g1_ml[:104])
+        inf[96] = 1
+        out, st = conv(1, 4, bytes(inf), 3, 4)
+        assert list(st) == [0] and out[95] & 0x40 and out[:95] == kgz[:95]
+        out, st = conv(1, 4, bytes(inf), 3, 14)
+        assert list(st) == [3]
+
+
+def test_differential_fuzz_c_oracle_vs_limb_code(hostemul, cref):
+    """Random and semi-valid records through both implementations, every input format and
+    check mode: status and (when accepted) output bytes must agree."""
+    rnd = random.Random(4242)
+    P = o.P
+    valid1 = [o.g1_mul(o.G1_GEN, rnd.randrange(1, o.R_ORDER)) for _ in range(6)]
+    valid2 = [o.g2_mul(o.G2_GEN, rnd.randrange(1, o.R_ORDER)) for _ in range(4)]
+
+    def mutate(rec):
+        b = bytearray(rec)
+        k = rnd.randrange(5)
+        if k == 0:
+            b[rnd.randrange(len(b))] ^= 1 << rnd.randrange(8)
+        elif k == 1:
+            b[0] ^= rnd.choice([0x80, 0x40, 0x20, 0xC0, 0xE0])
+        elif k == 2:
+            pos = rnd.choice(range(0, len(b), 48))
+            b[pos:pos + 48] = rnd.choice([P, P - 1, P + 1, 0, 1, (1 << 381) - 1, (1 << 384) - 1]).to_bytes(48, "big")
+        elif k == 3:
+            b[-1] ^= rnd.choice([0x80, 0x40, 0xC0])
+        else:
+            b[48 * rnd.randrange(len(b) // 48)] ^= rnd.choice([0x80, 0x40, 0xC0])
+        return bytes(b)
+
+    cases = []
+    for q in valid1:
+        cases += [(1, 1, o.zcash_g1_uncompressed_encode(q)), (1, 2, o.zcash_g1_compressed_encode(q)),
+                  (1, 3, o.ark_g1_serialize_uncompressed(q)), (1, 4, o.g1_mont_record(q[0], q[1], False))]
+    for q in valid2:
+        cases += [(2, 1, o.zcash_g2_uncompressed_encode(q)), (2, 2, o.zcash_g2_compressed_encode(q)),
+                  (2, 3, o.ark_g2_serialize_uncompressed(q)), (2, 4, o.g2_mont_record(q[0], q[1], False))]
+    fuzz = []
+    for g, f, rec in cases:
+        fuzz.append((g, f, rec))
+        for _ in range(6):
+            fuzz.append((g, f, mutate(rec)))
+        fuzz.append((g, f, bytes(rnd.randrange(256) for _ in range(len(rec)))))
+    n_bad = 0
+    for g, f, rec in fuzz:
+        for checks in (0, 4, 14, 8):
+            for of in (1, 3, 4):
+                a, sa = _conv(hostemul, g, f, rec, of, checks)
+                b, sb = cref.convert(g, f, rec, of, checks)
+                assert sa == sb, (g, f, checks, rec.hex())
+                if sa[0] == 0:
+                    assert a == b, (g, f, checks, of, rec.hex())
+                else:
+                    n_bad += 1
+    assert n_bad > 200  # the mutations really produce rejected records
+
+
 # ---- C ABI surface ---------------------------------------------------------------
 def _header_symbols():
     text = open(os.path.join(ROOT, "include", "ptau_b200.h")).read()
