@@ -459,38 +459,64 @@ def test_config3_compressed_full_size(ctx):
         assert 0.4 < float((flags != 0).mean()) < 0.6
 
 
-def test_config4_validated_load(ctx):
-    """load of a 2^18-power kgz file (2^22 under PTAU_TEST_FULL): validated and
-    unchecked loads return identical Montgomery limbs; limbs decode back to the file."""
-    k = 22 if os.environ.get("PTAU_TEST_FULL") else 18
+def test_config4_validated_load(ctx, tmp_path):
+    """BASELINE configs[3]: load of a 2^21-power setup (powers_of_g up to degree 2^22-2; 2^17
+    powers under PTAU_TEST_FAST), both variants, through the file loaders: validated and
+    unchecked loads return identical Montgomery limbs; limbs decode back to the file;
+    KZG10 commit sanity with the known tau; a corrupted point deep in the file is found by
+    the validated load only."""
+    k = 17 if os.environ.get("PTAU_TEST_FAST") else 21
     n = 1 << k
     tau, alpha, _ = o.derive_scalars(0xB200)
     g1 = np.concatenate([ctx.generate(1, ZU, 1, tau, 0, 2 * n - 1), ctx.generate(1, ZU, alpha, tau, 0, n)])
-    g2 = ctx.generate(2, ZU, 1, tau, 0, 2)
-    setup = np.concatenate([ctx.convert(1, ZU, g1, AU, 0), ctx.convert(1, ZU, g1[:96], AU, 0),
-                            ctx.convert(1, ZU, g1[(2 * n - 1) * 96:(2 * n) * 96], AU, 0), ctx.convert(2, ZU, g2, AU, 0)])
-    assert setup.size == o.kgz_size(n)
-    a1, a2 = ctx.load_setup(kz.VARIANT_KGZ, setup, n, kz.CHECKS_LOAD)
-    b1, b2 = ctx.load_setup(kz.VARIANT_KGZ, setup, n, STRICT)
-    assert np.array_equal(a1, b1) and np.array_equal(a2, b2)
-    assert not a1[:, 96].any() and not a1[:, 97:].any()
-    for i in (0, 1, n, 3 * n):
-        x, y, inf = o.ark_g1_deserialize_unchecked(setup[i * 96:(i + 1) * 96].tobytes())
-        assert a1[i].tobytes() == o.g1_mont_record(x, y, inf)
+    g1_ark = ctx.convert(1, ZU, g1, AU, 0)
+    del g1
+    nh = n if k <= 18 else 1 << 18  # powers_of_h of the fastkgz file (kept smaller: 192 B each)
+    g2_ark = ctx.convert(2, ZU, ctx.generate(2, ZU, 1, tau, 0, max(nh, 2)), AU, 0)
+    kgz = np.concatenate([g1_ark, g1_ark[:96], g1_ark[(2 * n - 1) * 96:(2 * n) * 96], g2_ark[:384]])
+    assert kgz.size == o.kgz_size(n)
+    path = str(tmp_path / "kzg_setup")
+    kgz.tofile(path)
+    powers, vk = kz.load_kzg_setup(path, ctx=ctx)                       # reference: unchecked
+    powers_v, vk_v = kz.load_kzg_setup(path, ctx=ctx, checks=STRICT)    # validated
+    assert powers.powers_of_g.shape == (2 * n - 1, 104) and powers.powers_of_gamma_g.shape == (n, 104)
+    assert np.array_equal(powers.powers_of_g, powers_v.powers_of_g)
+    assert np.array_equal(powers.powers_of_gamma_g, powers_v.powers_of_gamma_g)
+    assert np.array_equal(vk.h, vk_v.h) and np.array_equal(vk.beta_h, vk_v.beta_h)
+    assert not powers.powers_of_g[:, 96:].any()
+    for i in (0, 1, n, 2 * n - 2):
+        x, y, inf = o.ark_g1_deserialize_unchecked(kgz[i * 96:(i + 1) * 96].tobytes())
+        assert powers.powers_of_g[i].tobytes() == o.g1_mont_record(x, y, inf)
+    assert vk.g.tobytes() == powers.powers_of_g[0].tobytes() and vk.gamma_g.tobytes() == powers.powers_of_gamma_g[0].tobytes()
+    # serialize direction: Montgomery limbs -> ark bytes reproduces the file (round trip)
+    back = ctx.convert(1, ML, powers.powers_of_g[:4096].reshape(-1), AU, 0)
+    assert np.array_equal(back, kgz[:4096 * 96])
     # KZG10 commit sanity with the known tau: sum c_i [tau^i]G == [p(tau)]G
     coeffs = [3, 1, 4, 1, 5, 9, 2, 6]
     pts = []
     for i in range(len(coeffs)):
-        x, y, _ = o.ark_g1_deserialize_unchecked(setup[i * 96:(i + 1) * 96].tobytes())
+        x, y, _ = o.ark_g1_deserialize_unchecked(kgz[i * 96:(i + 1) * 96].tobytes())
         pts.append((x, y))
     ptau = sum(c * pow(tau, i, o.R_ORDER) for i, c in enumerate(coeffs)) % o.R_ORDER
     assert o.kzg_commit(pts, coeffs) == o.g1_mul(o.G1_GEN, ptau)
     # corrupt one point deep in the file: validated load finds it, unchecked load does not
-    setup[(2 * n + 5) * 96 + 3] ^= 0x04
-    ctx.load_setup(kz.VARIANT_KGZ, setup, n, kz.CHECKS_LOAD)
+    kgz[(2 * n + 5) * 96 + 3] ^= 0x04
+    kgz.tofile(path)
+    kz.load_kzg_setup(path, ctx=ctx)
     with pytest.raises(kz.PtauError) as e:
-        ctx.load_setup(kz.VARIANT_KGZ, setup, n, STRICT)
+        kz.load_kzg_setup(path, ctx=ctx, checks=STRICT)
     assert e.value.index == 2 * n + 5
+    del kgz, powers, powers_v
+    # UniversalParams variant (load_fastkzg_setup), n_h powers
+    m = nh
+    fast = np.concatenate([g1_ark[:(2 * m - 1) * 96], g1_ark[(2 * n - 1) * 96:(2 * n - 1 + m) * 96], g2_ark[:384], g2_ark[:m * 192]])
+    assert fast.size == o.fastkgz_size(m)
+    fast.tofile(path)
+    params, ph = kz.load_fastkzg_setup(path, ctx=ctx, checks=STRICT)
+    assert params.powers_of_g.shape == (2 * m - 1, 104) and ph.shape == (m, 200)
+    assert params.beta_h.tobytes() == ph[1].tobytes() and params.h.tobytes() == ph[0].tobytes()
+    x, y, inf = o.ark_g2_deserialize_unchecked(fast[-192:].tobytes())
+    assert ph[m - 1].tobytes() == o.g2_mont_record(x, y, inf)
 
 
 def test_multi_gpu_sharding_is_invisible(cref):
