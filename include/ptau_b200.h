@@ -218,8 +218,9 @@ int ptau_selftest_fq_op(ptau_ctx* ctx, int gpu, int op, const void* a, const voi
 /* ---- microbenchmarks used by bench.py for the IMAD roofline denominator ------ */
 /* Runs `iters` dependent-chain iterations per thread; returns elapsed ms (CUDA
  * events) in *ms and the number of instructions of the class issued in *ops.
- * kind: 0 = IMAD (32-bit), 1 = IMAD.WIDE.U32 carry chains, 2 = Fq Montgomery
- * multiplication (ops = number of Fq multiplications). */
+ * kind: 0 = IMAD (32-bit), 1 = IMAD.WIDE.U32.X carry chains, 2 = Fq Montgomery multiplication
+ * (ops = multiplications), 3 / 4 = G1 doubling loop with called / inlined multiplications (ops =
+ * doublings), 5 = plain IMAD.WIDE.U32 without carry. */
 int ptau_microbench(ptau_ctx* ctx, int gpu, int kind, int iters, double* ms, double* ops);
 
 #if defined(__GNUC__)

@@ -714,7 +714,7 @@ int ptau_microbench(ptau_ctx* ctx, int gpu, int kind, int iters, double* ms, dou
   cudaDeviceProp prop;
   CUDA_TRY(ctx, cudaGetDeviceProperties(&prop, s.device));
   const int block = 256;
-  const int grid = prop.multiProcessorCount * (kind == 2 ? 2 : (kind >= 3 ? 1 : 4));
+  const int grid = prop.multiProcessorCount * (kind == 2 ? 2 : ((kind == 3 || kind == 4) ? 1 : 4));
   uint32_t* d_out = nullptr;
   CUDA_TRY(ctx, cudaMalloc((void**)&d_out, (size_t)grid * block * 4 * 4));
   double o = 0;

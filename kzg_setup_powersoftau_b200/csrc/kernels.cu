@@ -642,6 +642,28 @@ __global__ void __launch_bounds__(256) mb_fqmul(uint32_t* out, int iters, uint32
   out[blockIdx.x * blockDim.x + threadIdx.x] = r;
 }
 
+// kind 5: plain IMAD.WIDE.U32 (64-bit accumulate, no carry in/out), 8 independent chains
+__global__ void __launch_bounds__(256) mb_imad_wide_plain(uint32_t* out, int iters, uint32_t seed) {
+  unsigned long long c0 = seed + threadIdx.x, c1 = c0 * 3, c2 = c0 * 5, c3 = c0 * 7, c4 = c0 * 11, c5 = c0 * 13, c6 = c0 * 17,
+                     c7 = c0 * 19;
+  uint32_t a = seed | 1u, b = (seed * 2654435761u) | 1u;
+#pragma unroll 1
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      asm volatile(
+          "mad.wide.u32 %0, %8, %9, %0;\n\tmad.wide.u32 %1, %8, %9, %1;\n\t"
+          "mad.wide.u32 %2, %8, %9, %2;\n\tmad.wide.u32 %3, %8, %9, %3;\n\t"
+          "mad.wide.u32 %4, %8, %9, %4;\n\tmad.wide.u32 %5, %8, %9, %5;\n\t"
+          "mad.wide.u32 %6, %8, %9, %6;\n\tmad.wide.u32 %7, %8, %9, %7;"
+          : "+l"(c0), "+l"(c1), "+l"(c2), "+l"(c3), "+l"(c4), "+l"(c5), "+l"(c6), "+l"(c7)
+          : "r"(a), "r"(b));
+    }
+  }
+  unsigned long long r = c0 ^ c1 ^ c2 ^ c3 ^ c4 ^ c5 ^ c6 ^ c7;
+  out[blockIdx.x * blockDim.x + threadIdx.x] = (uint32_t)r ^ (uint32_t)(r >> 32);
+}
+
 // kind 3 / 4: the G1 doubling loop of the subgroup ladders, with the product's non-inlined
 // fq_mul/fq_sqr (3) and with everything inlined (4): bounds the cost of the call ABI
 template <bool INL>
@@ -695,6 +717,10 @@ cudaError_t launch_microbench(int kind, int iters, uint32_t* d_out, int grid, in
     case 2:
       mb_fqmul<<<grid, block, 0, stream>>>(d_out, iters, 12345u);
       *ops = threads * iters * 2.0;
+      break;
+    case 5:
+      mb_imad_wide_plain<<<grid, block, 0, stream>>>(d_out, iters, 12345u);
+      *ops = threads * iters * 64.0;
       break;
     case 3:
       mb_dbl<false><<<grid * PTAU_MB_MINB, 128, 0, stream>>>(d_out, iters, 12345u);
