@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # PTAU_LIB selects an alternative build of the same library (A/B kernel experiments)
 LIB_PATH = os.environ.get("PTAU_LIB") or os.path.join(_HERE, "libptau_b200.so")
 
-# constants mirrored from include/ptau_b200.h (checked by tests/test_abi.py)
+# constants mirrored from include/ptau_b200.h (checked by tests/test_host_logic.py)
 G1, G2 = 1, 2
 FMT_ZCASH_UNCOMPRESSED, FMT_ZCASH_COMPRESSED, FMT_ARK_UNCOMPRESSED, FMT_ARK_MONT_LIMBS = 1, 2, 3, 4
 CHECK_ON_CURVE, CHECK_SUBGROUP, CHECK_REJECT_INFINITY = 2, 4, 8

@@ -157,20 +157,6 @@ Fr fr_to_mont(const Fr& a) {
   memcpy(r2.l, FR_R2, 32);
   return fr_mont_mul(a, r2);
 }
-Fr fr_from_mont(const Fr& a) {
-  Fr one = {{1, 0, 0, 0}};
-  return fr_mont_mul(a, one);
-}
-Fr fr_pow_mont(Fr base_m, uint64_t e, const Fr& one_m) {
-  Fr acc = one_m;
-  while (e) {
-    if (e & 1) acc = fr_mont_mul(acc, base_m);
-    base_m = fr_mont_mul(base_m, base_m);
-    e >>= 1;
-  }
-  return acc;
-}
-
 struct Section {
   int group;
   uint64_t count;

@@ -8,6 +8,10 @@
 // lands on a 64-bit aligned register pair of its accumulator and a whole row is
 // one carry chain of 6 wide MADs.
 //
+// fq_sqr_inl is the dedicated squaring (78 product MADs instead of 144).  Measured on B200:
+// IMAD 18.4 T/s, IMAD.WIDE.X carry chains 8.9 T/s (a wide carry MAD = two IMAD issue
+// slots), one multiplication = 581 slots, one squaring = 446.
+//
 // Every function is also compiled for the host (plain C emulation of the same
 // instruction sequences, including the carry flag) so that tests/host_emul can
 // check the exact limb algorithm against the oracle without a GPU.  The host

@@ -163,7 +163,8 @@ cudaError_t launch_convert(int group, int in_fmt, int out_fmt, const void* d_in,
 }
 
 // =============================================================================
-// synthetic Powers-of-Tau generator: out[i] = [k_i] G for host-supplied scalars
+// generator v1: out[i] = [k_i] G for host-supplied scalars, plain double-and-add and a
+// Fermat inversion per point.  Only used to build the fixed-base table of generator v2.
 // =============================================================================
 __constant__ uint32_t K_PM2[12] = {0xffffaaa9u, 0xb9feffffu, 0xb153ffffu, 0x1eabfffeu, 0xf6b0f624u, 0x6730d2a0u,
                                    0xf38512bfu, 0x64774b84u, 0x434bacd7u, 0x4b1ba7b6u, 0x397fe69au, 0x1a0111eau};
@@ -177,14 +178,6 @@ static __device__ __noinline__ Fq fq_inv(Fq a) {
     if ((K_PM2[i >> 5] >> (i & 31)) & 1u) acc = fq_mul(acc, a);
   }
   return acc;
-}
-
-template <class F>
-__device__ __forceinline__ void select_jac(Jac<F>& dst, const Jac<F>& a, bool take) {
-  uint32_t* d = reinterpret_cast<uint32_t*>(&dst);
-  const uint32_t* s = reinterpret_cast<const uint32_t*>(&a);
-#pragma unroll
-  for (int i = 0; i < (int)(sizeof(Jac<F>) / 4); i++) d[i] = take ? s[i] : d[i];
 }
 
 template <int G, int OUTFMT>
