@@ -382,6 +382,24 @@ def main():
                 setup.free()
             except Exception as e:  # pinned allocation of 1.2 GB may be refused on small hosts
                 extra["preprocess_kgz_2^21_fused(host->host)"] = {"error": repr(e)}
+            # SURVEY 8f-4 first step: KZG10 commit (MSM) over 2^20 powers, host -> host
+            try:
+                import numpy as np
+
+                nc = 1 << 20
+                pw = ctx.convert(kz.G1, ZU, ctx.generate(kz.G1, ZU, 1, tau, 0, nc), ML, 0)
+                sc = np.random.default_rng(1).integers(0, 256, size=nc * 32, dtype=np.uint8)
+                sc.reshape(nc, 32)[:, 31] &= 0x3F  # < 2^254 < r
+                outp = np.zeros(104, dtype=np.uint8)
+                L = kz._ffi.lib()
+                for _ in range(2):
+                    rcc = L.ptau_kzg_commit(ctx._h, pw.ctypes.data, sc.ctypes.data, nc, outp.ctypes.data)
+                assert rcc == 0
+                kms = ctx.timing()["kernel_ms"][0]
+                extra["kzg10_commit_2^20(msm, kernels only)"] = {"points": nc, "ms": kms, "points_per_s": nc / (kms / 1e3),
+                                                                  "note": "Straus interleaving, 8 points per thread; not Pippenger"}
+            except Exception as e:
+                extra["kzg10_commit_2^20(msm, kernels only)"] = {"error": repr(e)}
             hb = extra["g1_reencode_only(hbm)"]
             line["roofline_hbm"] = {"bound": "hbm", "kernel": "zcash->ark re-encode only (no checks)",
                                     "achieved": hb["GBps"], "peak": 6552.0, "unit": "GB/s",

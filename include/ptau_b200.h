@@ -209,6 +209,15 @@ int ptau_load_setup_file(ptau_ctx* ctx, int variant, const char* setup_path, uin
 /* unkeyed BLAKE2b-512 of a file as 128 hex chars + NUL (blake2b_simd, src/lib.rs:128-131) */
 int ptau_blake2b_file(const char* path, char out_hex[129]);
 
+/* ---- consumer side (first step) ---------------------------------------- */
+/* KZG10 commitment without hiding: commitment = sum_i [coeffs_i] powers_i, the multi-scalar
+ * multiplication inside ark-poly-commit 0.2 KZG10::commit (used at src/lib.rs:268-275).
+ * powers: n PTAU_FMT_ARK_MONT_LIMBS G1 records (e.g. Powers.powers_of_g from ptau_load_setup);
+ * coeffs: n scalars, 32 bytes little-endian each, canonical (< r) and NOT in Montgomery form;
+ * commitment: one 104-byte record.  A hiding commitment is commit(p, powers_of_g) +
+ * commit(blinding, powers_of_gamma_g): pass both (point, scalar) lists concatenated. */
+int ptau_kzg_commit(ptau_ctx* ctx, const void* powers, const void* coeffs, size_t n, void* commitment);
+
 /* ---- self-test hook --------------------------------------------------------------- */
 /* Raw Fq operations on n pairs of 48-byte Montgomery-limb values (host pointers), computed by
  * the kernels' own field code on the GPU: op 0 mul, 1 add, 2 sub, 3 neg, 4 sqr, 5 a^((p-3)/4),

@@ -280,6 +280,69 @@ class Context:
         return ms.value, ops.value
 
 
+R_ORDER = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001  # Fr modulus
+
+
+class KZG10:
+    """First step of SURVEY 8f-4: the commitment side of ark-poly-commit 0.2 `KZG10` on the
+    GPU (the reference's consumer usage, src/lib.rs:266-286).  Polynomials are lists of
+    coefficients (ints mod r, low degree first).  Hiding: ark draws a random polynomial of
+    degree `hiding_bound`; here the caller passes its coefficients (`blinding`) so results
+    are reproducible.  `check` / `batch_check` need pairings and stay on the CPU side
+    (out of scope); tests verify commitments and proofs against the known tau."""
+
+    @staticmethod
+    def _msm(ctx, pairs) -> np.ndarray:
+        pts = np.concatenate([np.ascontiguousarray(p[: len(c)]).reshape(-1) for p, c in pairs if len(c)] or
+                             [np.zeros(0, dtype=np.uint8)])
+        sc = b"".join((int(v) % R_ORDER).to_bytes(32, "little") for _, c in pairs for v in c)
+        n = len(sc) // 32
+        out = np.zeros(104, dtype=np.uint8)
+        scb = np.frombuffer(sc, dtype=np.uint8) if n else np.zeros(0, dtype=np.uint8)
+        rc = _ffi.lib().ptau_kzg_commit(ctx._h, _ptr(pts) if n else None, _ptr(scb) if n else None, n, _ptr(out))
+        if rc != 0:
+            ctx._raise(rc)
+        return out
+
+    @staticmethod
+    def commit(powers: "Powers", coeffs, blinding=None, ctx: Optional["Context"] = None) -> np.ndarray:
+        """KZG10::commit: sum c_i powers_of_g[i] (+ sum b_i powers_of_gamma_g[i] when hiding).
+        Returns the commitment as a 104-byte Montgomery-limb record."""
+        ctx = ctx or default_context()
+        if len(coeffs) > len(powers.powers_of_g) or (blinding and len(blinding) > len(powers.powers_of_gamma_g)):
+            raise PtauError(_ffi.ERR_ARG, detail="polynomial degree exceeds the supported degree")  # Error::TooManyCoefficients
+        pairs = [(powers.powers_of_g, list(coeffs))]
+        if blinding:
+            pairs.append((powers.powers_of_gamma_g, list(blinding)))
+        return KZG10._msm(ctx, pairs)
+
+    @staticmethod
+    def _quotient(coeffs, z):
+        """(p(X) - p(z)) / (X - z) by synthetic division; returns (p(z), quotient coefficients)."""
+        n = len(coeffs)
+        q = [0] * max(n - 1, 0)
+        carry = 0
+        for i in range(n - 1, 0, -1):
+            carry = (coeffs[i] + carry * z) % R_ORDER
+            q[i - 1] = carry
+        value = ((coeffs[0] if n else 0) + carry * z) % R_ORDER
+        return value, q
+
+    @staticmethod
+    def open(powers: "Powers", coeffs, point: int, blinding=None, ctx: Optional["Context"] = None):
+        """KZG10::open: witness commitment w = commit((p - p(z)) / (X - z)) (+ the blinding
+        polynomial's witness on powers_of_gamma_g).  Returns (value p(z), proof record,
+        random_v = blinding(z) or None)."""
+        ctx = ctx or default_context()
+        value, q = KZG10._quotient([int(c) % R_ORDER for c in coeffs], int(point) % R_ORDER)
+        pairs = [(powers.powers_of_g, q)]
+        random_v = None
+        if blinding:
+            random_v, rq = KZG10._quotient([int(c) % R_ORDER for c in blinding], int(point) % R_ORDER)
+            pairs.append((powers.powers_of_gamma_g, rq))
+        return value, KZG10._msm(ctx, pairs), random_v
+
+
 _default_ctx: Optional[Context] = None
 
 

@@ -670,6 +670,48 @@ int ptau_load_phase1(ptau_ctx* ctx, const void* data, uint64_t len, uint64_t m, 
                       bad_kind, &sec);
 }
 
+int ptau_kzg_commit(ptau_ctx* ctx, const void* powers, const void* coeffs, size_t n, void* commitment) {
+  if (!ctx || (!powers && n) || (!coeffs && n) || !commitment) return PTAU_ERR_ARG;
+  // scalars must be canonical (< r), like ark's Fr
+  for (size_t i = 0; i < n; i++) {
+    Fr c = fr_from_le32((const uint8_t*)coeffs + i * 32);
+    if (fr_ge_mod(c.l)) return PTAU_ERR_ARG;
+  }
+  GpuSlot& s = ctx->gpu[0];
+  CUDA_TRY(ctx, cudaSetDevice(s.device));
+  const size_t threads = ((n + 7) / 8 + 127) / 128 * 128;
+  void *d_pts = nullptr, *d_sc = nullptr, *d_part = nullptr, *d_out = nullptr;
+  CUDA_TRY(ctx, cudaMalloc(&d_pts, n * 104 + 16));
+  CUDA_TRY(ctx, cudaMalloc(&d_sc, n * 32 + 16));
+  CUDA_TRY(ctx, cudaMalloc(&d_part, (threads ? threads : 128) * 144));
+  CUDA_TRY(ctx, cudaMalloc(&d_out, 104));
+  cudaError_t e = cudaMemcpyAsync(d_pts, powers, n * 104, cudaMemcpyHostToDevice, s.stream[0]);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_sc, coeffs, n * 32, cudaMemcpyHostToDevice, s.stream[0]);
+  if (e == cudaSuccess) e = cudaEventRecord(s.ev_k0[0], s.stream[0]);
+  if (e == cudaSuccess) e = ptau::launch_msm_g1(d_pts, d_sc, n, d_part, d_out, s.stream[0]);
+  if (e == cudaSuccess) e = cudaEventRecord(s.ev_k1[0], s.stream[0]);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(commitment, d_out, 104, cudaMemcpyDeviceToHost, s.stream[0]);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s.stream[0]);
+  float ms = 0;
+  if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, s.ev_k0[0], s.ev_k1[0]);
+  cudaFree(d_pts);
+  cudaFree(d_sc);
+  cudaFree(d_part);
+  cudaFree(d_out);
+  if (e != cudaSuccess) {
+    ctx->last_error = std::string("kzg_commit: ") + cudaGetErrorString(e);
+    return PTAU_ERR_CUDA;
+  }
+  memset(&ctx->timing, 0, sizeof(ctx->timing));
+  ctx->timing.n_gpus = ctx->n_gpus;
+  ctx->timing.kernel_ms[0] = ms;
+  ctx->timing.gpu_ms[0] = ms;
+  ctx->timing.kernel_launches = 2;
+  ctx->timing.h2d_bytes[0] = n * 136;
+  ctx->timing.d2h_bytes[0] = 104;
+  return PTAU_OK;
+}
+
 int ptau_selftest_fq_op(ptau_ctx* ctx, int gpu, int op, const void* a, const void* b, void* out, size_t n) {
   if (!ctx || gpu < 0 || gpu >= ctx->n_gpus || !a || !b || !out) return PTAU_ERR_ARG;
   GpuSlot& s = ctx->gpu[gpu];

@@ -543,6 +543,209 @@ cudaError_t launch_generate_win(int group, int fmt, const uint32_t* s0_mont, con
 }
 
 // =============================================================================
+// SURVEY 8f-4 (first step): KZG10 commit = multi-scalar multiplication over the loaded
+// powers,  C = sum_i [c_i] P_i   (ark-poly-commit 0.2 KZG10::commit, used at
+// /root/reference/src/lib.rs:268-275).  First version: Straus interleaving, 8 points per
+// thread share one chain of 254 doublings (about 1,630 Fq-mul per point instead of 3,200
+// for independent ladders), block tree reduction, one final inversion.  Complete addition
+// rules are used where arbitrary partial sums meet (equal / opposite / infinity), because
+// the inputs here are caller data, not ladders with known-safe scalars.
+// Not Pippenger yet: a bucket method is the known next step for large n.
+// =============================================================================
+#define PTAU_MSM_K 8
+
+// acc += (x, y) with every special case of the group law
+static __device__ __noinline__ void g1_madd_complete(Jac<Fq>& acc, const Fq& x, const Fq& y) {
+  if (fq_is_zero(acc.Z)) {
+    acc.X = x;
+    acc.Y = y;
+    acc.Z = fq_one();
+    return;
+  }
+  Fq zz = fq_sqr(acc.Z);
+  Fq u2 = fq_mul(x, zz);
+  Fq s2 = fq_mul(fq_mul(y, acc.Z), zz);
+  if (fq_eq(u2, acc.X)) {
+    if (fq_eq(s2, acc.Y)) {
+      jac_dbl(acc);
+    } else {
+      acc.Z = fq_zero();  // P + (-P)
+    }
+    return;
+  }
+  jac_madd(acc, x, y);
+}
+static __device__ __noinline__ void g1_add_complete(Jac<Fq>& p, const Jac<Fq>& q) {
+  if (fq_is_zero(q.Z)) return;
+  if (fq_is_zero(p.Z)) {
+    p = q;
+    return;
+  }
+  Fq z1z1 = fq_sqr(p.Z), z2z2 = fq_sqr(q.Z);
+  Fq u1 = fq_mul(p.X, z2z2), u2 = fq_mul(q.X, z1z1);
+  Fq s1 = fq_mul(fq_mul(p.Y, q.Z), z2z2), s2 = fq_mul(fq_mul(q.Y, p.Z), z1z1);
+  if (fq_eq(u1, u2)) {
+    if (fq_eq(s1, s2)) {
+      jac_dbl(p);
+    } else {
+      p.Z = fq_zero();
+    }
+    return;
+  }
+  jac_add(p, q);
+}
+
+// points: ARK_MONT_LIMBS records (26 words); scalars: 8 x u32 LE each, < r
+__global__ void __launch_bounds__(PTAU_BLOCK)
+    msm_g1_partial(const uint32_t* __restrict__ pts, const uint32_t* __restrict__ scalars, uint64_t n,
+                   uint32_t* __restrict__ partial /* 36 words per block */) {
+  const uint64_t g = (uint64_t)blockIdx.x * PTAU_BLOCK + threadIdx.x;
+  const uint64_t i0 = g * PTAU_MSM_K;
+  Jac<Fq> acc;
+  acc.X = fq_zero();
+  acc.Y = fq_one();
+  acc.Z = fq_zero();
+  int cnt = 0;
+  if (i0 < n) cnt = (int)((n - i0) < (uint64_t)PTAU_MSM_K ? (n - i0) : (uint64_t)PTAU_MSM_K);
+  uint32_t k[PTAU_MSM_K][8];
+  uint32_t any = 0;
+#pragma unroll
+  for (int j = 0; j < PTAU_MSM_K; j++) {
+#pragma unroll
+    for (int w = 0; w < 8; w++) {
+      k[j][w] = (j < cnt) ? scalars[(i0 + j) * 8 + w] : 0u;
+      any |= k[j][w];
+    }
+    // a point flagged infinity contributes nothing
+    if (j < cnt && (pts[(i0 + j) * 26 + 24] & 0xffu)) {
+#pragma unroll
+      for (int w = 0; w < 8; w++) k[j][w] = 0u;
+    }
+  }
+  if (any) {
+#pragma unroll 1
+    for (int bit = 254; bit >= 0; --bit) {
+      if (!fq_is_zero(acc.Z)) jac_dbl(acc);
+#pragma unroll 1
+      for (int j = 0; j < PTAU_MSM_K; j++) {
+        if ((k[j][bit >> 5] >> (bit & 31)) & 1u) {
+          const uint32_t* rec = pts + (i0 + j) * 26;
+          Fq x = load_tbl_field<Fq>(rec), y = load_tbl_field<Fq>(rec + 12);
+          g1_madd_complete(acc, x, y);
+        }
+      }
+    }
+  }
+  // block tree reduction: one Jacobian partial per block
+  __shared__ uint32_t sm[PTAU_BLOCK * 36];
+  for (int stride = PTAU_BLOCK / 2; stride >= 1; stride >>= 1) {
+    uint32_t* mine = sm + threadIdx.x * 36;
+#pragma unroll
+    for (int w = 0; w < 12; w++) {
+      mine[w] = acc.X.l[w];
+      mine[12 + w] = acc.Y.l[w];
+      mine[24 + w] = acc.Z.l[w];
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < stride) {
+      const uint32_t* q32 = sm + (threadIdx.x + stride) * 36;
+      Jac<Fq> q;
+#pragma unroll
+      for (int w = 0; w < 12; w++) {
+        q.X.l[w] = q32[w];
+        q.Y.l[w] = q32[12 + w];
+        q.Z.l[w] = q32[24 + w];
+      }
+      g1_add_complete(acc, q);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    uint32_t* o = partial + (uint64_t)blockIdx.x * 36;
+#pragma unroll
+    for (int w = 0; w < 12; w++) {
+      o[w] = acc.X.l[w];
+      o[12 + w] = acc.Y.l[w];
+      o[24 + w] = acc.Z.l[w];
+    }
+  }
+}
+
+// one block: sums m Jacobian partials, writes one ARK_MONT_LIMBS record (affine or infinity)
+__global__ void __launch_bounds__(256) msm_g1_reduce(const uint32_t* __restrict__ partial, uint64_t m, uint32_t* __restrict__ out) {
+  __shared__ uint32_t sm[256 * 36];
+  Jac<Fq> acc;
+  acc.X = fq_zero();
+  acc.Y = fq_one();
+  acc.Z = fq_zero();
+  for (uint64_t i = threadIdx.x; i < m; i += 256) {
+    Jac<Fq> q;
+    const uint32_t* s = partial + i * 36;
+#pragma unroll
+    for (int w = 0; w < 12; w++) {
+      q.X.l[w] = s[w];
+      q.Y.l[w] = s[12 + w];
+      q.Z.l[w] = s[24 + w];
+    }
+    g1_add_complete(acc, q);
+  }
+  for (int stride = 128; stride >= 1; stride >>= 1) {
+    uint32_t* mine = sm + threadIdx.x * 36;
+#pragma unroll
+    for (int w = 0; w < 12; w++) {
+      mine[w] = acc.X.l[w];
+      mine[12 + w] = acc.Y.l[w];
+      mine[24 + w] = acc.Z.l[w];
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < stride) {
+      const uint32_t* s = sm + (threadIdx.x + stride) * 36;
+      Jac<Fq> q;
+#pragma unroll
+      for (int w = 0; w < 12; w++) {
+        q.X.l[w] = s[w];
+        q.Y.l[w] = s[12 + w];
+        q.Z.l[w] = s[24 + w];
+      }
+      g1_add_complete(acc, q);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    if (fq_is_zero(acc.Z)) {  // ark zero(): (0, 1, infinity)
+      Fq one = fq_one();
+#pragma unroll
+      for (int w = 0; w < 12; w++) {
+        out[w] = 0;
+        out[12 + w] = one.l[w];
+      }
+      out[24] = 1;
+      out[25] = 0;
+    } else {
+      Fq zi = fq_inv(acc.Z);
+      Fq zi2 = fq_sqr(zi);
+      Fq x = fq_mul(acc.X, zi2), y = fq_mul(acc.Y, fq_mul(zi2, zi));
+#pragma unroll
+      for (int w = 0; w < 12; w++) {
+        out[w] = x.l[w];
+        out[12 + w] = y.l[w];
+      }
+      out[24] = 0;
+      out[25] = 0;
+    }
+  }
+}
+
+cudaError_t launch_msm_g1(const void* d_pts, const void* d_scalars, uint64_t n, void* d_partial, void* d_out,
+                          cudaStream_t stream) {
+  const uint64_t threads = (n + PTAU_MSM_K - 1) / PTAU_MSM_K;
+  const unsigned grid = (unsigned)((threads + PTAU_BLOCK - 1) / PTAU_BLOCK);
+  if (grid) msm_g1_partial<<<grid, PTAU_BLOCK, 0, stream>>>((const uint32_t*)d_pts, (const uint32_t*)d_scalars, n, (uint32_t*)d_partial);
+  msm_g1_reduce<<<1, 256, 0, stream>>>((const uint32_t*)d_partial, (uint64_t)grid, (uint32_t*)d_out);
+  return cudaGetLastError();
+}
+
+// =============================================================================
 // self-test hook: raw field operations on caller-supplied Montgomery limbs, so that the
 // PTX carry chains themselves (not only their host emulation) can be checked against big
 // integers on carry-propagation stress patterns.  op: 0 mul, 1 add, 2 sub, 3 neg, 4 sqr,

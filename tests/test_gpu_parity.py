@@ -519,6 +519,62 @@ def test_config4_validated_load(ctx, tmp_path):
     assert ph[m - 1].tobytes() == o.g2_mont_record(x, y, inf)
 
 
+def test_kzg10_commit_open_known_tau(ctx, tmp_path):
+    """SURVEY 8f-4, first step: KZG10 commit / open on the GPU, mirroring the reference's
+    end_to_end_test_kzg (src/lib.rs:250-289: 10 x 10 random polynomials of degree 2..19,
+    hiding_bound 1) but verified without pairings through the known tau:
+      C = [p(tau) + alpha b(tau)] G ,   W = [w(tau) + alpha bw(tau)] G ,   p(tau) - v = (tau - z) w(tau)."""
+    n = 1 << 10
+    tau, alpha, _ = o.derive_scalars(0xB200)
+    g1 = np.concatenate([ctx.generate(1, ZU, 1, tau, 0, 2 * n - 1), ctx.generate(1, ZU, alpha, tau, 0, n)])
+    g2 = ctx.generate(2, ZU, 1, tau, 0, 2)
+    setup = np.concatenate([ctx.convert(1, ZU, g1, AU, 0), ctx.convert(1, ZU, g1[:96], AU, 0),
+                            ctx.convert(1, ZU, g1[(2 * n - 1) * 96:(2 * n) * 96], AU, 0), ctx.convert(2, ZU, g2, AU, 0)])
+    path = str(tmp_path / "kzg_setup")
+    setup.tofile(path)
+    powers, vk = kz.load_kzg_setup(path, ctx=ctx)
+    R = o.R_ORDER
+
+    def ev(c, x):
+        return sum(v * pow(x, i, R) for i, v in enumerate(c)) % R
+
+    def rec(k):
+        q = o.g1_mul(o.G1_GEN, k % R)
+        return o.g1_mont_record(0, 1, True) if q is None else o.g1_mont_record(q[0], q[1], False)
+
+    rnd = random.Random(20)
+    for _ in range(10):
+        degree = rnd.randrange(2, 20)
+        for _ in range(3):
+            p = [rnd.randrange(R) for _ in range(degree + 1)]
+            b = [rnd.randrange(R) for _ in range(2)]  # hiding_bound = Some(1)
+            comm = kz.KZG10.commit(powers, p, blinding=b, ctx=ctx)
+            assert comm.tobytes() == rec(ev(p, tau) + alpha * ev(b, tau))
+            z = rnd.randrange(R)
+            value, proof, random_v = kz.KZG10.open(powers, p, z, blinding=b, ctx=ctx)
+            assert value == ev(p, z) and random_v == ev(b, z)
+            _, w = kz.KZG10._quotient(p, z)
+            _, bw = kz.KZG10._quotient(b, z)
+            assert proof.tobytes() == rec(ev(w, tau) + alpha * ev(bw, tau))
+            assert (ev(p, tau) - value) % R == (tau - z) * ev(w, tau) % R
+    # special cases of the group law inside the MSM
+    assert kz.KZG10.commit(powers, [0, 0, 0], ctx=ctx).tobytes() == o.g1_mont_record(0, 1, True)  # zero polynomial
+    assert kz.KZG10.commit(powers, [], ctx=ctx).tobytes() == o.g1_mont_record(0, 1, True)
+    same = kz.Powers(powers_of_g=np.repeat(powers.powers_of_g[1:2], 16, axis=0), powers_of_gamma_g=powers.powers_of_gamma_g)
+    assert kz.KZG10.commit(same, [1, 1], ctx=ctx).tobytes() == rec(2 * tau)               # P + P -> doubling
+    assert kz.KZG10.commit(same, [5, R - 5], ctx=ctx).tobytes() == o.g1_mont_record(0, 1, True)  # P + (-P)
+    assert kz.KZG10.commit(same, [3] * 16, ctx=ctx).tobytes() == rec(48 * tau)
+    assert kz.KZG10.commit(same, [0, 7, 0, 0, 0, 0, 0, 0, 0, 9], ctx=ctx).tobytes() == rec(16 * tau)
+    # a full-degree polynomial against p(tau)
+    big = [rnd.randrange(R) for _ in range(2 * n - 1)]
+    assert kz.KZG10.commit(powers, big, ctx=ctx).tobytes() == rec(ev(big, tau))
+    with pytest.raises(kz.PtauError):
+        kz.KZG10.commit(powers, [1] * (2 * n), ctx=ctx)  # Error::TooManyCoefficients
+    bad = np.frombuffer((R).to_bytes(32, "little"), dtype=np.uint8)
+    out = np.zeros(104, dtype=np.uint8)
+    assert kz._ffi.lib().ptau_kzg_commit(ctx._h, powers.powers_of_g[:1].ctypes.data, bad.ctypes.data, 1, out.ctypes.data) == kz._ffi.ERR_ARG
+
+
 def test_multi_gpu_sharding_is_invisible(cref):
     """Same bytes and same first-bad-index with 1 GPU and with every GPU of the box."""
     from kzg_setup_powersoftau_b200 import _ffi
