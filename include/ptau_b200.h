@@ -229,7 +229,9 @@ int ptau_selftest_fq_op(ptau_ctx* ctx, int gpu, int op, const void* a, const voi
  * events) in *ms and the number of instructions of the class issued in *ops.
  * kind: 0 = IMAD (32-bit), 1 = IMAD.WIDE.U32.X carry chains, 2 = Fq Montgomery multiplication
  * (ops = multiplications), 3 / 4 = G1 doubling loop with called / inlined multiplications (ops =
- * doublings), 5 = plain IMAD.WIDE.U32 without carry. */
+ * doublings), 5 = IMAD.WIDE.U32 pure products without carry (measured: half rate, like 1), 6 = DFMA chains,
+ * 7 = DFMA chains in the odd warps beside IMAD.WIDE.X rows in the even warps (ops = slots of the shared
+ * FMA-heavy pipe: one per DFMA, two per wide MAD). */
 int ptau_microbench(ptau_ctx* ctx, int gpu, int kind, int iters, double* ms, double* ops);
 
 #if defined(__GNUC__)

@@ -838,26 +838,70 @@ __global__ void __launch_bounds__(256) mb_fqmul(uint32_t* out, int iters, uint32
   out[blockIdx.x * blockDim.x + threadIdx.x] = r;
 }
 
-// kind 5: plain IMAD.WIDE.U32 (64-bit accumulate, no carry in/out), 8 independent chains
+// kind 5: IMAD.WIDE.U32 with no carry in or out: eight dependent chains acc = lo(acc) * hi(acc) (pure
+// 32x32->64 products; every product is distinct, so ptxas cannot hoist it and replace the MAD by a
+// multiply plus ALU adds, which is what it does to a loop-invariant `mad.wide`).  Measured: 9.25 T/s,
+// the same half rate as the carry-chained form: a 64-bit result costs two IMAD slots, carry or not.
 __global__ void __launch_bounds__(256) mb_imad_wide_plain(uint32_t* out, int iters, uint32_t seed) {
-  unsigned long long c0 = seed + threadIdx.x, c1 = c0 * 3, c2 = c0 * 5, c3 = c0 * 7, c4 = c0 * 11, c5 = c0 * 13, c6 = c0 * 17,
-                     c7 = c0 * 19;
-  uint32_t a = seed | 1u, b = (seed * 2654435761u) | 1u;
+  unsigned long long c[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) c[i] = ((unsigned long long)(seed * (2 * i + 3) + threadIdx.x) << 32) | (seed + i * 7 + threadIdx.x) | 1ull;
 #pragma unroll 1
   for (int i = 0; i < iters; i++) {
 #pragma unroll
     for (int u = 0; u < 8; u++) {
-      asm volatile(
-          "mad.wide.u32 %0, %8, %9, %0;\n\tmad.wide.u32 %1, %8, %9, %1;\n\t"
-          "mad.wide.u32 %2, %8, %9, %2;\n\tmad.wide.u32 %3, %8, %9, %3;\n\t"
-          "mad.wide.u32 %4, %8, %9, %4;\n\tmad.wide.u32 %5, %8, %9, %5;\n\t"
-          "mad.wide.u32 %6, %8, %9, %6;\n\tmad.wide.u32 %7, %8, %9, %7;"
-          : "+l"(c0), "+l"(c1), "+l"(c2), "+l"(c3), "+l"(c4), "+l"(c5), "+l"(c6), "+l"(c7)
-          : "r"(a), "r"(b));
+#pragma unroll
+      for (int k = 0; k < 8; k++)
+        asm volatile("{.reg .u32 l, h;\n\tmov.b64 {l, h}, %0;\n\tmul.wide.u32 %0, l, h;}" : "+l"(c[k]));
     }
   }
-  unsigned long long r = c0 ^ c1 ^ c2 ^ c3 ^ c4 ^ c5 ^ c6 ^ c7;
+  unsigned long long r = c[0] ^ c[1] ^ c[2] ^ c[3] ^ c[4] ^ c[5] ^ c[6] ^ c[7];
   out[blockIdx.x * blockDim.x + threadIdx.x] = (uint32_t)r ^ (uint32_t)(r >> 32);
+}
+
+// kind 6: DFMA, eight independent chains (the FP64 pipe: 17.9 T/s = 64 /clk/SM on B200).
+// kind 7: the same block runs DFMA chains in its odd warps and IMAD.WIDE.X rows in its even warps.  Measured:
+// the two rates add up to one pipe's worth (DFMA and IMAD share the FMA-heavy datapath), which is why an
+// FP64 (48-bit limb) field multiplier run beside the integer one buys nothing.
+template <bool MIXED>
+__global__ void __launch_bounds__(256) mb_dfma(uint32_t* out, int iters, uint32_t seed) {
+  uint32_t r = 0;
+  if (MIXED && ((threadIdx.x >> 5) & 1) == 0) {
+    uint32_t E[12], X[12], a[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+      E[i] = seed + i + threadIdx.x;
+      X[i] = seed * 3 + i + threadIdx.x;
+      a[i] = seed * 7 + i * 5 + threadIdx.x;
+    }
+    uint32_t bi = seed | 1u;
+#pragma unroll 1
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        row_mac_even(E, X[11], a, bi);
+        row_mac_even(X, E[11], a, bi + u);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 12; i++) r ^= E[i] ^ X[i];
+  } else {
+    double d[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) d[i] = 1.0 + (double)(threadIdx.x + i) * 1e-3;
+    const double m = 1.0000001, c = 1e-9;
+#pragma unroll 1
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+      for (int u = 0; u < 12; u++) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) d[k] = __fma_rz(d[k], m, c);
+      }
+    }
+    double s = d[0] + d[1] + d[2] + d[3] + d[4] + d[5] + d[6] + d[7];
+    r = (uint32_t)__double2hiint(s) ^ (uint32_t)__double2loint(s);
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = r;
 }
 
 // kind 3 / 4: the G1 doubling loop of the subgroup ladders, with the product's non-inlined
@@ -917,6 +961,14 @@ cudaError_t launch_microbench(int kind, int iters, uint32_t* d_out, int grid, in
     case 5:
       mb_imad_wide_plain<<<grid, block, 0, stream>>>(d_out, iters, 12345u);
       *ops = threads * iters * 64.0;
+      break;
+    case 6:
+      mb_dfma<false><<<grid, block, 0, stream>>>(d_out, iters, 12345u);
+      *ops = threads * iters * 96.0;
+      break;
+    case 7:  // ops = slots of the shared pipe: 96 DFMA per odd-warp thread, 96 wide MADs (2 slots each) per even-warp thread
+      mb_dfma<true><<<grid, block, 0, stream>>>(d_out, iters, 12345u);
+      *ops = threads * 0.5 * iters * 96.0 + threads * 0.5 * iters * 96.0 * 2.0;
       break;
     case 3:
       mb_dbl<false><<<grid * PTAU_MB_MINB, 128, 0, stream>>>(d_out, iters, 12345u);
