@@ -679,16 +679,19 @@ int ptau_kzg_commit(ptau_ctx* ctx, const void* powers, const void* coeffs, size_
   }
   GpuSlot& s = ctx->gpu[0];
   CUDA_TRY(ctx, cudaSetDevice(s.device));
-  const size_t threads = ((n + 7) / 8 + 127) / 128 * 128;
+  if (n >= (1ull << 31)) return PTAU_ERR_ARG;  // point indices travel in 31 bits
+  ptau::MsmPlan plan;
+  ptau::msm_g1_plan(n, &plan);
+  int launches = 0;
   void *d_pts = nullptr, *d_sc = nullptr, *d_part = nullptr, *d_out = nullptr;
-  CUDA_TRY(ctx, cudaMalloc(&d_pts, n * 104 + 16));
-  CUDA_TRY(ctx, cudaMalloc(&d_sc, n * 32 + 16));
-  CUDA_TRY(ctx, cudaMalloc(&d_part, (threads ? threads : 128) * 144));
-  CUDA_TRY(ctx, cudaMalloc(&d_out, 104));
-  cudaError_t e = cudaMemcpyAsync(d_pts, powers, n * 104, cudaMemcpyHostToDevice, s.stream[0]);
+  cudaError_t e = cudaMalloc(&d_pts, n * 104 + 16);
+  if (e == cudaSuccess) e = cudaMalloc(&d_sc, n * 32 + 16);
+  if (e == cudaSuccess) e = cudaMalloc(&d_part, plan.scratch_bytes);
+  if (e == cudaSuccess) e = cudaMalloc(&d_out, 104);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_pts, powers, n * 104, cudaMemcpyHostToDevice, s.stream[0]);
   if (e == cudaSuccess) e = cudaMemcpyAsync(d_sc, coeffs, n * 32, cudaMemcpyHostToDevice, s.stream[0]);
   if (e == cudaSuccess) e = cudaEventRecord(s.ev_k0[0], s.stream[0]);
-  if (e == cudaSuccess) e = ptau::launch_msm_g1(d_pts, d_sc, n, d_part, d_out, s.stream[0]);
+  if (e == cudaSuccess) e = ptau::launch_msm_g1(d_pts, d_sc, n, d_part, d_out, &launches, s.stream[0]);
   if (e == cudaSuccess) e = cudaEventRecord(s.ev_k1[0], s.stream[0]);
   if (e == cudaSuccess) e = cudaMemcpyAsync(commitment, d_out, 104, cudaMemcpyDeviceToHost, s.stream[0]);
   if (e == cudaSuccess) e = cudaStreamSynchronize(s.stream[0]);
@@ -706,7 +709,7 @@ int ptau_kzg_commit(ptau_ctx* ctx, const void* powers, const void* coeffs, size_
   ctx->timing.n_gpus = ctx->n_gpus;
   ctx->timing.kernel_ms[0] = ms;
   ctx->timing.gpu_ms[0] = ms;
-  ctx->timing.kernel_launches = 2;
+  ctx->timing.kernel_launches = launches;
   ctx->timing.h2d_bytes[0] = n * 136;
   ctx->timing.d2h_bytes[0] = 104;
   return PTAU_OK;

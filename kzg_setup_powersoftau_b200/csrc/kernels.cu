@@ -543,16 +543,21 @@ cudaError_t launch_generate_win(int group, int fmt, const uint32_t* s0_mont, con
 }
 
 // =============================================================================
-// SURVEY 8f-4 (first step): KZG10 commit = multi-scalar multiplication over the loaded
-// powers,  C = sum_i [c_i] P_i   (ark-poly-commit 0.2 KZG10::commit, used at
-// /root/reference/src/lib.rs:268-275).  First version: Straus interleaving, 8 points per
-// thread share one chain of 254 doublings (about 1,630 Fq-mul per point instead of 3,200
-// for independent ladders), block tree reduction, one final inversion.  Complete addition
-// rules are used where arbitrary partial sums meet (equal / opposite / infinity), because
-// the inputs here are caller data, not ladders with known-safe scalars.
-// Not Pippenger yet: a bucket method is the known next step for large n.
+// KZG10 commit = multi-scalar multiplication over the loaded powers,
+//   C = sum_i [c_i] P_i   (ark-poly-commit 0.2 KZG10::commit, used at /root/reference/src/lib.rs:268-275).
+// Bucket (Pippenger) method with signed c-bit windows:
+//   1. msm_count    one thread per scalar: signed digits d_w in [-(2^(c-1)-1), 2^(c-1)], histogram of
+//                   bucket (w, |d_w|) sizes
+//   2. msm_scan     exclusive prefix sum of the histogram (one block; <= 2^19 + 1 counters)
+//   3. msm_scatter  the same digits again, each non-zero one claims a slot of its bucket: a list of
+//                   point indices (sign in bit 31) grouped by bucket -- a counting sort without a key array
+//   4. msm_bucket_sum    one thread per bucket: sum of its points (mixed additions)
+//   5. msm_window_segments  per window, runs of L consecutive buckets: sum_j j B_j by running sums
+//   6. msm_window_sum    one block per window adds the runs up
+//   7. msm_finish   Horner over the windows (c doublings each), one inversion, ark record
+// Complete addition rules everywhere: the inputs are caller data (equal points, opposite points,
+// infinity and zero scalars all occur in the tests), not ladders with known-safe scalars.
 // =============================================================================
-#define PTAU_MSM_K 8
 
 // acc += (x, y) with every special case of the group law
 static __device__ __noinline__ void g1_madd_complete(Jac<Fq>& acc, const Fq& x, const Fq& y) {
@@ -594,154 +599,261 @@ static __device__ __noinline__ void g1_add_complete(Jac<Fq>& p, const Jac<Fq>& q
   }
   jac_add(p, q);
 }
+static __device__ __forceinline__ Jac<Fq> jac_infinity() {
+  Jac<Fq> a;
+  a.X = fq_zero();
+  a.Y = fq_one();
+  a.Z = fq_zero();
+  return a;
+}
+static __device__ __forceinline__ void jac_store(uint32_t* o, const Jac<Fq>& a) {
+#pragma unroll
+  for (int w = 0; w < 12; w++) {
+    o[w] = a.X.l[w];
+    o[12 + w] = a.Y.l[w];
+    o[24 + w] = a.Z.l[w];
+  }
+}
+static __device__ __forceinline__ Jac<Fq> jac_load(const uint32_t* s) {
+  Jac<Fq> q;
+#pragma unroll
+  for (int w = 0; w < 12; w++) {
+    q.X.l[w] = s[w];
+    q.Y.l[w] = s[12 + w];
+    q.Z.l[w] = s[24 + w];
+  }
+  return q;
+}
 
-// points: ARK_MONT_LIMBS records (26 words); scalars: 8 x u32 LE each, < r
-__global__ void __launch_bounds__(PTAU_BLOCK)
-    msm_g1_partial(const uint32_t* __restrict__ pts, const uint32_t* __restrict__ scalars, uint64_t n,
-                   uint32_t* __restrict__ partial /* 36 words per block */) {
-  const uint64_t g = (uint64_t)blockIdx.x * PTAU_BLOCK + threadIdx.x;
-  const uint64_t i0 = g * PTAU_MSM_K;
-  Jac<Fq> acc;
-  acc.X = fq_zero();
-  acc.Y = fq_one();
-  acc.Z = fq_zero();
-  int cnt = 0;
-  if (i0 < n) cnt = (int)((n - i0) < (uint64_t)PTAU_MSM_K ? (n - i0) : (uint64_t)PTAU_MSM_K);
-  uint32_t k[PTAU_MSM_K][8];
-  uint32_t any = 0;
-#pragma unroll
-  for (int j = 0; j < PTAU_MSM_K; j++) {
-#pragma unroll
-    for (int w = 0; w < 8; w++) {
-      k[j][w] = (j < cnt) ? scalars[(i0 + j) * 8 + w] : 0u;
-      any |= k[j][w];
-    }
-    // a point flagged infinity contributes nothing
-    if (j < cnt && (pts[(i0 + j) * 26 + 24] & 0xffu)) {
-#pragma unroll
-      for (int w = 0; w < 8; w++) k[j][w] = 0u;
-    }
+// signed digit of window w (c <= 16 bits) of the 256-bit little-endian scalar k, with the carry of the
+// windows below.  v in [0, 2^c]; v > 2^(c-1) becomes v - 2^c with a carry into the next window.
+static __device__ __forceinline__ int msm_digit(const uint32_t* __restrict__ k, int w, int c, uint32_t& carry) {
+  const int bit = w * c;
+  const int wi = bit >> 5, sh = bit & 31;
+  uint32_t v = 0;
+  if (wi < 8) {
+    uint64_t t = k[wi];
+    if (wi + 1 < 8) t |= (uint64_t)k[wi + 1] << 32;
+    v = (uint32_t)(t >> sh) & ((1u << c) - 1u);
   }
-  if (any) {
-#pragma unroll 1
-    for (int bit = 254; bit >= 0; --bit) {
-      if (!fq_is_zero(acc.Z)) jac_dbl(acc);
-#pragma unroll 1
-      for (int j = 0; j < PTAU_MSM_K; j++) {
-        if ((k[j][bit >> 5] >> (bit & 31)) & 1u) {
-          const uint32_t* rec = pts + (i0 + j) * 26;
-          Fq x = load_tbl_field<Fq>(rec), y = load_tbl_field<Fq>(rec + 12);
-          g1_madd_complete(acc, x, y);
-        }
-      }
-    }
+  v += carry;
+  if (v > (1u << (c - 1))) {
+    carry = 1;
+    return (int)v - (1 << c);
   }
-  // block tree reduction: one Jacobian partial per block
-  __shared__ uint32_t sm[PTAU_BLOCK * 36];
-  for (int stride = PTAU_BLOCK / 2; stride >= 1; stride >>= 1) {
-    uint32_t* mine = sm + threadIdx.x * 36;
-#pragma unroll
-    for (int w = 0; w < 12; w++) {
-      mine[w] = acc.X.l[w];
-      mine[12 + w] = acc.Y.l[w];
-      mine[24 + w] = acc.Z.l[w];
-    }
-    __syncthreads();
-    if ((int)threadIdx.x < stride) {
-      const uint32_t* q32 = sm + (threadIdx.x + stride) * 36;
-      Jac<Fq> q;
-#pragma unroll
-      for (int w = 0; w < 12; w++) {
-        q.X.l[w] = q32[w];
-        q.Y.l[w] = q32[12 + w];
-        q.Z.l[w] = q32[24 + w];
-      }
-      g1_add_complete(acc, q);
-    }
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) {
-    uint32_t* o = partial + (uint64_t)blockIdx.x * 36;
-#pragma unroll
-    for (int w = 0; w < 12; w++) {
-      o[w] = acc.X.l[w];
-      o[12 + w] = acc.Y.l[w];
-      o[24 + w] = acc.Z.l[w];
-    }
+  carry = 0;
+  return (int)v;
+}
+
+// pts: ARK_MONT_LIMBS records (26 words); scalars: 8 x u32 LE each, < r.  SCATTER = false: histogram
+// into cnt[]; SCATTER = true: cnt[] holds the running cursor of every bucket, entries[] receives the indices.
+template <bool SCATTER>
+__global__ void __launch_bounds__(256) msm_digits(const uint32_t* __restrict__ pts, const uint32_t* __restrict__ scalars,
+                                                  uint64_t n, int c, int W, uint32_t NB, uint32_t* __restrict__ cnt,
+                                                  uint32_t* __restrict__ entries) {
+  const uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  if (pts[i * 26 + 24] & 0xffu) return;  // a point flagged infinity contributes nothing
+  const uint32_t* k = scalars + i * 8;
+  uint32_t carry = 0;
+  for (int w = 0; w < W; w++) {
+    int d = msm_digit(k, w, c, carry);
+    if (d == 0) continue;
+    uint32_t b = (uint32_t)w * NB + (uint32_t)(d < 0 ? -d : d) - 1u;
+    uint32_t pos = atomicAdd(&cnt[b], 1u);
+    if (SCATTER) entries[pos] = (uint32_t)i | (d < 0 ? 0x80000000u : 0u);
   }
 }
 
-// one block: sums m Jacobian partials, writes one ARK_MONT_LIMBS record (affine or infinity)
-__global__ void __launch_bounds__(256) msm_g1_reduce(const uint32_t* __restrict__ partial, uint64_t m, uint32_t* __restrict__ out) {
-  __shared__ uint32_t sm[256 * 36];
-  Jac<Fq> acc;
-  acc.X = fq_zero();
-  acc.Y = fq_one();
-  acc.Z = fq_zero();
-  for (uint64_t i = threadIdx.x; i < m; i += 256) {
-    Jac<Fq> q;
-    const uint32_t* s = partial + i * 36;
-#pragma unroll
-    for (int w = 0; w < 12; w++) {
-      q.X.l[w] = s[w];
-      q.Y.l[w] = s[12 + w];
-      q.Z.l[w] = s[24 + w];
+// exclusive scan of cnt[0..m) into off[0..m], off[m] = total; cur[] = copy of off[] (scatter cursors)
+__global__ void __launch_bounds__(1024) msm_scan(const uint32_t* __restrict__ cnt, uint32_t m, uint32_t* __restrict__ off,
+                                                 uint32_t* __restrict__ cur) {
+  __shared__ uint32_t part[1024];
+  const uint32_t per = (m + 1023u) / 1024u;
+  const uint32_t lo = threadIdx.x * per, hi = min(m, lo + per);
+  uint32_t s = 0;
+  for (uint32_t j = lo; j < hi; j++) s += cnt[j];
+  part[threadIdx.x] = s;
+  __syncthreads();
+  for (int d = 1; d < 1024; d <<= 1) {  // Hillis-Steele inclusive scan of the 1024 partial sums
+    uint32_t v = (int)threadIdx.x >= d ? part[threadIdx.x - d] : 0u;
+    __syncthreads();
+    part[threadIdx.x] += v;
+    __syncthreads();
+  }
+  uint32_t run = part[threadIdx.x] - s;
+  for (uint32_t j = lo; j < hi; j++) {
+    off[j] = run;
+    cur[j] = run;
+    run += cnt[j];
+  }
+  if (threadIdx.x == 1023) off[m] = part[1023];
+}
+
+// one thread per bucket: sum of the bucket's points
+__global__ void __launch_bounds__(PTAU_BLOCK) msm_bucket_sum(const uint32_t* __restrict__ pts, const uint32_t* __restrict__ entries,
+                                                             const uint32_t* __restrict__ off, uint32_t m,
+                                                             uint32_t* __restrict__ buckets /* 36 words each */) {
+  const uint32_t b = blockIdx.x * PTAU_BLOCK + threadIdx.x;
+  if (b >= m) return;
+  Jac<Fq> acc = jac_infinity();
+  const uint32_t e1 = off[b + 1];
+#pragma unroll 1
+  for (uint32_t e = off[b]; e < e1; e++) {
+    const uint32_t v = entries[e];
+    const uint32_t* rec = pts + (uint64_t)(v & 0x7fffffffu) * 26;
+    Fq x = load_tbl_field<Fq>(rec), y = load_tbl_field<Fq>(rec + 12);
+    if (v >> 31) y = fq_neg(y);
+    g1_madd_complete(acc, x, y);
+  }
+  jac_store(buckets + (uint64_t)b * 36, acc);
+}
+
+// one thread per run of L = 2^lgL consecutive buckets of one window: sum_{j in run} j * B_j, where bucket
+// index j0 (0-based) holds the points of digit magnitude j0 + 1.  Running sums from the top give
+// sum (j0 - lo + 1) B_j0 and t = sum B_j0; the run's offset adds [lo] t.
+__global__ void __launch_bounds__(PTAU_BLOCK) msm_window_segments(const uint32_t* __restrict__ buckets, uint32_t NB, int lgL,
+                                                                  uint32_t nseg_total, uint32_t* __restrict__ seg /* 36 words each */) {
+  const uint32_t g = blockIdx.x * PTAU_BLOCK + threadIdx.x;
+  if (g >= nseg_total) return;
+  const uint32_t per_window = NB >> lgL;
+  const uint32_t w = g / per_window, sidx = g % per_window;
+  const uint32_t lo = sidx << lgL;
+  const uint32_t* base = buckets + ((uint64_t)w * NB + lo) * 36;
+  Jac<Fq> t = jac_infinity(), sacc = jac_infinity();
+#pragma unroll 1
+  for (int j = (1 << lgL) - 1; j >= 0; --j) {
+    Jac<Fq> q = jac_load(base + (uint64_t)j * 36);
+    g1_add_complete(t, q);
+    g1_add_complete(sacc, t);
+  }
+  if (lo) {  // sacc += [lo] t = [2^lgL] [sidx] t
+    Jac<Fq> m = jac_infinity();
+#pragma unroll 1
+    for (int bit = 31 - __clz(sidx); bit >= 0; --bit) {
+      if (!fq_is_zero(m.Z)) jac_dbl(m);
+      if ((sidx >> bit) & 1u) g1_add_complete(m, t);
     }
+#pragma unroll 1
+    for (int k = 0; k < lgL; k++)
+      if (!fq_is_zero(m.Z)) jac_dbl(m);
+    g1_add_complete(sacc, m);
+  }
+  jac_store(seg + (uint64_t)g * 36, sacc);
+}
+
+// one block per window: adds the window's runs up (strided per thread, then a shared-memory tree)
+__global__ void __launch_bounds__(PTAU_BLOCK) msm_window_sum(const uint32_t* __restrict__ seg, uint32_t per_window,
+                                                             uint32_t* __restrict__ wsum /* 36 words per window */) {
+  __shared__ uint32_t sm[PTAU_BLOCK * 36];
+  const uint32_t* base = seg + (uint64_t)blockIdx.x * per_window * 36;
+  Jac<Fq> acc = jac_infinity();
+  for (uint32_t i = threadIdx.x; i < per_window; i += PTAU_BLOCK) {
+    Jac<Fq> q = jac_load(base + (uint64_t)i * 36);
     g1_add_complete(acc, q);
   }
-  for (int stride = 128; stride >= 1; stride >>= 1) {
-    uint32_t* mine = sm + threadIdx.x * 36;
-#pragma unroll
-    for (int w = 0; w < 12; w++) {
-      mine[w] = acc.X.l[w];
-      mine[12 + w] = acc.Y.l[w];
-      mine[24 + w] = acc.Z.l[w];
-    }
+  for (int stride = PTAU_BLOCK / 2; stride >= 1; stride >>= 1) {
+    jac_store(sm + threadIdx.x * 36, acc);
     __syncthreads();
     if ((int)threadIdx.x < stride) {
-      const uint32_t* s = sm + (threadIdx.x + stride) * 36;
-      Jac<Fq> q;
-#pragma unroll
-      for (int w = 0; w < 12; w++) {
-        q.X.l[w] = s[w];
-        q.Y.l[w] = s[12 + w];
-        q.Z.l[w] = s[24 + w];
-      }
+      Jac<Fq> q = jac_load(sm + (threadIdx.x + stride) * 36);
       g1_add_complete(acc, q);
     }
     __syncthreads();
   }
-  if (threadIdx.x == 0) {
-    if (fq_is_zero(acc.Z)) {  // ark zero(): (0, 1, infinity)
-      Fq one = fq_one();
+  if (threadIdx.x == 0) jac_store(wsum + (uint64_t)blockIdx.x * 36, acc);
+}
+
+// sum_w 2^(c w) S_w by Horner, then one ARK_MONT_LIMBS record (affine, or ark zero() = (0, 1, infinity))
+__global__ void msm_finish(const uint32_t* __restrict__ wsum, int W, int c, uint32_t* __restrict__ out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  Jac<Fq> acc = jac_infinity();
+#pragma unroll 1
+  for (int w = W - 1; w >= 0; --w) {
+#pragma unroll 1
+    for (int k = 0; k < c; k++)
+      if (!fq_is_zero(acc.Z)) jac_dbl(acc);
+    Jac<Fq> q = jac_load(wsum + (uint64_t)w * 36);
+    g1_add_complete(acc, q);
+  }
+  if (fq_is_zero(acc.Z)) {
+    Fq one = fq_one();
 #pragma unroll
-      for (int w = 0; w < 12; w++) {
-        out[w] = 0;
-        out[12 + w] = one.l[w];
-      }
-      out[24] = 1;
-      out[25] = 0;
-    } else {
-      Fq zi = fq_inv(acc.Z);
-      Fq zi2 = fq_sqr(zi);
-      Fq x = fq_mul(acc.X, zi2), y = fq_mul(acc.Y, fq_mul(zi2, zi));
-#pragma unroll
-      for (int w = 0; w < 12; w++) {
-        out[w] = x.l[w];
-        out[12 + w] = y.l[w];
-      }
-      out[24] = 0;
-      out[25] = 0;
+    for (int w = 0; w < 12; w++) {
+      out[w] = 0;
+      out[12 + w] = one.l[w];
     }
+    out[24] = 1;
+    out[25] = 0;
+  } else {
+    Fq zi = fq_inv(acc.Z);
+    Fq zi2 = fq_sqr(zi);
+    Fq x = fq_mul(acc.X, zi2), y = fq_mul(acc.Y, fq_mul(zi2, zi));
+#pragma unroll
+    for (int w = 0; w < 12; w++) {
+      out[w] = x.l[w];
+      out[12 + w] = y.l[w];
+    }
+    out[24] = 0;
+    out[25] = 0;
   }
 }
 
-cudaError_t launch_msm_g1(const void* d_pts, const void* d_scalars, uint64_t n, void* d_partial, void* d_out,
-                          cudaStream_t stream) {
-  const uint64_t threads = (n + PTAU_MSM_K - 1) / PTAU_MSM_K;
-  const unsigned grid = (unsigned)((threads + PTAU_BLOCK - 1) / PTAU_BLOCK);
-  if (grid) msm_g1_partial<<<grid, PTAU_BLOCK, 0, stream>>>((const uint32_t*)d_pts, (const uint32_t*)d_scalars, n, (uint32_t*)d_partial);
-  msm_g1_reduce<<<1, 256, 0, stream>>>((const uint32_t*)d_partial, (uint64_t)grid, (uint32_t*)d_out);
+void msm_g1_plan(uint64_t n, MsmPlan* p) {
+  int c = n < (1u << 7) ? 4 : n < (1u << 11) ? 7 : n < (1u << 15) ? 10 : n < (1u << 18) ? 13 : 16;
+  p->c = c;
+  p->W = 255 / c + 1;  // the top window holds fewer than c bits, so the last carry is absorbed
+  p->NB = 1u << (c - 1);
+  p->lgL = c - 1 < 4 ? c - 1 : 4;
+  p->buckets = (uint64_t)p->W * p->NB;
+  p->segments = p->buckets >> p->lgL;
+  const uint64_t a256 = 256;
+  auto up = [&](uint64_t v) { return (v + a256 - 1) / a256 * a256; };
+  p->off_counts = 0;
+  p->off_offsets = up((p->buckets + 1) * 4);
+  p->off_cursor = p->off_offsets + up((p->buckets + 1) * 4);
+  p->off_entries = p->off_cursor + up((p->buckets + 1) * 4);
+  p->off_buckets = p->off_entries + up((n ? n : 1) * (uint64_t)p->W * 4);
+  p->off_segments = p->off_buckets + up(p->buckets * 144);
+  p->off_wsum = p->off_segments + up(p->segments * 144);
+  p->scratch_bytes = p->off_wsum + up((uint64_t)p->W * 144);
+}
+
+cudaError_t launch_msm_g1(const void* d_pts, const void* d_scalars, uint64_t n, void* d_scratch, void* d_out,
+                          int* launches, cudaStream_t stream) {
+  MsmPlan p;
+  msm_g1_plan(n, &p);
+  uint8_t* base = (uint8_t*)d_scratch;
+  uint32_t* counts = (uint32_t*)(base + p.off_counts);
+  uint32_t* offsets = (uint32_t*)(base + p.off_offsets);
+  uint32_t* cursor = (uint32_t*)(base + p.off_cursor);
+  uint32_t* entries = (uint32_t*)(base + p.off_entries);
+  uint32_t* buckets = (uint32_t*)(base + p.off_buckets);
+  uint32_t* segs = (uint32_t*)(base + p.off_segments);
+  uint32_t* wsum = (uint32_t*)(base + p.off_wsum);
+  const uint32_t m = (uint32_t)p.buckets;
+  const uint32_t* pts = (const uint32_t*)d_pts;
+  const uint32_t* sc = (const uint32_t*)d_scalars;
+  cudaError_t e = cudaMemsetAsync(counts, 0, (size_t)(m + 1) * 4, stream);
+  if (e != cudaSuccess) return e;
+  const unsigned gn = (unsigned)((n + 255) / 256);
+  int nl = 0;
+  if (gn) {
+    msm_digits<false><<<gn, 256, 0, stream>>>(pts, sc, n, p.c, p.W, p.NB, counts, nullptr);
+    nl++;
+  }
+  msm_scan<<<1, 1024, 0, stream>>>(counts, m, offsets, cursor);
+  if (gn) {
+    msm_digits<true><<<gn, 256, 0, stream>>>(pts, sc, n, p.c, p.W, p.NB, cursor, entries);
+    nl++;
+  }
+  msm_bucket_sum<<<(m + PTAU_BLOCK - 1) / PTAU_BLOCK, PTAU_BLOCK, 0, stream>>>(pts, entries, offsets, m, buckets);
+  const uint32_t nseg = (uint32_t)p.segments;
+  msm_window_segments<<<(nseg + PTAU_BLOCK - 1) / PTAU_BLOCK, PTAU_BLOCK, 0, stream>>>(buckets, p.NB, p.lgL, nseg, segs);
+  msm_window_sum<<<p.W, PTAU_BLOCK, 0, stream>>>(segs, p.NB >> p.lgL, wsum);
+  msm_finish<<<1, 32, 0, stream>>>(wsum, p.W, p.c, (uint32_t*)d_out);
+  nl += 5;
+  if (launches) *launches = nl;
   return cudaGetLastError();
 }
 

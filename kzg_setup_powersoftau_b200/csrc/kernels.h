@@ -18,10 +18,17 @@ cudaError_t launch_generate(int group, int fmt, const uint32_t* d_scalars, void*
 cudaError_t launch_generate_win(int group, int fmt, const uint32_t* s0_mont, const uint32_t (*pw_mont)[8],
                                 const uint32_t* d_tbl, void* d_out, uint64_t first, uint64_t n, cudaStream_t stream);
 
-// sum_i [s_i] P_i over ARK_MONT_LIMBS G1 records and 32-byte LE scalars (< r); d_partial holds
-// 144 bytes per thread (ceil(n / 8) rounded up to whole blocks of 128); result: one record
-cudaError_t launch_msm_g1(const void* d_pts, const void* d_scalars, uint64_t n, void* d_partial, void* d_out,
-                          cudaStream_t stream);
+// sum_i [s_i] P_i over ARK_MONT_LIMBS G1 records and 32-byte LE scalars (< r) by the bucket method;
+// msm_g1_plan sizes the device scratch buffer (window width by n); result: one ARK_MONT_LIMBS record
+struct MsmPlan {
+  int c, W, lgL;
+  uint32_t NB;
+  uint64_t buckets, segments;
+  uint64_t off_counts, off_offsets, off_cursor, off_entries, off_buckets, off_segments, off_wsum, scratch_bytes;
+};
+void msm_g1_plan(uint64_t n, MsmPlan* plan);
+cudaError_t launch_msm_g1(const void* d_pts, const void* d_scalars, uint64_t n, void* d_scratch, void* d_out,
+                          int* launches, cudaStream_t stream);
 
 cudaError_t launch_fq_op(int op, const void* d_a, const void* d_b, void* d_out, uint64_t n, cudaStream_t stream);
 

@@ -575,6 +575,59 @@ def test_kzg10_commit_open_known_tau(ctx, tmp_path):
     assert kz._ffi.lib().ptau_kzg_commit(ctx._h, powers.powers_of_g[:1].ctypes.data, bad.ctypes.data, 1, out.ctypes.data) == kz._ffi.ERR_ARG
 
 
+def test_msm_bucket_method_window_widths_and_adversarial_scalars(ctx):
+    """The bucket (Pippenger) MSM behind KZG10::commit at sizes that select every window width
+    (c = 4, 7, 10, 13, 16), against the known tau:  sum c_i [tau^i]G == [sum c_i tau^i]G.
+    Adversarial scalars: all equal (one hot bucket per window), r - 1 (carries through every signed
+    window), digits exactly on the signed-window boundary 2^(c-1), zero scalars, the same point
+    repeated, and records flagged infinity (which must contribute nothing)."""
+    R = o.R_ORDER
+    tau = o.derive_scalars(0xC0FFEE)[0]
+    nmax = (1 << 18) + 5
+    pts = ctx.convert(1, ZU, ctx.generate(1, ZU, 1, tau, 0, nmax), ML, 0).reshape(nmax, 104)
+    lib = kz._ffi.lib()
+
+    def msm(points, scalars):
+        n = len(scalars)
+        sc = np.frombuffer(b"".join(int(v).to_bytes(32, "little") for v in scalars), dtype=np.uint8)
+        out = np.zeros(104, dtype=np.uint8)
+        pp = np.ascontiguousarray(points[:n])
+        assert lib.ptau_kzg_commit(ctx._h, pp.ctypes.data, sc.ctypes.data, n, out.ctypes.data) == 0
+        return out.tobytes()
+
+    def rec(k):
+        q = o.g1_mul(o.G1_GEN, k % R)
+        return o.g1_mont_record(0, 1, True) if q is None else o.g1_mont_record(q[0], q[1], False)
+
+    tp = [1]
+    for _ in range(nmax - 1):
+        tp.append(tp[-1] * tau % R)
+
+    def ev(scalars):
+        return sum(c * t for c, t in zip(scalars, tp)) % R
+
+    rnd = random.Random(77)
+    for n in (1, 2, 127, 128, 300, 2047, 2048, 5000, (1 << 15) - 1, 1 << 15, 40_000, nmax):
+        sc = [rnd.randrange(R) for _ in range(n)]
+        assert msm(pts, sc) == rec(ev(sc)), n
+    for n, c in ((100, 4), (1000, 7), (20_000, 10), (100_000, 13), (nmax, 16)):
+        for sc in ([R - 1] * n,                                            # = -sum P_i, carries everywhere
+                   [0x1234567] * n,                                        # one hot bucket per window
+                   [sum(1 << (c * w + c - 1) for w in range(255 // c)) % R] * n,   # digits on the boundary 2^(c-1)
+                   [0] * (n - 1) + [5],
+                   [rnd.randrange(1 << 20) for _ in range(n)]):            # short scalars: the top windows stay empty
+            assert msm(pts, sc) == rec(ev(sc)), (n, c)
+    # the same point many times, and P + (-P) inside one bucket
+    same = np.repeat(pts[3:4], 5000, axis=0)
+    assert msm(same, [7] * 5000) == rec(35_000 * tp[3])
+    assert msm(same, [9, R - 9] * 2500) == o.g1_mont_record(0, 1, True)
+    # records flagged infinity are skipped
+    holes = pts[:3000].copy()
+    holes[::3, 96] = 1
+    sc = [rnd.randrange(R) for _ in range(3000)]
+    assert msm(holes, sc) == rec(sum(c * t for i, (c, t) in enumerate(zip(sc, tp)) if i % 3))
+
+
 def test_multi_gpu_sharding_is_invisible(cref):
     """Same bytes and same first-bad-index with 1 GPU and with every GPU of the box."""
     from kzg_setup_powersoftau_b200 import _ffi
