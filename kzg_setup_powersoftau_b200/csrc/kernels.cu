@@ -545,21 +545,26 @@ cudaError_t launch_generate_win(int group, int fmt, const uint32_t* s0_mont, con
 // =============================================================================
 // KZG10 commit = multi-scalar multiplication over the loaded powers,
 //   C = sum_i [c_i] P_i   (ark-poly-commit 0.2 KZG10::commit, used at /root/reference/src/lib.rs:268-275).
-// Bucket (Pippenger) method with signed c-bit windows:
-//   1. msm_count    one thread per scalar: signed digits d_w in [-(2^(c-1)-1), 2^(c-1)], histogram of
+// Bucket (Pippenger) method with signed windows.  The 256 scalar bits are cut into W = ceil(256 / c) windows of
+// width c (the low `a` ones) or c - 1 (the rest) that add up to exactly 256, so that no window is partial:
+// a partial top window (or a carry-only window) would put n / 2^few points into each of a handful of buckets
+// and serialise them in a handful of threads.  The top window ends at bit 255, which is 0 for every scalar < r,
+// so its digit never goes negative and never carries out.
+//   1. msm_digits<false>  one thread per scalar: signed digits d_w in [-(2^(cw-1)-1), 2^(cw-1)], histogram of
 //                   bucket (w, |d_w|) sizes
 //   2. msm_scan     exclusive prefix sum of the histogram (one block; <= 2^19 + 1 counters)
-//   3. msm_scatter  the same digits again, each non-zero one claims a slot of its bucket: a list of
+//   3. msm_digits<true>  the same digits again, each non-zero one claims a slot of its bucket: a list of
 //                   point indices (sign in bit 31) grouped by bucket -- a counting sort without a key array
 //   4. msm_bucket_sum    one thread per bucket: sum of its points (mixed additions)
 //   5. msm_window_segments  per window, runs of L consecutive buckets: sum_j j B_j by running sums
-//   6. msm_window_sum    one block per window adds the runs up
-//   7. msm_finish   Horner over the windows (c doublings each), one inversion, ark record
+//   6. msm_window_sum    one block per window adds the runs up and applies the window's weight 2^(c w)
+//   7. msm_finish   adds the windows, one inversion, ark record
 // Complete addition rules everywhere: the inputs are caller data (equal points, opposite points,
 // infinity and zero scalars all occur in the tests), not ladders with known-safe scalars.
 // =============================================================================
 
-// acc += (x, y) with every special case of the group law
+// acc += (x, y) with every special case of the group law (madd-2007-bl, 7M + 4S; the quantities that
+// decide the special cases are the ones the formula needs anyway)
 static __device__ __noinline__ void g1_madd_complete(Jac<Fq>& acc, const Fq& x, const Fq& y) {
   if (fq_is_zero(acc.Z)) {
     acc.X = x;
@@ -578,8 +583,17 @@ static __device__ __noinline__ void g1_madd_complete(Jac<Fq>& acc, const Fq& x, 
     }
     return;
   }
-  jac_madd(acc, x, y);
+  Fq H = fq_sub(u2, acc.X);
+  Fq I = fq_sqr(fq_dbl(H));
+  Fq J = fq_mul(H, I);
+  Fq rr = fq_dbl(fq_sub(s2, acc.Y));
+  Fq V = fq_mul(acc.X, I);
+  Fq X3 = fq_sub(fq_sub(fq_sqr(rr), J), fq_dbl(V));
+  acc.Y = fq_sub(fq_mul(rr, fq_sub(V, X3)), fq_dbl(fq_mul(acc.Y, J)));
+  acc.Z = fq_dbl(fq_mul(acc.Z, H));
+  acc.X = X3;
 }
+// p += q, both Jacobian (add-2007-bl, 11M + 5S), every special case
 static __device__ __noinline__ void g1_add_complete(Jac<Fq>& p, const Jac<Fq>& q) {
   if (fq_is_zero(q.Z)) return;
   if (fq_is_zero(p.Z)) {
@@ -597,7 +611,15 @@ static __device__ __noinline__ void g1_add_complete(Jac<Fq>& p, const Jac<Fq>& q
     }
     return;
   }
-  jac_add(p, q);
+  Fq H = fq_sub(u2, u1);
+  Fq I = fq_sqr(fq_dbl(H));
+  Fq J = fq_mul(H, I);
+  Fq rr = fq_dbl(fq_sub(s2, s1));
+  Fq V = fq_mul(u1, I);
+  Fq X3 = fq_sub(fq_sub(fq_sqr(rr), J), fq_dbl(V));
+  p.Y = fq_sub(fq_mul(rr, fq_sub(V, X3)), fq_dbl(fq_mul(s1, J)));
+  p.Z = fq_mul(fq_dbl(fq_mul(p.Z, q.Z)), H);
+  p.X = X3;
 }
 static __device__ __forceinline__ Jac<Fq> jac_infinity() {
   Jac<Fq> a;
@@ -625,21 +647,27 @@ static __device__ __forceinline__ Jac<Fq> jac_load(const uint32_t* s) {
   return q;
 }
 
-// signed digit of window w (c <= 16 bits) of the 256-bit little-endian scalar k, with the carry of the
-// windows below.  v in [0, 2^c]; v > 2^(c-1) becomes v - 2^c with a carry into the next window.
-static __device__ __forceinline__ int msm_digit(const uint32_t* __restrict__ k, int w, int c, uint32_t& carry) {
-  const int bit = w * c;
+// window geometry shared by the kernels: windows [0, a) are c bits wide with NB = 2^(c-1) buckets,
+// windows [a, W) are c - 1 bits wide with NB / 2 buckets
+struct MsmGeom {
+  int c, W, a, lgL;
+  uint32_t NB;
+};
+static __device__ __forceinline__ int msm_bitoff(const MsmGeom& g, int w) { return w < g.a ? w * g.c : g.a * g.c + (w - g.a) * (g.c - 1); }
+static __device__ __forceinline__ uint32_t msm_bucket_base(const MsmGeom& g, int w) {
+  return w < g.a ? (uint32_t)w * g.NB : (uint32_t)g.a * g.NB + (uint32_t)(w - g.a) * (g.NB >> 1);
+}
+
+// signed digit of the cw-bit window (cw <= 16) starting at `bit` of the 256-bit little-endian scalar k, with the
+// carry of the windows below.  v in [0, 2^cw]; v > 2^(cw-1) becomes v - 2^cw with a carry into the next window.
+static __device__ __forceinline__ int msm_digit(const uint32_t* __restrict__ k, int bit, int cw, uint32_t& carry) {
   const int wi = bit >> 5, sh = bit & 31;
-  uint32_t v = 0;
-  if (wi < 8) {
-    uint64_t t = k[wi];
-    if (wi + 1 < 8) t |= (uint64_t)k[wi + 1] << 32;
-    v = (uint32_t)(t >> sh) & ((1u << c) - 1u);
-  }
-  v += carry;
-  if (v > (1u << (c - 1))) {
+  uint64_t t = k[wi];
+  if (wi + 1 < 8) t |= (uint64_t)k[wi + 1] << 32;
+  uint32_t v = ((uint32_t)(t >> sh) & ((1u << cw) - 1u)) + carry;
+  if (v > (1u << (cw - 1))) {
     carry = 1;
-    return (int)v - (1 << c);
+    return (int)v - (1 << cw);
   }
   carry = 0;
   return (int)v;
@@ -649,45 +677,75 @@ static __device__ __forceinline__ int msm_digit(const uint32_t* __restrict__ k, 
 // into cnt[]; SCATTER = true: cnt[] holds the running cursor of every bucket, entries[] receives the indices.
 template <bool SCATTER>
 __global__ void __launch_bounds__(256) msm_digits(const uint32_t* __restrict__ pts, const uint32_t* __restrict__ scalars,
-                                                  uint64_t n, int c, int W, uint32_t NB, uint32_t* __restrict__ cnt,
+                                                  uint64_t n, MsmGeom g, uint32_t* __restrict__ cnt,
                                                   uint32_t* __restrict__ entries) {
   const uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x;
   if (i >= n) return;
   if (pts[i * 26 + 24] & 0xffu) return;  // a point flagged infinity contributes nothing
   const uint32_t* k = scalars + i * 8;
-  uint32_t carry = 0;
-  for (int w = 0; w < W; w++) {
-    int d = msm_digit(k, w, c, carry);
-    if (d == 0) continue;
-    uint32_t b = (uint32_t)w * NB + (uint32_t)(d < 0 ? -d : d) - 1u;
-    uint32_t pos = atomicAdd(&cnt[b], 1u);
-    if (SCATTER) entries[pos] = (uint32_t)i | (d < 0 ? 0x80000000u : 0u);
+  uint32_t carry = 0, base = 0;
+  int bit = 0;
+  for (int w = 0; w < g.W; w++) {
+    const int cw = w < g.a ? g.c : g.c - 1;
+    int d = msm_digit(k, bit, cw, carry);
+    if (d != 0) {
+      uint32_t b = base + (uint32_t)(d < 0 ? -d : d) - 1u;
+      uint32_t pos = atomicAdd(&cnt[b], 1u);
+      if (SCATTER) entries[pos] = (uint32_t)i | (d < 0 ? 0x80000000u : 0u);
+    }
+    bit += cw;
+    base += 1u << (cw - 1);
   }
 }
 
-// exclusive scan of cnt[0..m) into off[0..m], off[m] = total; cur[] = copy of off[] (scatter cursors)
+// exclusive scan of cnt[0..m) into off[0..m], off[m] = total; cur[] = copy of off[] (scatter cursors).
+// One block walks the array in coalesced tiles of 1024 x 4 counters (m <= 2^19 + 1: a few hundred tiles).
 __global__ void __launch_bounds__(1024) msm_scan(const uint32_t* __restrict__ cnt, uint32_t m, uint32_t* __restrict__ off,
                                                  uint32_t* __restrict__ cur) {
-  __shared__ uint32_t part[1024];
-  const uint32_t per = (m + 1023u) / 1024u;
-  const uint32_t lo = threadIdx.x * per, hi = min(m, lo + per);
-  uint32_t s = 0;
-  for (uint32_t j = lo; j < hi; j++) s += cnt[j];
-  part[threadIdx.x] = s;
+  __shared__ uint32_t wsum[32];
+  __shared__ uint32_t carry_s;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry_s = 0;
   __syncthreads();
-  for (int d = 1; d < 1024; d <<= 1) {  // Hillis-Steele inclusive scan of the 1024 partial sums
-    uint32_t v = (int)threadIdx.x >= d ? part[threadIdx.x - d] : 0u;
+  for (uint32_t base = 0; base < m; base += 4096) {
+    const uint32_t j = base + threadIdx.x * 4;
+    uint32_t v[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) v[k] = (j + k < m) ? cnt[j + k] : 0u;
+    const uint32_t mine = v[0] + v[1] + v[2] + v[3];
+    uint32_t incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += t;
+    }
+    if (lane == 31) wsum[wid] = incl;
     __syncthreads();
-    part[threadIdx.x] += v;
+    if (wid == 0) {
+      uint32_t w = wsum[lane], wi = w;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, wi, d);
+        if (lane >= d) wi += t;
+      }
+      wsum[lane] = wi - w;  // exclusive prefix of the warp totals
+    }
+    __syncthreads();
+    const uint32_t carry = carry_s;
+    uint32_t run = carry + wsum[wid] + incl - mine;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      if (j + k < m) {
+        off[j + k] = run;
+        cur[j + k] = run;
+      }
+      run += v[k];
+    }
+    __syncthreads();
+    if (threadIdx.x == 1023) carry_s = run;
     __syncthreads();
   }
-  uint32_t run = part[threadIdx.x] - s;
-  for (uint32_t j = lo; j < hi; j++) {
-    off[j] = run;
-    cur[j] = run;
-    run += cnt[j];
-  }
-  if (threadIdx.x == 1023) off[m] = part[1023];
+  if (threadIdx.x == 0) off[m] = carry_s;
 }
 
 // one thread per bucket: sum of the bucket's points
@@ -712,22 +770,24 @@ __global__ void __launch_bounds__(PTAU_BLOCK) msm_bucket_sum(const uint32_t* __r
 // one thread per run of L = 2^lgL consecutive buckets of one window: sum_{j in run} j * B_j, where bucket
 // index j0 (0-based) holds the points of digit magnitude j0 + 1.  Running sums from the top give
 // sum (j0 - lo + 1) B_j0 and t = sum B_j0; the run's offset adds [lo] t.
-__global__ void __launch_bounds__(PTAU_BLOCK) msm_window_segments(const uint32_t* __restrict__ buckets, uint32_t NB, int lgL,
-                                                                  uint32_t nseg_total, uint32_t* __restrict__ seg /* 36 words each */) {
-  const uint32_t g = blockIdx.x * PTAU_BLOCK + threadIdx.x;
-  if (g >= nseg_total) return;
-  const uint32_t per_window = NB >> lgL;
-  const uint32_t w = g / per_window, sidx = g % per_window;
-  const uint32_t lo = sidx << lgL;
-  const uint32_t* base = buckets + ((uint64_t)w * NB + lo) * 36;
+__global__ void __launch_bounds__(PTAU_BLOCK) msm_window_segments(const uint32_t* __restrict__ buckets, MsmGeom g, uint32_t nseg_total,
+                                                                  uint32_t* __restrict__ seg /* 36 words each */) {
+  const uint32_t t_id = blockIdx.x * PTAU_BLOCK + threadIdx.x;
+  if (t_id >= nseg_total) return;
+  // runs are laid out exactly like the buckets, L buckets per run
+  const uint32_t lo_abs = t_id << g.lgL;
+  const uint32_t wide = (uint32_t)g.a * g.NB;
+  const uint32_t in_window = lo_abs < wide ? lo_abs % g.NB : (lo_abs - wide) % (g.NB >> 1);
+  const uint32_t sidx = in_window >> g.lgL;
+  const uint32_t* base = buckets + (uint64_t)lo_abs * 36;
   Jac<Fq> t = jac_infinity(), sacc = jac_infinity();
 #pragma unroll 1
-  for (int j = (1 << lgL) - 1; j >= 0; --j) {
+  for (int j = (1 << g.lgL) - 1; j >= 0; --j) {
     Jac<Fq> q = jac_load(base + (uint64_t)j * 36);
     g1_add_complete(t, q);
     g1_add_complete(sacc, t);
   }
-  if (lo) {  // sacc += [lo] t = [2^lgL] [sidx] t
+  if (sidx) {  // sacc += [lo] t = [2^lgL] [sidx] t
     Jac<Fq> m = jac_infinity();
 #pragma unroll 1
     for (int bit = 31 - __clz(sidx); bit >= 0; --bit) {
@@ -735,20 +795,24 @@ __global__ void __launch_bounds__(PTAU_BLOCK) msm_window_segments(const uint32_t
       if ((sidx >> bit) & 1u) g1_add_complete(m, t);
     }
 #pragma unroll 1
-    for (int k = 0; k < lgL; k++)
+    for (int k = 0; k < g.lgL; k++)
       if (!fq_is_zero(m.Z)) jac_dbl(m);
     g1_add_complete(sacc, m);
   }
-  jac_store(seg + (uint64_t)g * 36, sacc);
+  jac_store(seg + (uint64_t)t_id * 36, sacc);
 }
 
-// one block per window: adds the window's runs up (strided per thread, then a shared-memory tree)
-__global__ void __launch_bounds__(PTAU_BLOCK) msm_window_sum(const uint32_t* __restrict__ seg, uint32_t per_window,
+// one block per window: adds the window's runs up (strided per thread, then a shared-memory tree) and applies
+// the window's weight 2^bitoff, all windows in parallel
+__global__ void __launch_bounds__(PTAU_BLOCK) msm_window_sum(const uint32_t* __restrict__ seg, MsmGeom g,
                                                              uint32_t* __restrict__ wsum /* 36 words per window */) {
   __shared__ uint32_t sm[PTAU_BLOCK * 36];
-  const uint32_t* base = seg + (uint64_t)blockIdx.x * per_window * 36;
+  const int w = blockIdx.x;
+  const uint32_t first = msm_bucket_base(g, w) >> g.lgL;
+  const uint32_t count = (w < g.a ? g.NB : g.NB >> 1) >> g.lgL;
+  const uint32_t* base = seg + (uint64_t)first * 36;
   Jac<Fq> acc = jac_infinity();
-  for (uint32_t i = threadIdx.x; i < per_window; i += PTAU_BLOCK) {
+  for (uint32_t i = threadIdx.x; i < count; i += PTAU_BLOCK) {
     Jac<Fq> q = jac_load(base + (uint64_t)i * 36);
     g1_add_complete(acc, q);
   }
@@ -761,18 +825,21 @@ __global__ void __launch_bounds__(PTAU_BLOCK) msm_window_sum(const uint32_t* __r
     }
     __syncthreads();
   }
-  if (threadIdx.x == 0) jac_store(wsum + (uint64_t)blockIdx.x * 36, acc);
+  if (threadIdx.x == 0) {
+    const int nd = msm_bitoff(g, w);
+#pragma unroll 1
+    for (int k = 0; k < nd; k++)
+      if (!fq_is_zero(acc.Z)) jac_dbl(acc);
+    jac_store(wsum + (uint64_t)w * 36, acc);
+  }
 }
 
-// sum_w 2^(c w) S_w by Horner, then one ARK_MONT_LIMBS record (affine, or ark zero() = (0, 1, infinity))
-__global__ void msm_finish(const uint32_t* __restrict__ wsum, int W, int c, uint32_t* __restrict__ out) {
+// sum of the weighted window sums, then one ARK_MONT_LIMBS record (affine, or ark zero() = (0, 1, infinity))
+__global__ void msm_finish(const uint32_t* __restrict__ wsum, int W, uint32_t* __restrict__ out) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   Jac<Fq> acc = jac_infinity();
 #pragma unroll 1
-  for (int w = W - 1; w >= 0; --w) {
-#pragma unroll 1
-    for (int k = 0; k < c; k++)
-      if (!fq_is_zero(acc.Z)) jac_dbl(acc);
+  for (int w = 0; w < W; w++) {
     Jac<Fq> q = jac_load(wsum + (uint64_t)w * 36);
     g1_add_complete(acc, q);
   }
@@ -800,12 +867,16 @@ __global__ void msm_finish(const uint32_t* __restrict__ wsum, int W, int c, uint
 }
 
 void msm_g1_plan(uint64_t n, MsmPlan* p) {
-  int c = n < (1u << 7) ? 4 : n < (1u << 11) ? 7 : n < (1u << 15) ? 10 : n < (1u << 18) ? 13 : 16;
+  int lg = 0;
+  while (lg < 63 && (1ull << lg) < n) lg++;
+  int c = lg - 4;  // about 32 points per bucket
+  c = c < 3 ? 3 : c > 16 ? 16 : c;
   p->c = c;
-  p->W = 255 / c + 1;  // the top window holds fewer than c bits, so the last carry is absorbed
+  p->W = (256 + c - 1) / c;
+  p->a = 256 - (c - 1) * p->W;  // windows of width c; the other W - a are c - 1 wide: a c + (W - a)(c - 1) = 256
   p->NB = 1u << (c - 1);
-  p->lgL = c - 1 < 4 ? c - 1 : 4;
-  p->buckets = (uint64_t)p->W * p->NB;
+  p->lgL = c - 2 < 4 ? c - 2 : 4;
+  p->buckets = (uint64_t)p->a * p->NB + (uint64_t)(p->W - p->a) * (p->NB >> 1);
   p->segments = p->buckets >> p->lgL;
   const uint64_t a256 = 256;
   auto up = [&](uint64_t v) { return (v + a256 - 1) / a256 * a256; };
@@ -823,6 +894,12 @@ cudaError_t launch_msm_g1(const void* d_pts, const void* d_scalars, uint64_t n, 
                           int* launches, cudaStream_t stream) {
   MsmPlan p;
   msm_g1_plan(n, &p);
+  MsmGeom g;
+  g.c = p.c;
+  g.W = p.W;
+  g.a = p.a;
+  g.lgL = p.lgL;
+  g.NB = p.NB;
   uint8_t* base = (uint8_t*)d_scratch;
   uint32_t* counts = (uint32_t*)(base + p.off_counts);
   uint32_t* offsets = (uint32_t*)(base + p.off_offsets);
@@ -839,19 +916,19 @@ cudaError_t launch_msm_g1(const void* d_pts, const void* d_scalars, uint64_t n, 
   const unsigned gn = (unsigned)((n + 255) / 256);
   int nl = 0;
   if (gn) {
-    msm_digits<false><<<gn, 256, 0, stream>>>(pts, sc, n, p.c, p.W, p.NB, counts, nullptr);
+    msm_digits<false><<<gn, 256, 0, stream>>>(pts, sc, n, g, counts, nullptr);
     nl++;
   }
   msm_scan<<<1, 1024, 0, stream>>>(counts, m, offsets, cursor);
   if (gn) {
-    msm_digits<true><<<gn, 256, 0, stream>>>(pts, sc, n, p.c, p.W, p.NB, cursor, entries);
+    msm_digits<true><<<gn, 256, 0, stream>>>(pts, sc, n, g, cursor, entries);
     nl++;
   }
   msm_bucket_sum<<<(m + PTAU_BLOCK - 1) / PTAU_BLOCK, PTAU_BLOCK, 0, stream>>>(pts, entries, offsets, m, buckets);
   const uint32_t nseg = (uint32_t)p.segments;
-  msm_window_segments<<<(nseg + PTAU_BLOCK - 1) / PTAU_BLOCK, PTAU_BLOCK, 0, stream>>>(buckets, p.NB, p.lgL, nseg, segs);
-  msm_window_sum<<<p.W, PTAU_BLOCK, 0, stream>>>(segs, p.NB >> p.lgL, wsum);
-  msm_finish<<<1, 32, 0, stream>>>(wsum, p.W, p.c, (uint32_t*)d_out);
+  msm_window_segments<<<(nseg + PTAU_BLOCK - 1) / PTAU_BLOCK, PTAU_BLOCK, 0, stream>>>(buckets, g, nseg, segs);
+  msm_window_sum<<<p.W, PTAU_BLOCK, 0, stream>>>(segs, g, wsum);
+  msm_finish<<<1, 32, 0, stream>>>(wsum, p.W, (uint32_t*)d_out);
   nl += 5;
   if (launches) *launches = nl;
   return cudaGetLastError();

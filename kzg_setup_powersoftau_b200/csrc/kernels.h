@@ -21,7 +21,7 @@ cudaError_t launch_generate_win(int group, int fmt, const uint32_t* s0_mont, con
 // sum_i [s_i] P_i over ARK_MONT_LIMBS G1 records and 32-byte LE scalars (< r) by the bucket method;
 // msm_g1_plan sizes the device scratch buffer (window width by n); result: one ARK_MONT_LIMBS record
 struct MsmPlan {
-  int c, W, lgL;
+  int c, W, a, lgL;
   uint32_t NB;
   uint64_t buckets, segments;
   uint64_t off_counts, off_offsets, off_cursor, off_entries, off_buckets, off_segments, off_wsum, scratch_bytes;

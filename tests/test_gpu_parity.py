@@ -577,13 +577,13 @@ def test_kzg10_commit_open_known_tau(ctx, tmp_path):
 
 def test_msm_bucket_method_window_widths_and_adversarial_scalars(ctx):
     """The bucket (Pippenger) MSM behind KZG10::commit at sizes that select every window width
-    (c = 4, 7, 10, 13, 16), against the known tau:  sum c_i [tau^i]G == [sum c_i tau^i]G.
+    (c = 3 .. 16), against the known tau:  sum c_i [tau^i]G == [sum c_i tau^i]G.
     Adversarial scalars: all equal (one hot bucket per window), r - 1 (carries through every signed
-    window), digits exactly on the signed-window boundary 2^(c-1), zero scalars, the same point
+    window), digits exactly on the signed-window boundary 2^(cw-1), zero scalars, the same point
     repeated, and records flagged infinity (which must contribute nothing)."""
     R = o.R_ORDER
     tau = o.derive_scalars(0xC0FFEE)[0]
-    nmax = (1 << 18) + 5
+    nmax = (1 << 20) + 3
     pts = ctx.convert(1, ZU, ctx.generate(1, ZU, 1, tau, 0, nmax), ML, 0).reshape(nmax, 104)
     lib = kz._ffi.lib()
 
@@ -607,13 +607,27 @@ def test_msm_bucket_method_window_widths_and_adversarial_scalars(ctx):
         return sum(c * t for c, t in zip(scalars, tp)) % R
 
     rnd = random.Random(77)
-    for n in (1, 2, 127, 128, 300, 2047, 2048, 5000, (1 << 15) - 1, 1 << 15, 40_000, nmax):
+    def geometry(n):  # mirrors msm_g1_plan
+        lg = max(n - 1, 0).bit_length()
+        c = min(max(lg - 4, 3), 16)
+        W = (256 + c - 1) // c
+        a = 256 - (c - 1) * W
+        return c, W, a
+
+    widths = set()
+    for n in (1, 2, 127, 128, 200, 300, 600, 2047, 2048, 4096, 5000, 10_000, (1 << 15) - 1, 1 << 15, 40_000, (1 << 16) + 1,
+              (1 << 17) + 1, (1 << 18) + 5, nmax):
+        widths.add(geometry(n)[0])
         sc = [rnd.randrange(R) for _ in range(n)]
         assert msm(pts, sc) == rec(ev(sc)), n
-    for n, c in ((100, 4), (1000, 7), (20_000, 10), (100_000, 13), (nmax, 16)):
+    assert widths == set(range(3, 17))
+    for n in (100, 1000, 20_000, 100_000, (1 << 18) + 5):
+        c, W, a = geometry(n)
+        tops = [(w + 1) * c - 1 if w < a else a * c + (w - a + 1) * (c - 1) - 1 for w in range(W - 1)]  # top bit of each window
         for sc in ([R - 1] * n,                                            # = -sum P_i, carries everywhere
                    [0x1234567] * n,                                        # one hot bucket per window
-                   [sum(1 << (c * w + c - 1) for w in range(255 // c)) % R] * n,   # digits on the boundary 2^(c-1)
+                   [sum(1 << b for b in tops[:-1])] * n,                   # digits on the boundary 2^(cw-1)
+                   [sum(1 << b for b in tops[:-1]) + 1] * n,               # ... and just above it (negative digits, carries)
                    [0] * (n - 1) + [5],
                    [rnd.randrange(1 << 20) for _ in range(n)]):            # short scalars: the top windows stay empty
             assert msm(pts, sc) == rec(ev(sc)), (n, c)
