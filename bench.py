@@ -126,6 +126,11 @@ def run_config5(args, kz, sharding, torch, dist, ctx, rank, world, dev):
     status = torch.full((1,), -1, dtype=torch.int64, device=dev)
     stream = torch.cuda.current_stream()
     ZC, AU = kz.FMT_ZCASH_COMPRESSED, kz.FMT_ARK_UNCOMPRESSED
+    h_in = h_out = None
+    if not args.no_e2e:
+        h_in, h_out = kz.PinnedBuffer(slab * 96), kz.PinnedBuffer(slab * 192)
+        h_in_t, h_out_t = torch.from_numpy(h_in.array), torch.from_numpy(h_out.array)
+    e2e_s, h2d, d2h, e2e_launches, checked = 0.0, 0, 0, 0, set()
     # warm-up (also builds the generator tables)
     for g in (kz.G1, kz.G2):
         ctx.generate_device(g, ZC, 1, tau, 0, 4096, d_in.data_ptr(), stream=stream.cuda_stream)
@@ -157,6 +162,19 @@ def run_config5(args, kz, sharding, torch, dist, ctx, rank, world, dev):
             ms[key] += e0.elapsed_time(e1)
             pts[key] += c
             launches += 1
+            if h_in is not None:
+                ri, ro = (48, 96) if g == kz.G1 else (96, 192)
+                h_in_t[:c * ri].copy_(d_in[:c * ri])  # untimed: stands for the file read
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                ctx.convert(g, ZC, h_in.array[:c * ri], AU, kz.CHECKS_STRICT, out=h_out.array[:c * ro])
+                e2e_s += time.perf_counter() - t0
+                e2e_launches += ctx.timing()["kernel_launches"]
+                h2d += c * ri
+                d2h += c * ro
+                if name not in checked:  # byte-compare the first slab of every section with the device-resident pass
+                    checked.add(name)
+                    assert torch.equal(h_out_t[:c * ro], d_out[:c * ro].cpu()), "e2e output differs (%s)" % name
     torch.cuda.synchronize()
     wall = time.perf_counter() - t_wall
     stop.set()
@@ -168,6 +186,13 @@ def run_config5(args, kz, sharding, torch, dist, ctx, rank, world, dev):
     g1_ms, g2_ms = sharding.reduce_max_ms(ms["G1"]), sharding.reduce_max_ms(ms["G2"])
     tot_g1, tot_g2 = int(sharding.reduce_sum(pts["G1"])), int(sharding.reduce_sum(pts["G2"]))
     wall_max = sharding.reduce_max_ms(wall * 1e3)
+    e2e = None
+    if h_in is not None:
+        e2e_ms = sharding.reduce_max_ms(e2e_s * 1e3)
+        e2e = {"value": (tot_g1 + tot_g2) / (e2e_ms / 1e3), "unit": "points/s",
+               "h2d_bytes_per_step": int(sharding.reduce_sum(h2d)), "d2h_bytes_per_step": int(sharding.reduce_sum(d2h)),
+               "ms_per_step": e2e_ms, "note": "pinned host slabs of 2^22 points -> ptau_convert -> pinned host, max over ranks"}
+        launches += e2e_launches
     if rank == 0:
         line = {
             "metric": "G1+G2 points/sec, compressed parse + sqrt decompress + subgroup check + ark re-encode "
@@ -181,7 +206,7 @@ def run_config5(args, kz, sharding, torch, dist, ctx, rank, world, dev):
                        "g2_points_per_s": tot_g2 / (g2_ms / 1e3), "kernel_ms_g1_max_rank": g1_ms,
                        "kernel_ms_g2_max_rank": g2_ms, "wall_s_incl_generation": wall_max / 1e3,
                        "l2": "inputs larger than L2 (slabs of 2^22 points, 200-400 MB)"},
-            "e2e": None, "gpu_launches": launches, "clocks": summarize_clocks(clocks),
+            "e2e": e2e, "gpu_launches": launches, "clocks": summarize_clocks(clocks),
         }
         print(json.dumps(line), flush=True)
 
@@ -198,6 +223,7 @@ def main():
                     help="config2 = headline (2^20 uncompressed G1 per GPU); config5 = 2^K-power compressed setup "
                          "sharded by index range over all ranks (strong scaling, device-resident)")
     ap.add_argument("--log2-powers", type=int, default=26, help="powers of the config5 setup")
+    ap.add_argument("--no-e2e", action="store_true", help="config5: skip the host -> host leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
