@@ -218,6 +218,20 @@ int ptau_blake2b_file(const char* path, char out_hex[129]);
  * commit(blinding, powers_of_gamma_g): pass both (point, scalar) lists concatenated. */
 int ptau_kzg_commit(ptau_ctx* ctx, const void* powers, const void* coeffs, size_t n, void* commitment);
 
+/* KZG10::check for n openings in parallel -- ark-poly-commit 0.2 kzg10 `check`, the call the reference's
+ * consumer code makes at /root/reference/src/lib.rs:276-286:
+ *     e(C_i - [v_i] g - [rv_i] gamma_g, h) == e(w_i, beta_h - [z_i] h)
+ * vk_g1 = {g, gamma_g} (2 x 104-byte ARK_MONT_LIMBS records), vk_g2 = {h, beta_h} (2 x 200 bytes); comms, proofs_w:
+ * n x 104; points (z), values (v), random_v: n x 32-byte little-endian scalars < r (random_v may be NULL: proofs
+ * without hiding).  ok[i] = 1 when opening i verifies.  Returns PTAU_ERR_ARG for a non-canonical scalar. */
+int ptau_kzg_check(ptau_ctx* ctx, const void* vk_g1, const void* vk_g2, const void* comms, const void* points,
+                   const void* values, const void* proofs_w, const void* random_v, size_t n, uint8_t* ok);
+/* prod_{k<2} e(P_ik, Q_ik) for n items (ark Bls12::product_of_pairings; a pair with a point at infinity counts as 1).
+ * g1: n x 2 x 104, g2: n x 2 x 200 (ARK_MONT_LIMBS).  gt_out (may be NULL): n x 576 bytes, the 12 Fq coefficients in
+ * arkworks' Fq12 order, canonical little-endian; is_one (may be NULL): n bytes.  KZG10::batch_check is one MSM
+ * (ptau_kzg_commit) followed by one such product against {beta_h, h}. */
+int ptau_pairing_product2(ptau_ctx* ctx, const void* g1, const void* g2, size_t n, void* gt_out, uint8_t* is_one);
+
 /* ---- self-test hook --------------------------------------------------------------- */
 /* Raw Fq operations on n pairs of 48-byte Montgomery-limb values (host pointers), computed by
  * the kernels' own field code on the GPU: op 0 mul, 1 add, 2 sub, 3 neg, 4 sqr, 5 a^((p-3)/4),

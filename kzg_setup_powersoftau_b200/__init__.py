@@ -284,12 +284,12 @@ R_ORDER = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001  # 
 
 
 class KZG10:
-    """First step of SURVEY 8f-4: the commitment side of ark-poly-commit 0.2 `KZG10` on the
-    GPU (the reference's consumer usage, src/lib.rs:266-286).  Polynomials are lists of
-    coefficients (ints mod r, low degree first).  Hiding: ark draws a random polynomial of
-    degree `hiding_bound`; here the caller passes its coefficients (`blinding`) so results
-    are reproducible.  `check` / `batch_check` need pairings and stay on the CPU side
-    (out of scope); tests verify commitments and proofs against the known tau."""
+    """ark-poly-commit 0.2 `KZG10` on the GPU (the reference's consumer usage,
+    src/lib.rs:266-286): `commit` / `open` (bucket MSM), `check` / `batch_check` (pairings).
+    Polynomials are lists of coefficients (ints mod r, low degree first).  Hiding: ark draws a
+    random polynomial of degree `hiding_bound`; here the caller passes its coefficients
+    (`blinding`) so results are reproducible, and `batch_check` takes its randomizers as an
+    argument for the same reason (ark draws u128s from the caller's rng)."""
 
     @staticmethod
     def _msm(ctx, pairs) -> np.ndarray:
@@ -343,6 +343,78 @@ class KZG10:
         return value, KZG10._msm(ctx, pairs), random_v
 
 
+    @staticmethod
+    def _scalars(vals) -> np.ndarray:
+        b = b"".join((int(v) % R_ORDER).to_bytes(32, "little") for v in vals)
+        return np.frombuffer(b, dtype=np.uint8) if b else np.zeros(0, dtype=np.uint8)
+
+    @staticmethod
+    def check_many(vk: "VerifierKey", comms, points, values, proofs, random_vs=None, ctx: Optional["Context"] = None) -> np.ndarray:
+        """KZG10::check for many openings at once (one GPU thread per opening).  comms / proofs: arrays of
+        104-byte records; points / values / random_vs: ints.  Returns a bool array."""
+        ctx = ctx or default_context()
+        n = len(points)
+        c = np.ascontiguousarray(np.asarray(comms, dtype=np.uint8).reshape(n, 104))
+        w = np.ascontiguousarray(np.asarray(proofs, dtype=np.uint8).reshape(n, 104))
+        g1 = np.ascontiguousarray(np.concatenate([vk.g.reshape(-1), vk.gamma_g.reshape(-1)]))
+        g2 = np.ascontiguousarray(np.concatenate([vk.h.reshape(-1), vk.beta_h.reshape(-1)]))
+        z, v = KZG10._scalars(points), KZG10._scalars(values)
+        rv = KZG10._scalars([0 if r is None else r for r in random_vs]) if random_vs is not None else None
+        ok = np.zeros(n, dtype=np.uint8)
+        rc = _ffi.lib().ptau_kzg_check(ctx._h, _ptr(g1), _ptr(g2), _ptr(c) if n else None, _ptr(z) if n else None,
+                                       _ptr(v) if n else None, _ptr(w) if n else None,
+                                       _ptr(rv) if (rv is not None and n) else None, n, _ptr(ok) if n else None)
+        if rc != 0:
+            ctx._raise(rc)
+        return ok.astype(bool)
+
+    @staticmethod
+    def check(vk: "VerifierKey", comm, point: int, value: int, proof, random_v=None, ctx: Optional["Context"] = None) -> bool:
+        """KZG10::check(&vk, &comm, point, value, &proof): e(C - [v]g - [rv]gamma_g, h) == e(w, beta_h - [z]h)."""
+        return bool(KZG10.check_many(vk, [comm], [point], [value], [proof], None if random_v is None else [random_v], ctx=ctx)[0])
+
+    @staticmethod
+    def pairing_product2(g1_pairs: np.ndarray, g2_pairs: np.ndarray, ctx: Optional["Context"] = None):
+        """prod_{k<2} e(P_ik, Q_ik) for n items: g1_pairs [n, 2, 104], g2_pairs [n, 2, 200] Montgomery-limb records.
+        Returns (gt [n, 576] canonical little-endian Fq12 coefficients in arkworks order, is_one [n] bool)."""
+        ctx = ctx or default_context()
+        a = np.ascontiguousarray(np.asarray(g1_pairs, dtype=np.uint8).reshape(-1, 2, 104))
+        b = np.ascontiguousarray(np.asarray(g2_pairs, dtype=np.uint8).reshape(-1, 2, 200))
+        n = a.shape[0]
+        gt = np.zeros((n, 576), dtype=np.uint8)
+        one = np.zeros(n, dtype=np.uint8)
+        if n:
+            rc = _ffi.lib().ptau_pairing_product2(ctx._h, _ptr(a), _ptr(b), n, _ptr(gt), _ptr(one))
+            if rc != 0:
+                ctx._raise(rc)
+        return gt, one.astype(bool)
+
+    @staticmethod
+    def batch_check(vk: "VerifierKey", comms, points, values, proofs, random_vs=None, randomizers=None,
+                    ctx: Optional["Context"] = None) -> bool:
+        """KZG10::batch_check: with randomizers r_i (ark: r_0 = 1, then u128s from the rng),
+            total_c = sum r_i (C_i + [z_i] w_i) - [sum r_i v_i] g - [sum r_i rv_i] gamma_g,   total_w = sum r_i w_i,
+            e(-total_w, beta_h) * e(total_c, h) == 1.
+        Both sums are one multi-scalar multiplication each (ptau_kzg_commit), followed by one pairing product."""
+        ctx = ctx or default_context()
+        n = len(points)
+        if randomizers is None:
+            randomizers = [1] + [int.from_bytes(os.urandom(16), "little") for _ in range(n - 1)]
+        c = np.asarray(comms, dtype=np.uint8).reshape(n, 104)
+        w = np.asarray(proofs, dtype=np.uint8).reshape(n, 104)
+        rvs = [0] * n if random_vs is None else [0 if r is None else int(r) for r in random_vs]
+        gm = sum(r * int(v) for r, v in zip(randomizers, values)) % R_ORDER
+        ggm = sum(r * rv for r, rv in zip(randomizers, rvs)) % R_ORDER
+        pts_c = np.concatenate([c, w, vk.g.reshape(1, 104), vk.gamma_g.reshape(1, 104)])
+        sc_c = [r % R_ORDER for r in randomizers] + [r * int(z) % R_ORDER for r, z in zip(randomizers, points)] + \
+               [(-gm) % R_ORDER, (-ggm) % R_ORDER]
+        total_c = KZG10._msm(ctx, [(pts_c, sc_c)])
+        total_w = KZG10._msm(ctx, [(w, [(-r) % R_ORDER for r in randomizers])])  # = -sum r_i w_i
+        g1 = np.stack([total_w, total_c]).reshape(1, 2, 104)
+        g2 = np.stack([vk.beta_h.reshape(-1), vk.h.reshape(-1)]).reshape(1, 2, 200)
+        return bool(KZG10.pairing_product2(g1, g2, ctx=ctx)[1][0])
+
+
 _default_ctx: Optional[Context] = None
 
 
@@ -380,8 +452,9 @@ class Powers:
 @dataclass
 class VerifierKey:
     """kzg10::VerifierKey { g, gamma_g, h, beta_h } (src/lib.rs:191-192).  prepared_h /
-    prepared_beta_h are Miller-loop precomputations of h and beta_h that ark derives
-    on the CPU from these two points (out of scope)."""
+    prepared_beta_h are Miller-loop line coefficients that ark derives from h and beta_h
+    when it reads the key; KZG10.check / batch_check here compute the same lines inside
+    their Miller loops (csrc/pairing.cuh), so the key keeps only the four points."""
     g: np.ndarray
     gamma_g: np.ndarray
     h: np.ndarray

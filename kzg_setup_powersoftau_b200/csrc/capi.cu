@@ -715,6 +715,106 @@ int ptau_kzg_commit(ptau_ctx* ctx, const void* powers, const void* coeffs, size_
   return PTAU_OK;
 }
 
+namespace {
+// device copies of a list of host arrays, freed together
+struct DevArgs {
+  std::vector<void*> ptrs;
+  ~DevArgs() {
+    for (void* p : ptrs) cudaFree(p);
+  }
+  cudaError_t push(const void* host, size_t bytes, cudaStream_t st, void** out) {
+    void* d = nullptr;
+    cudaError_t e = cudaMalloc(&d, bytes ? bytes : 16);
+    if (e != cudaSuccess) return e;
+    ptrs.push_back(d);
+    if (host && bytes) e = cudaMemcpyAsync(d, host, bytes, cudaMemcpyHostToDevice, st);
+    *out = d;
+    return e;
+  }
+};
+bool scalars_canonical(const void* p, size_t n) {
+  for (size_t i = 0; i < n; i++) {
+    Fr c = fr_from_le32((const uint8_t*)p + i * 32);
+    if (fr_ge_mod(c.l)) return false;
+  }
+  return true;
+}
+}  // namespace
+
+int ptau_pairing_product2(ptau_ctx* ctx, const void* g1, const void* g2, size_t n, void* gt_out, uint8_t* is_one) {
+  if (!ctx || (n && (!g1 || !g2)) || (!gt_out && !is_one)) return PTAU_ERR_ARG;
+  if (n == 0) return PTAU_OK;
+  GpuSlot& s = ctx->gpu[0];
+  CUDA_TRY(ctx, cudaSetDevice(s.device));
+  DevArgs a;
+  void *d1 = nullptr, *d2 = nullptr, *dgt = nullptr, *dis = nullptr;
+  cudaError_t e = a.push(g1, n * 2 * 104, s.stream[0], &d1);
+  if (e == cudaSuccess) e = a.push(g2, n * 2 * 200, s.stream[0], &d2);
+  if (e == cudaSuccess && gt_out) e = a.push(nullptr, n * 576, s.stream[0], &dgt);
+  if (e == cudaSuccess && is_one) e = a.push(nullptr, n, s.stream[0], &dis);
+  if (e == cudaSuccess) e = cudaEventRecord(s.ev_k0[0], s.stream[0]);
+  if (e == cudaSuccess) e = ptau::launch_pairing_product2(d1, d2, n, dgt, dis, s.stream[0]);
+  if (e == cudaSuccess) e = cudaEventRecord(s.ev_k1[0], s.stream[0]);
+  if (e == cudaSuccess && gt_out) e = cudaMemcpyAsync(gt_out, dgt, n * 576, cudaMemcpyDeviceToHost, s.stream[0]);
+  if (e == cudaSuccess && is_one) e = cudaMemcpyAsync(is_one, dis, n, cudaMemcpyDeviceToHost, s.stream[0]);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s.stream[0]);
+  float ms = 0;
+  if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, s.ev_k0[0], s.ev_k1[0]);
+  if (e != cudaSuccess) {
+    ctx->last_error = std::string("pairing_product2: ") + cudaGetErrorString(e);
+    return PTAU_ERR_CUDA;
+  }
+  memset(&ctx->timing, 0, sizeof(ctx->timing));
+  ctx->timing.n_gpus = ctx->n_gpus;
+  ctx->timing.kernel_ms[0] = ms;
+  ctx->timing.gpu_ms[0] = ms;
+  ctx->timing.kernel_launches = 1;
+  ctx->timing.h2d_bytes[0] = n * 608;
+  ctx->timing.d2h_bytes[0] = n * ((gt_out ? 576 : 0) + (is_one ? 1 : 0));
+  return PTAU_OK;
+}
+
+int ptau_kzg_check(ptau_ctx* ctx, const void* vk_g1, const void* vk_g2, const void* comms, const void* points,
+                   const void* values, const void* proofs_w, const void* random_v, size_t n, uint8_t* ok) {
+  if (!ctx || !vk_g1 || !vk_g2 || (n && (!comms || !points || !values || !proofs_w || !ok))) return PTAU_ERR_ARG;
+  if (n == 0) return PTAU_OK;
+  // scalars must be canonical (< r), like ark's Fr
+  if (!scalars_canonical(points, n) || !scalars_canonical(values, n) || (random_v && !scalars_canonical(random_v, n)))
+    return PTAU_ERR_ARG;
+  GpuSlot& s = ctx->gpu[0];
+  CUDA_TRY(ctx, cudaSetDevice(s.device));
+  DevArgs a;
+  void *dv1 = nullptr, *dv2 = nullptr, *dc = nullptr, *dz = nullptr, *dv = nullptr, *dw = nullptr, *drv = nullptr, *dok = nullptr;
+  cudaStream_t st = s.stream[0];
+  cudaError_t e = a.push(vk_g1, 2 * 104, st, &dv1);
+  if (e == cudaSuccess) e = a.push(vk_g2, 2 * 200, st, &dv2);
+  if (e == cudaSuccess) e = a.push(comms, n * 104, st, &dc);
+  if (e == cudaSuccess) e = a.push(points, n * 32, st, &dz);
+  if (e == cudaSuccess) e = a.push(values, n * 32, st, &dv);
+  if (e == cudaSuccess) e = a.push(proofs_w, n * 104, st, &dw);
+  if (e == cudaSuccess && random_v) e = a.push(random_v, n * 32, st, &drv);
+  if (e == cudaSuccess) e = a.push(nullptr, n, st, &dok);
+  if (e == cudaSuccess) e = cudaEventRecord(s.ev_k0[0], st);
+  if (e == cudaSuccess) e = ptau::launch_kzg_check(dv1, dv2, dc, dz, dv, dw, drv, n, dok, st);
+  if (e == cudaSuccess) e = cudaEventRecord(s.ev_k1[0], st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(ok, dok, n, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  float ms = 0;
+  if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, s.ev_k0[0], s.ev_k1[0]);
+  if (e != cudaSuccess) {
+    ctx->last_error = std::string("kzg_check: ") + cudaGetErrorString(e);
+    return PTAU_ERR_CUDA;
+  }
+  memset(&ctx->timing, 0, sizeof(ctx->timing));
+  ctx->timing.n_gpus = ctx->n_gpus;
+  ctx->timing.kernel_ms[0] = ms;
+  ctx->timing.gpu_ms[0] = ms;
+  ctx->timing.kernel_launches = 1;
+  ctx->timing.h2d_bytes[0] = 608 + n * (104 + 32 + 32 + 104 + (random_v ? 32 : 0));
+  ctx->timing.d2h_bytes[0] = n;
+  return PTAU_OK;
+}
+
 int ptau_selftest_fq_op(ptau_ctx* ctx, int gpu, int op, const void* a, const void* b, void* out, size_t n) {
   if (!ctx || gpu < 0 || gpu >= ctx->n_gpus || !a || !b || !out) return PTAU_ERR_ARG;
   GpuSlot& s = ctx->gpu[gpu];

@@ -30,6 +30,14 @@ void msm_g1_plan(uint64_t n, MsmPlan* plan);
 cudaError_t launch_msm_g1(const void* d_pts, const void* d_scalars, uint64_t n, void* d_scratch, void* d_out,
                           int* launches, cudaStream_t stream);
 
+// kzg.cu: prod_{k<2} e(P_ik, Q_ik) for n items (d_gt: n x 576 bytes or null, d_is_one: n bytes or null), and
+// KZG10::check for n openings (d_random_v may be null: no hiding), one item per thread
+cudaError_t launch_pairing_product2(const void* d_g1, const void* d_g2, uint64_t n, void* d_gt, void* d_is_one,
+                                    cudaStream_t stream);
+cudaError_t launch_kzg_check(const void* d_vk_g1, const void* d_vk_g2, const void* d_comms, const void* d_points,
+                             const void* d_values, const void* d_proofs, const void* d_random_v, uint64_t n, void* d_ok,
+                             cudaStream_t stream);
+
 cudaError_t launch_fq_op(int op, const void* d_a, const void* d_b, void* d_out, uint64_t n, cudaStream_t stream);
 
 cudaError_t launch_microbench(int kind, int iters, uint32_t* d_out, int grid, int block, double* ops,

@@ -1,0 +1,363 @@
+// BLS12-381 optimal ate pairing on the device: the tower Fq2[v]/(v^3 - (1+u)) = Fq6, Fq6[w]/(w^2 - v) = Fq12,
+// the Miller loop with projective line coefficients, and the final exponentiation.
+//
+// What this restates: ark-ec 0.2.0 models/bls12 (G2Prepared doubling_step / addition_step, ell with the
+// M-type twist, miller_loop over BitIterator(|z|) with the final conjugation for z < 0, final_exponentiation)
+// as reached from ark-poly-commit 0.2 KZG10::check / batch_check, which is what the reference's consumer
+// code calls (/root/reference/src/lib.rs:276-286: KZG10::check(&vk, &comm, point, value, &proof)).
+// The hard part of the final exponentiation uses
+//     (p^4 - p^2 + 1) / r = ((z-1)^2 / 3) (z + p) (z^2 + p^2 - 1) + 1
+// (checked numerically in tests/test_oracle_pins.py), i.e. the exact exponent, not its multiple by 3, so the
+// value in GT is the same as a plain f^((p^12-1)/r).
+//
+// One pairing product per thread; an Fq12 is 144 registers' worth of limbs, so these functions work on
+// references to thread-local values and are not inlined.  This is a latency-tolerant side path (two pairings
+// per KZG opening), data-parallel over openings, not a throughput kernel like the point path.
+#pragma once
+#include "curve.cuh"
+
+namespace ptau {
+
+struct Fq6 {
+  Fq2 c0, c1, c2;
+};
+struct Fq12 {
+  Fq6 c0, c1;
+};
+
+#ifdef __CUDACC__
+__constant__ uint32_t K_PM2_PAIR[12] = {0xffffaaa9u, 0xb9feffffu, 0xb153ffffu, 0x1eabfffeu, 0xf6b0f624u, 0x6730d2a0u,
+                                        0xf38512bfu, 0x64774b84u, 0x434bacd7u, 0x4b1ba7b6u, 0x397fe69au, 0x1a0111eau};
+// (z-1)^2 / 3 = 0x396c8c005555e1568c00aaab0000aaab (126 bits)
+__constant__ uint32_t K_H1[4] = {0x0000aaabu, 0x8c00aaabu, 0x5555e156u, 0x396c8c00u};
+
+// a^(p-2)
+static __device__ __noinline__ Fq fq_inv_fermat(Fq a) {
+  Fq acc = a;
+#pragma unroll 1
+  for (int i = 379; i >= 0; --i) {
+    acc = fq_sqr(acc);
+    if ((K_PM2_PAIR[i >> 5] >> (i & 31)) & 1u) acc = fq_mul(acc, a);
+  }
+  return acc;
+}
+static __device__ __noinline__ Fq2 fq2_inv(const Fq2& a) {
+  Fq n = fq_inv_fermat(fq_add(fq_sqr(a.c0), fq_sqr(a.c1)));
+  Fq2 r;
+  r.c0 = fq_mul(a.c0, n);
+  r.c1 = fq_neg(fq_mul(a.c1, n));
+  return r;
+}
+static __device__ __forceinline__ Fq finv(const Fq& a) { return fq_inv_fermat(a); }
+static __device__ __forceinline__ Fq2 finv(const Fq2& a) { return fq2_inv(a); }
+
+// a * (1 + u)
+static __device__ __forceinline__ Fq2 fq2_mul_xi(const Fq2& a) {
+  Fq2 r;
+  r.c0 = fq_sub(a.c0, a.c1);
+  r.c1 = fq_add(a.c0, a.c1);
+  return r;
+}
+
+// ---- Fq6 ----------------------------------------------------------------------------------------
+static __device__ __forceinline__ void fq6_add(Fq6& r, const Fq6& a, const Fq6& b) {
+  r.c0 = fq2_add(a.c0, b.c0);
+  r.c1 = fq2_add(a.c1, b.c1);
+  r.c2 = fq2_add(a.c2, b.c2);
+}
+static __device__ __forceinline__ void fq6_sub(Fq6& r, const Fq6& a, const Fq6& b) {
+  r.c0 = fq2_sub(a.c0, b.c0);
+  r.c1 = fq2_sub(a.c1, b.c1);
+  r.c2 = fq2_sub(a.c2, b.c2);
+}
+static __device__ __forceinline__ void fq6_neg(Fq6& r, const Fq6& a) {
+  r.c0 = fq2_neg(a.c0);
+  r.c1 = fq2_neg(a.c1);
+  r.c2 = fq2_neg(a.c2);
+}
+// Karatsuba, 6 Fq2 multiplications; r may alias a or b
+static __device__ __noinline__ void fq6_mul(Fq6& r, const Fq6& a, const Fq6& b) {
+  Fq2 v0 = fq2_mul(a.c0, b.c0), v1 = fq2_mul(a.c1, b.c1), v2 = fq2_mul(a.c2, b.c2);
+  Fq2 t0 = fq2_sub(fq2_sub(fq2_mul(fq2_add(a.c1, a.c2), fq2_add(b.c1, b.c2)), v1), v2);
+  Fq2 t1 = fq2_sub(fq2_sub(fq2_mul(fq2_add(a.c0, a.c1), fq2_add(b.c0, b.c1)), v0), v1);
+  Fq2 t2 = fq2_sub(fq2_sub(fq2_mul(fq2_add(a.c0, a.c2), fq2_add(b.c0, b.c2)), v0), v2);
+  r.c0 = fq2_add(v0, fq2_mul_xi(t0));
+  r.c1 = fq2_add(t1, fq2_mul_xi(v2));
+  r.c2 = fq2_add(t2, v1);
+}
+// a * v
+static __device__ __forceinline__ void fq6_mul_v(Fq6& r, const Fq6& a) {
+  Fq2 t = fq2_mul_xi(a.c2);
+  r.c2 = a.c1;
+  r.c1 = a.c0;
+  r.c0 = t;
+}
+static __device__ __noinline__ void fq6_inv(Fq6& r, const Fq6& a) {
+  Fq2 t0 = fq2_sub(fq2_sqr(a.c0), fq2_mul_xi(fq2_mul(a.c1, a.c2)));
+  Fq2 t1 = fq2_sub(fq2_mul_xi(fq2_sqr(a.c2)), fq2_mul(a.c0, a.c1));
+  Fq2 t2 = fq2_sub(fq2_sqr(a.c1), fq2_mul(a.c0, a.c2));
+  Fq2 d = fq2_add(fq2_mul(a.c0, t0), fq2_mul_xi(fq2_add(fq2_mul(a.c2, t1), fq2_mul(a.c1, t2))));
+  Fq2 di = fq2_inv(d);
+  r.c0 = fq2_mul(t0, di);
+  r.c1 = fq2_mul(t1, di);
+  r.c2 = fq2_mul(t2, di);
+}
+// Frobenius: conjugate the Fq2 coefficients, times xi^((p-1)/3), xi^(2(p-1)/3)
+static __device__ __noinline__ void fq6_frob(Fq6& r, const Fq6& a) {
+  Fq2 g1, g2;
+  g1.c0 = k_frob6_1_c0_mont();
+  g1.c1 = k_frob6_1_c1_mont();
+  g2.c0 = k_frob6_2_c0_mont();
+  g2.c1 = k_frob6_2_c1_mont();
+  r.c0 = fq2_conj(a.c0);
+  r.c1 = fq2_mul(fq2_conj(a.c1), g1);
+  r.c2 = fq2_mul(fq2_conj(a.c2), g2);
+}
+
+// ---- Fq12 ---------------------------------------------------------------------------------------
+static __device__ __forceinline__ void fq12_one(Fq12& r) {
+  r.c0.c0 = fq2_one();
+  r.c0.c1 = fq2_zero();
+  r.c0.c2 = fq2_zero();
+  r.c1.c0 = fq2_zero();
+  r.c1.c1 = fq2_zero();
+  r.c1.c2 = fq2_zero();
+}
+// r = a * b (3 Fq6 multiplications); r may alias a or b
+static __device__ __noinline__ void fq12_mul(Fq12& r, const Fq12& a, const Fq12& b) {
+  Fq6 v0, v1, s, t;
+  fq6_mul(v0, a.c0, b.c0);
+  fq6_mul(v1, a.c1, b.c1);
+  fq6_add(s, a.c0, a.c1);
+  fq6_add(t, b.c0, b.c1);
+  fq6_mul(s, s, t);
+  fq6_sub(s, s, v0);
+  fq6_sub(r.c1, s, v1);
+  fq6_mul_v(t, v1);
+  fq6_add(r.c0, v0, t);
+}
+static __device__ __forceinline__ void fq12_conj(Fq12& r, const Fq12& a) {
+  r.c0 = a.c0;
+  fq6_neg(r.c1, a.c1);
+}
+static __device__ __noinline__ void fq12_inv(Fq12& r, const Fq12& a) {
+  Fq6 t, u;
+  fq6_mul(t, a.c0, a.c0);
+  fq6_mul(u, a.c1, a.c1);
+  fq6_mul_v(u, u);
+  fq6_sub(t, t, u);
+  fq6_inv(t, t);
+  fq6_mul(u, a.c1, t);
+  fq6_mul(r.c0, a.c0, t);
+  fq6_neg(r.c1, u);
+}
+static __device__ __noinline__ void fq12_frob(Fq12& r, const Fq12& a) {
+  Fq2 g;
+  g.c0 = k_frob12_c0_mont();
+  g.c1 = k_frob12_c1_mont();
+  fq6_frob(r.c0, a.c0);
+  Fq6 t;
+  fq6_frob(t, a.c1);
+  r.c1.c0 = fq2_mul(t.c0, g);
+  r.c1.c1 = fq2_mul(t.c1, g);
+  r.c1.c2 = fq2_mul(t.c2, g);
+}
+static __device__ __noinline__ bool fq12_is_one(const Fq12& a) {
+  bool ok = fq2_eq(a.c0.c0, fq2_one());
+  ok = ok && fq2_is_zero(a.c0.c1) && fq2_is_zero(a.c0.c2);
+  ok = ok && fq2_is_zero(a.c1.c0) && fq2_is_zero(a.c1.c1) && fq2_is_zero(a.c1.c2);
+  return ok;
+}
+// r = a^e, e = nbits-bit exponent in 32-bit words, top bit set
+static __device__ __noinline__ void fq12_pow(Fq12& r, const Fq12& a, const uint32_t* e, int nbits) {
+  Fq12 acc = a;
+#pragma unroll 1
+  for (int i = nbits - 2; i >= 0; --i) {
+    fq12_mul(acc, acc, acc);
+    if ((e[i >> 5] >> (i & 31)) & 1u) fq12_mul(acc, acc, a);
+  }
+  r = acc;
+}
+// a^z for a in the cyclotomic subgroup (z < 0: inverse = conjugate)
+static __device__ __noinline__ void fq12_exp_z(Fq12& r, const Fq12& a) {
+  const uint32_t za[2] = {0x00010000u, 0xd2010000u};
+  Fq12 t;
+  fq12_pow(t, a, za, 64);
+  fq12_conj(r, t);
+}
+
+// f^((p^12 - 1) / r)
+static __device__ __noinline__ void final_exponentiation(Fq12& r, const Fq12& f) {
+  Fq12 m, t, a, b, c;
+  fq12_conj(t, f);
+  fq12_inv(m, f);
+  fq12_mul(m, t, m);  // f^(p^6 - 1)
+  fq12_frob(t, m);
+  fq12_frob(t, t);
+  fq12_mul(m, t, m);  // ^(p^2 + 1): m is in the cyclotomic subgroup from here on
+  {
+    uint32_t h1[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) h1[i] = K_H1[i];
+    fq12_pow(a, m, h1, 126);  // ^((z-1)^2 / 3)
+  }
+  fq12_exp_z(b, a);
+  fq12_frob(t, a);
+  fq12_mul(b, b, t);  // ^(z + p)
+  fq12_exp_z(c, b);
+  fq12_exp_z(c, c);
+  fq12_frob(t, b);
+  fq12_frob(t, t);
+  fq12_mul(c, c, t);
+  fq12_conj(t, b);
+  fq12_mul(c, c, t);  // ^(z^2 + p^2 - 1)
+  fq12_mul(r, c, m);  // + 1
+}
+
+// ---- Miller loop (ark-ec 0.2 bls12, TwistType::M) -------------------------------------------------
+struct G2Hom {
+  Fq2 x, y, z;
+};
+struct EllCoeff {
+  Fq2 c0, c1, c2;
+};
+
+static __device__ __noinline__ void doubling_step(G2Hom& r, EllCoeff& co) {
+  const Fq two_inv = k_half_mont();
+  Fq2 a = fq2_mul_fq(fq2_mul(r.x, r.y), two_inv);
+  Fq2 b = fq2_sqr(r.y);
+  Fq2 c = fq2_sqr(r.z);
+  Fq2 bt;
+  bt.c0 = k_b1_mont();
+  bt.c1 = bt.c0;
+  Fq2 e = fq2_mul(bt, fq2_add(fq2_dbl(c), c));
+  Fq2 f = fq2_add(fq2_dbl(e), e);
+  Fq2 g = fq2_mul_fq(fq2_add(b, f), two_inv);
+  Fq2 h = fq2_sub(fq2_sqr(fq2_add(r.y, r.z)), fq2_add(b, c));
+  Fq2 i = fq2_sub(e, b);
+  Fq2 j = fq2_sqr(r.x);
+  Fq2 e2 = fq2_sqr(e);
+  r.x = fq2_mul(a, fq2_sub(b, f));
+  r.y = fq2_sub(fq2_sqr(g), fq2_add(fq2_dbl(e2), e2));
+  r.z = fq2_mul(b, h);
+  co.c0 = i;
+  co.c1 = fq2_add(fq2_dbl(j), j);
+  co.c2 = fq2_neg(h);
+}
+static __device__ __noinline__ void addition_step(G2Hom& r, const Fq2& qx, const Fq2& qy, EllCoeff& co) {
+  Fq2 theta = fq2_sub(r.y, fq2_mul(qy, r.z));
+  Fq2 lambda = fq2_sub(r.x, fq2_mul(qx, r.z));
+  Fq2 c = fq2_sqr(theta);
+  Fq2 d = fq2_sqr(lambda);
+  Fq2 e = fq2_mul(lambda, d);
+  Fq2 f = fq2_mul(r.z, c);
+  Fq2 g = fq2_mul(r.x, d);
+  Fq2 h = fq2_sub(fq2_add(e, f), fq2_dbl(g));
+  r.x = fq2_mul(lambda, h);
+  r.y = fq2_sub(fq2_mul(theta, fq2_sub(g, h)), fq2_mul(e, r.y));
+  r.z = fq2_mul(r.z, e);
+  co.c0 = fq2_sub(fq2_mul(theta, qx), fq2_mul(lambda, qy));
+  co.c1 = fq2_neg(theta);
+  co.c2 = lambda;
+}
+// f *= (c0 + c1 px v) + (c2 py v) w     (ark: mul_by_014)
+static __device__ __noinline__ void ell(Fq12& f, const EllCoeff& co, const Fq& px, const Fq& py) {
+  Fq12 s;
+  s.c0.c0 = co.c0;
+  s.c0.c1 = fq2_mul_fq(co.c1, px);
+  s.c0.c2 = fq2_zero();
+  s.c1.c0 = fq2_zero();
+  s.c1.c1 = fq2_mul_fq(co.c2, py);
+  s.c1.c2 = fq2_zero();
+  fq12_mul(f, f, s);
+}
+
+// Miller value of up to two pairs (P_k affine in G1, Q_k affine on the twist); a pair with use[k] == false
+// (P or Q at infinity) contributes 1, like ark's filter in miller_loop.
+static __device__ __noinline__ void miller_loop2(Fq12& f, const Fq* px, const Fq* py, const Fq2* qx, const Fq2* qy,
+                                                 const bool* use) {
+  fq12_one(f);
+  G2Hom r[2];
+#pragma unroll
+  for (int k = 0; k < 2; k++) {
+    r[k].x = qx[k];
+    r[k].y = qy[k];
+    r[k].z = fq2_one();
+  }
+  EllCoeff co;
+#pragma unroll 1
+  for (int i = 62; i >= 0; --i) {
+    fq12_mul(f, f, f);
+#pragma unroll 1
+    for (int k = 0; k < 2; k++) {
+      if (!use[k]) continue;
+      doubling_step(r[k], co);
+      ell(f, co, px[k], py[k]);
+    }
+    if ((PTAU_Z_ABS >> i) & 1ull) {
+#pragma unroll 1
+      for (int k = 0; k < 2; k++) {
+        if (!use[k]) continue;
+        addition_step(r[k], qx[k], qy[k], co);
+        ell(f, co, px[k], py[k]);
+      }
+    }
+  }
+  fq12_conj(f, f);  // z < 0
+}
+
+// ---- group operations with every special case, generic over the field -----------------------------------
+template <class F>
+static __device__ __noinline__ void jac_madd_complete_t(Jac<F>& acc, const F& x, const F& y, const F& one) {
+  if (fis_zero(acc.Z)) {
+    acc.X = x;
+    acc.Y = y;
+    acc.Z = one;
+    return;
+  }
+  F zz = fsqr(acc.Z);
+  F u2 = fmul(x, zz);
+  F s2 = fmul(fmul(y, acc.Z), zz);
+  if (feq(u2, acc.X)) {
+    if (feq(s2, acc.Y)) {
+      jac_dbl(acc);
+    } else {
+      acc.Z = fsub(acc.Z, acc.Z);  // P + (-P)
+    }
+    return;
+  }
+  F H = fsub(u2, acc.X);
+  F I = fsqr(fdbl(H));
+  F J = fmul(H, I);
+  F rr = fdbl(fsub(s2, acc.Y));
+  F V = fmul(acc.X, I);
+  F X3 = fsub(fsub(fsqr(rr), J), fdbl(V));
+  acc.Y = fsub(fmul(rr, fsub(V, X3)), fdbl(fmul(acc.Y, J)));
+  acc.Z = fdbl(fmul(acc.Z, H));
+  acc.X = X3;
+}
+// acc = [k] (x, y), k = 8 little-endian words (< 2^255); double-and-add
+template <class F>
+static __device__ __noinline__ void jac_scalar_mul_t(Jac<F>& acc, const F& x, const F& y, const uint32_t* k, const F& one) {
+  acc.X = fsub(one, one);
+  acc.Y = one;
+  acc.Z = acc.X;
+#pragma unroll 1
+  for (int i = 254; i >= 0; --i) {
+    if (!fis_zero(acc.Z)) jac_dbl(acc);
+    if ((k[i >> 5] >> (i & 31)) & 1u) jac_madd_complete_t(acc, x, y, one);
+  }
+}
+// Jacobian -> affine; returns false for the point at infinity
+template <class F>
+static __device__ __noinline__ bool jac_to_affine_t(const Jac<F>& p, F& x, F& y) {
+  if (fis_zero(p.Z)) return false;
+  F zi = finv(p.Z);
+  F zi2 = fsqr(zi);
+  x = fmul(p.X, zi2);
+  y = fmul(p.Y, fmul(zi2, zi));
+  return true;
+}
+#endif  // __CUDACC__
+
+}  // namespace ptau

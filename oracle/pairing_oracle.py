@@ -1,0 +1,242 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU restatement of the BLS12-381 pairing and of ark-poly-commit 0.2
+KZG10::check / batch_check (the consumer calls at /root/reference/src/lib.rs:276-286), for the
+parity tests of the GPU pairing.  Never imported by the product.
+
+Deliberately *not* the algorithm the GPU runs: Fq12 is the flat polynomial ring
+Fq[w] / (w^12 - 2 w^6 + 2) (so u = w^6 - 1, v = w^2 in terms of the tower Fq2[v]/(v^3 - (1+u))[w]/(w^2 - v)),
+both pairing arguments are mapped into E(Fq12), the Miller loop uses affine chord-and-tangent lines
+with generic Fq12 inversions, and the final exponentiation is one plain square-and-multiply by
+(p^12 - 1) / r.  The GPU uses the tower, projective line coefficients in Fq2 (ark-ec 0.2
+models/bls12: doubling_step / addition_step / ell) and the (p^6-1)(p^2+1) * hard-part split.
+
+Sign convention: z < 0.  ark-ec conjugates the Miller value when X_IS_NEGATIVE (f_{z,Q} =
+1 / f_{|z|,Q} up to factors the final exponentiation kills), so pairing() below inverts the result of
+the |z| loop.  Parity of the *value* with arkworks is unpinned (no arkworks here); what is pinned is
+bilinearity, non-degeneracy, e(P,Q)^r = 1 and agreement between this file and the GPU.
+"""
+from typing import List, Optional, Sequence, Tuple
+
+import ptau_oracle as o
+
+P = o.P
+R_ORDER = o.R_ORDER
+F12 = List[int]
+
+F12_ONE: F12 = [1] + [0] * 11
+F12_ZERO: F12 = [0] * 12
+
+
+def f12_mul(a: F12, b: F12) -> F12:
+    t = [0] * 23
+    for i, ai in enumerate(a):
+        if ai:
+            for j, bj in enumerate(b):
+                if bj:
+                    t[i + j] += ai * bj
+    for k in range(22, 11, -1):  # w^12 = 2 w^6 - 2
+        c = t[k]
+        if c:
+            t[k - 6] += 2 * c
+            t[k - 12] -= 2 * c
+    return [x % P for x in t[:12]]
+
+
+def f12_add(a: F12, b: F12) -> F12:
+    return [(x + y) % P for x, y in zip(a, b)]
+
+
+def f12_sub(a: F12, b: F12) -> F12:
+    return [(x - y) % P for x, y in zip(a, b)]
+
+
+def f12_scalar(a: F12, k: int) -> F12:
+    return [(x * k) % P for x in a]
+
+
+def _poly_deg(a):
+    d = len(a) - 1
+    while d >= 0 and a[d] == 0:
+        d -= 1
+    return d
+
+
+def f12_inv(a: F12) -> F12:
+    """Extended Euclid in Fq[w] against the modulus w^12 - 2 w^6 + 2."""
+    lm, hm = [1] + [0] * 12, [0] * 13
+    low, high = list(a) + [0], [2, 0, 0, 0, 0, 0, (-2) % P, 0, 0, 0, 0, 0, 1]
+    while _poly_deg(low) > 0:
+        # r = high / low (polynomial division, rounded)
+        dl, dh = _poly_deg(low), _poly_deg(high)
+        r = [0] * 13
+        temp = list(high)
+        inv_lead = pow(low[dl], -1, P)
+        for i in range(dh - dl, -1, -1):
+            q = temp[dl + i] * inv_lead % P
+            r[i] = q
+            if q:
+                for c in range(dl + 1):
+                    temp[c + i] = (temp[c + i] - low[c] * q) % P
+        nm, new = list(hm), list(high)
+        for i in range(13):
+            if lm[i] or low[i]:
+                for j in range(13 - i):
+                    if r[j]:
+                        nm[i + j] = (nm[i + j] - lm[i] * r[j]) % P
+                        new[i + j] = (new[i + j] - low[i] * r[j]) % P
+        lm, low, hm, high = nm, new, lm, low
+    assert low[0] != 0, "not invertible"
+    inv0 = pow(low[0], -1, P)
+    return [(x * inv0) % P for x in lm[:12]]
+
+
+def f12_pow(a: F12, e: int) -> F12:
+    r = F12_ONE
+    for bit in bin(e)[2:]:
+        r = f12_mul(r, r)
+        if bit == "1":
+            r = f12_mul(r, a)
+    return r
+
+
+def f12_from_fq2(a) -> F12:
+    """a0 + a1 u with u = w^6 - 1."""
+    r = [0] * 12
+    r[0] = (a[0] - a[1]) % P
+    r[6] = a[1] % P
+    return r
+
+
+def f12_from_tower(c) -> F12:
+    """Tower element given as 12 Fq coefficients in arkworks order
+    c[i][j][k] : i in Fq12 (w^i), j in Fq6 (v^j), k in Fq2 (u^k), flattened i-major -> the flat basis.
+    u^k v^j w^i = (w^6 - 1)^k w^(2j + i)."""
+    r = [0] * 12
+    for i in range(2):
+        for j in range(3):
+            a0, a1 = c[(i * 3 + j) * 2], c[(i * 3 + j) * 2 + 1]
+            e = 2 * j + i
+            r[e] = (r[e] + a0 - a1) % P
+            r[e + 6] = (r[e + 6] + a1) % P
+    return r
+
+
+_W = [0, 1] + [0] * 10
+_W2_INV = f12_inv(f12_mul(_W, _W))
+_W3_INV = f12_inv(f12_mul(f12_mul(_W, _W), _W))
+
+
+def twist(q):
+    """E'(Fq2) -> E(Fq12): (x, y) -> (x / w^2, y / w^3)  (M-type twist, b' = 4(1+u) = 4 w^6)."""
+    return f12_mul(f12_from_fq2(q[0]), _W2_INV), f12_mul(f12_from_fq2(q[1]), _W3_INV)
+
+
+def cast_g1(p):
+    return [p[0] % P] + [0] * 11, [p[1] % P] + [0] * 11
+
+
+def _e12_double(pt):
+    x, y = pt
+    m = f12_mul(f12_scalar(f12_mul(x, x), 3), f12_inv(f12_scalar(y, 2)))
+    nx = f12_sub(f12_mul(m, m), f12_scalar(x, 2))
+    ny = f12_sub(f12_mul(m, f12_sub(x, nx)), y)
+    return nx, ny
+
+
+def _e12_add(p1, p2):
+    if p1 is None:
+        return p2
+    if p2 is None:
+        return p1
+    x1, y1 = p1
+    x2, y2 = p2
+    if x1 == x2:
+        return _e12_double(p1) if y1 == y2 else None
+    m = f12_mul(f12_sub(y2, y1), f12_inv(f12_sub(x2, x1)))
+    nx = f12_sub(f12_sub(f12_mul(m, m), x1), x2)
+    ny = f12_sub(f12_mul(m, f12_sub(x1, nx)), y1)
+    return nx, ny
+
+
+def _linefunc(p1, p2, t):
+    """Line through p1, p2 (tangent if equal) evaluated at t."""
+    x1, y1 = p1
+    x2, y2 = p2
+    xt, yt = t
+    if x1 != x2:
+        m = f12_mul(f12_sub(y2, y1), f12_inv(f12_sub(x2, x1)))
+    elif y1 == y2:
+        m = f12_mul(f12_scalar(f12_mul(x1, x1), 3), f12_inv(f12_scalar(y1, 2)))
+    else:
+        return f12_sub(xt, x1)
+    return f12_sub(f12_mul(m, f12_sub(xt, x1)), f12_sub(yt, y1))
+
+
+def miller_loop_abs_z(q12, p12) -> F12:
+    """f_{|z|, Q}(P), |z| = 0xd201000000010000."""
+    r = q12
+    f = F12_ONE
+    for i in range(62, -1, -1):
+        f = f12_mul(f12_mul(f, f), _linefunc(r, r, p12))
+        r = _e12_double(r)
+        if (o.Z_ABS >> i) & 1:
+            f = f12_mul(f, _linefunc(r, q12, p12))
+            r = _e12_add(r, q12)
+    return f
+
+
+FINAL_EXP = (P ** 12 - 1) // R_ORDER
+
+
+def miller_product(pairs: Sequence[Tuple[Optional[tuple], Optional[tuple]]]) -> F12:
+    f = F12_ONE
+    for p, q in pairs:
+        if p is None or q is None:  # pairing with the point at infinity is 1
+            continue
+        f = f12_mul(f, miller_loop_abs_z(twist(q), cast_g1(p)))
+    return f
+
+
+def product_of_pairings(pairs) -> F12:
+    """prod e(P_i, Q_i) with ark's sign convention for z < 0 (see the module docstring)."""
+    return f12_inv(f12_pow(miller_product(pairs), FINAL_EXP))
+
+
+def pairing(p, q) -> F12:
+    return product_of_pairings([(p, q)])
+
+
+# ---- ark-poly-commit 0.2 kzg10 ---------------------------------------------------------------
+def _g1_sub(a, b):
+    nb = None if b is None else (b[0], (-b[1]) % P)
+    return o.affine_add(o._F1, a, nb)
+
+
+def kzg_check(vk, comm, point: int, value: int, proof_w, random_v: Optional[int]) -> bool:
+    """KZG10::check: e(C - [v]g - [rv]gamma_g, h) == e(w, beta_h - [z]h).
+    vk = (g, gamma_g, h, beta_h) affine points (None = infinity)."""
+    g, gamma_g, h, beta_h = vk
+    inner = _g1_sub(comm, o.g1_mul(g, value % R_ORDER))
+    if random_v is not None:
+        inner = _g1_sub(inner, o.g1_mul(gamma_g, random_v % R_ORDER))
+    zh = o.g2_mul(h, point % R_ORDER)
+    nzh = None if zh is None else (zh[0], o.fq2_neg(zh[1]))
+    q2 = o.affine_add(o._F2, beta_h, nzh)
+    return pairing(inner, h) == pairing(proof_w, q2)
+
+
+def kzg_batch_check(vk, comms, points, values, proofs, randomizers) -> bool:
+    """KZG10::batch_check with the caller's randomizers (ark draws u128s; the first one is 1):
+    e(sum r_i (C_i + [z_i] w_i) - [sum r_i v_i] g - [sum r_i rv_i] gamma_g, h) * e(-sum r_i w_i, beta_h) == 1."""
+    g, gamma_g, h, beta_h = vk
+    total_c, total_w, gm, ggm = None, None, 0, 0
+    for c, z, v, (w, rv), r in zip(comms, points, values, proofs, randomizers):
+        temp = o.affine_add(o._F1, o.g1_mul(w, z % R_ORDER), c)
+        total_c = o.affine_add(o._F1, total_c, o.g1_mul(temp, r))
+        total_w = o.affine_add(o._F1, total_w, o.g1_mul(w, r))
+        gm = (gm + r * v) % R_ORDER
+        if rv is not None:
+            ggm = (ggm + r * rv) % R_ORDER
+    total_c = _g1_sub(total_c, o.g1_mul(g, gm))
+    total_c = _g1_sub(total_c, o.g1_mul(gamma_g, ggm))
+    neg_w = None if total_w is None else (total_w[0], (-total_w[1]) % P)
+    return product_of_pairings([(neg_w, beta_h), (total_c, h)]) == F12_ONE

@@ -642,6 +642,120 @@ def test_msm_bucket_method_window_widths_and_adversarial_scalars(ctx):
     assert msm(holes, sc) == rec(sum(c * t for i, (c, t) in enumerate(zip(sc, tp)) if i % 3))
 
 
+def _g1_rec(q):
+    return np.frombuffer(o.g1_mont_record(0, 1, True) if q is None else o.g1_mont_record(q[0], q[1], False), dtype=np.uint8)
+
+
+def _g2_rec(q):
+    z2 = (0, 0)
+    return np.frombuffer(o.g2_mont_record(z2, (1, 0), True) if q is None else o.g2_mont_record(q[0], q[1], False), dtype=np.uint8)
+
+
+def test_pairing_value_vs_oracle(ctx):
+    """GPU pairing (tower arithmetic, projective lines, split final exponentiation) against the independent
+    CPU restatement (flat Fq12, affine lines in E(Fq12), one plain exponentiation): the 576 GT bytes themselves."""
+    import pairing_oracle as po
+
+    rnd = random.Random(5)
+    a, b, c, d = (rnd.randrange(1, o.R_ORDER) for _ in range(4))
+    P1, Q1, P2, Q2 = o.g1_mul(o.G1_GEN, a), o.g2_mul(o.G2_GEN, b), o.g1_mul(o.G1_GEN, c), o.g2_mul(o.G2_GEN, d)
+    negP1 = (P1[0], (-P1[1]) % o.P)
+    items = [((P1, Q1), (None, Q2)),           # one pairing, the other slot at infinity
+             ((P1, Q1), (P2, Q2)),             # product of two
+             ((P1, Q1), (negP1, Q1)),          # = 1
+             ((P2, None), (None, None)),       # empty product = 1
+             ((o.G1_GEN, o.G2_GEN), (None, None))]
+    g1 = np.stack([np.stack([_g1_rec(p) for p, _ in it]) for it in items])
+    g2 = np.stack([np.stack([_g2_rec(q) for _, q in it]) for it in items])
+    gt, one = kz.KZG10.pairing_product2(g1, g2, ctx=ctx)
+    assert list(one) == [False, False, True, True, False]
+
+    def flat(rec):
+        coeffs = [int.from_bytes(rec[48 * i:48 * i + 48].tobytes(), "little") for i in range(12)]
+        assert all(v < o.P for v in coeffs)
+        return po.f12_from_tower(coeffs)
+
+    e11 = po.pairing(P1, Q1)
+    assert flat(gt[0]) == e11
+    assert flat(gt[1]) == po.f12_mul(e11, po.pairing(P2, Q2))
+    assert flat(gt[2]) == po.F12_ONE and flat(gt[3]) == po.F12_ONE
+    # bilinearity on the GPU value: e(aG, bH) == e(G, H)^(ab)
+    assert e11 == po.f12_pow(flat(gt[4]), a * b % o.R_ORDER)
+
+
+def test_kzg10_check_mirrors_reference_test(ctx, tmp_path):
+    """The reference's end_to_end_test_kzg (src/lib.rs:250-289): random polynomials of degree 2..19, hiding bound 1,
+    commit -> open at a random point -> KZG10::check must accept; plus what the reference does not test: a wrong
+    value / point / proof / commitment must be rejected, the boolean must equal the CPU restatement's, and
+    batch_check must agree."""
+    import pairing_oracle as po
+
+    n = 32
+    tau, alpha, _ = o.derive_scalars(0xB201)
+    g1 = np.concatenate([ctx.generate(1, ZU, 1, tau, 0, 2 * n - 1), ctx.generate(1, ZU, alpha, tau, 0, n)])
+    g2 = ctx.generate(2, ZU, 1, tau, 0, 2)
+    setup = np.concatenate([ctx.convert(1, ZU, g1, AU, 0), ctx.convert(1, ZU, g1[:96], AU, 0),
+                            ctx.convert(1, ZU, g1[(2 * n - 1) * 96:(2 * n) * 96], AU, 0), ctx.convert(2, ZU, g2, AU, 0)])
+    path = str(tmp_path / "kzg_setup")
+    setup.tofile(path)
+    powers, vk = kz.load_kzg_setup(path, ctx=ctx)
+    R = o.R_ORDER
+    rnd = random.Random(21)
+    comms, points, values, proofs, rvs = [], [], [], [], []
+    for i in range(20):
+        degree = rnd.randrange(2, 20)
+        p = [rnd.randrange(R) for _ in range(degree + 1)]
+        b = [rnd.randrange(R) for _ in range(2)] if i % 4 else None   # every fourth opening without hiding
+        comm = kz.KZG10.commit(powers, p, blinding=b, ctx=ctx)
+        z = rnd.randrange(R)
+        value, proof, random_v = kz.KZG10.open(powers, p, z, blinding=b, ctx=ctx)
+        assert kz.KZG10.check(vk, comm, z, value, proof, random_v, ctx=ctx)          # the reference's assertion
+        comms.append(comm); points.append(z); values.append(value); proofs.append(proof); rvs.append(random_v)
+    N = len(points)
+    assert kz.KZG10.check_many(vk, comms, points, values, proofs, rvs, ctx=ctx).all()
+    # tampering: each of the five inputs in turn
+    bad_values = [(v + 1) % R for v in values]
+    assert not kz.KZG10.check_many(vk, comms, points, bad_values, proofs, rvs, ctx=ctx).any()
+    bad_points = [(z + 1) % R for z in points]
+    assert not kz.KZG10.check_many(vk, comms, bad_points, values, proofs, rvs, ctx=ctx).any()
+    assert not kz.KZG10.check_many(vk, comms, points, values, proofs[1:] + proofs[:1], rvs, ctx=ctx).any()
+    assert not kz.KZG10.check_many(vk, comms[1:] + comms[:1], points, values, proofs, rvs, ctx=ctx).any()
+    hid = [i for i in range(N) if rvs[i] is not None]
+    bad_rv = [None if r is None else (r + 1) % R for r in rvs]
+    res = kz.KZG10.check_many(vk, comms, points, values, proofs, bad_rv, ctx=ctx)
+    assert not res[hid].any() and res[[i for i in range(N) if rvs[i] is None]].all()
+    # same boolean as the CPU restatement of KZG10::check (slow: a few cases)
+    ovk = (o.g1_mul(o.G1_GEN, 1), o.g1_mul(o.G1_GEN, alpha), o.G2_GEN, o.g2_mul(o.G2_GEN, tau))
+
+    def aff(rec):
+        x, y, inf = kz.g1_limbs(rec)
+        if inf:
+            return None
+        rinv = pow(o.MONT_R, -1, o.P)
+        xi = sum(int(v) << (64 * k) for k, v in enumerate(x)) * rinv % o.P
+        yi = sum(int(v) << (64 * k) for k, v in enumerate(y)) * rinv % o.P
+        return (xi, yi)
+
+    for i in (0, 1):
+        assert po.kzg_check(ovk, aff(comms[i]), points[i], values[i], aff(proofs[i]), rvs[i]) is True
+        assert po.kzg_check(ovk, aff(comms[i]), points[i], bad_values[i], aff(proofs[i]), rvs[i]) is False
+    # batch_check (ark: r_0 = 1, then u128 randomizers)
+    rz = [1] + [rnd.randrange(1 << 128) for _ in range(N - 1)]
+    assert kz.KZG10.batch_check(vk, comms, points, values, proofs, rvs, randomizers=rz, ctx=ctx)
+    assert not kz.KZG10.batch_check(vk, comms, points, values[:-1] + [bad_values[-1]], proofs, rvs, randomizers=rz, ctx=ctx)
+    assert kz.KZG10.batch_check(vk, comms[:3], points[:3], values[:3], proofs[:3], rvs[:3], ctx=ctx)   # own randomizers
+    assert po.kzg_batch_check(ovk, [aff(c) for c in comms[:3]], points[:3], values[:3],
+                              [(aff(w), r) for w, r in zip(proofs[:3], rvs[:3])], rz[:3]) is True
+    # a non-canonical scalar is an argument error, as in ptau_kzg_commit
+    bad = np.frombuffer(R.to_bytes(32, "little"), dtype=np.uint8)
+    ok = np.zeros(1, dtype=np.uint8)
+    g1v = np.ascontiguousarray(np.concatenate([vk.g.reshape(-1), vk.gamma_g.reshape(-1)]))
+    g2v = np.ascontiguousarray(np.concatenate([vk.h.reshape(-1), vk.beta_h.reshape(-1)]))
+    c0 = np.ascontiguousarray(comms[0])
+    assert kz._ffi.lib().ptau_kzg_check(ctx._h, g1v.ctypes.data, g2v.ctypes.data, c0.ctypes.data, bad.ctypes.data, bad.ctypes.data,
+                                        c0.ctypes.data, None, 1, ok.ctypes.data) == kz._ffi.ERR_ARG
+
+
 def test_multi_gpu_sharding_is_invisible(cref):
     """Same bytes and same first-bad-index with 1 GPU and with every GPU of the box."""
     from kzg_setup_powersoftau_b200 import _ffi

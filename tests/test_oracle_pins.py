@@ -241,3 +241,53 @@ def test_c_oracle_generator(cref):
     got = cref.generate(2, 1, 1, tau, 0, 5)
     want = b"".join(o.zcash_g2_uncompressed_encode(o.g2_mul(o.G2_GEN, pow(tau, i, o.R_ORDER))) for i in range(5))
     assert got == want
+
+
+def test_pairing_oracle_pins():
+    """The CPU restatement of the pairing (oracle/pairing_oracle.py) is pinned by the properties that define
+    a pairing, and the identities the GPU code relies on are checked numerically:
+    bilinearity in both arguments, non-degeneracy, e(P,Q)^r = 1, pairing with infinity = 1, the
+    hard-part decomposition (p^4-p^2+1)/r = ((z-1)^2/3)(z+p)(z^2+p^2-1) + 1 and the Frobenius constants."""
+    import pairing_oracle as po
+
+    e = po.pairing(o.G1_GEN, o.G2_GEN)
+    assert e != po.F12_ONE
+    assert po.f12_pow(e, o.R_ORDER) == po.F12_ONE
+    assert po.pairing(o.g1_mul(o.G1_GEN, 6), o.G2_GEN) == po.f12_pow(e, 6)
+    assert po.pairing(o.G1_GEN, o.g2_mul(o.G2_GEN, 6)) == po.f12_pow(e, 6)
+    assert po.product_of_pairings([(o.G1_GEN, None), (None, o.G2_GEN)]) == po.F12_ONE
+    negg = (o.G1_GEN[0], (-o.G1_GEN[1]) % o.P)
+    assert po.product_of_pairings([(o.G1_GEN, o.G2_GEN), (negg, o.G2_GEN)]) == po.F12_ONE
+    z, p, r = o.Z, o.P, o.R_ORDER
+    assert (z - 1) ** 2 % 3 == 0 and (z - 1) ** 2 // 3 == 0x396C8C005555E1568C00AAAB0000AAAB
+    assert (p ** 4 - p ** 2 + 1) % r == 0
+    assert (p ** 4 - p ** 2 + 1) // r == ((z - 1) ** 2 // 3) * (z + p) * (z * z + p * p - 1) + 1
+    assert (p ** 12 - 1) // r == (p ** 6 - 1) * (p ** 2 + 1) * ((p ** 4 - p ** 2 + 1) // r)
+    # tower <-> flat basis: u = w^6 - 1 squares to -1, v = w^2 cubes to 1 + u
+    w = [0, 1] + [0] * 10
+    w6 = po.f12_pow(w, 6)
+    u = po.f12_sub(w6, po.F12_ONE)
+    assert po.f12_mul(u, u) == [o.P - 1] + [0] * 11
+    assert po.f12_pow(po.f12_mul(w, w), 3) == po.f12_add(po.F12_ONE, u)
+    # Frobenius constants of csrc/pairing.cuh: (a v)^p = conj(a) xi^((p-1)/3) v, (a w)^p = conj(a) xi^((p-1)/6) w
+    g61, g12 = o.fq2_pow((1, 1), (o.P - 1) // 3), o.fq2_pow((1, 1), (o.P - 1) // 6)
+    v = po.f12_mul(w, w)
+    assert po.f12_pow(v, o.P) == po.f12_mul(po.f12_from_fq2(g61), v)
+    assert po.f12_pow(w, o.P) == po.f12_mul(po.f12_from_fq2(g12), w)
+
+
+def test_kzg_check_oracle_accepts_and_rejects():
+    """ark-poly-commit KZG10::check restated on the CPU, against a known tau."""
+    import pairing_oracle as po
+
+    R = o.R_ORDER
+    tau, alpha = 0x1234567, 0x7654321
+    coeffs, blind = [5, 7, 11, 13], [17, 19]
+    zpt = 99
+    ev = lambda c, x: sum(v * pow(x, i, R) for i, v in enumerate(c)) % R  # noqa: E731
+    quot = lambda c, x: [sum(c[j] * pow(x, j - i - 1, R) for j in range(i + 1, len(c))) % R for i in range(len(c) - 1)]  # noqa: E731
+    comm = o.g1_mul(o.G1_GEN, (ev(coeffs, tau) + alpha * ev(blind, tau)) % R)
+    w = o.g1_mul(o.G1_GEN, (ev(quot(coeffs, zpt), tau) + alpha * ev(quot(blind, zpt), tau)) % R)
+    vk = (o.G1_GEN, o.g1_mul(o.G1_GEN, alpha), o.G2_GEN, o.g2_mul(o.G2_GEN, tau))
+    assert po.kzg_check(vk, comm, zpt, ev(coeffs, zpt), w, ev(blind, zpt)) is True
+    assert po.kzg_check(vk, comm, zpt, ev(coeffs, zpt) + 1, w, ev(blind, zpt)) is False
