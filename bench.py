@@ -428,6 +428,27 @@ def main():
                                                                           "one thread per bucket"}
             except Exception as e:
                 extra["kzg10_commit_2^20(msm, kernels only)"] = {"error": repr(e)}
+            # KZG10::check (two Miller loops + one final exponentiation per opening, one opening per thread)
+            try:
+                import numpy as np
+
+                nk = 1 << 14
+                pwk = pw.reshape(-1, 104)[:32]
+                g2p = ctx.convert(kz.G2, ZU, ctx.generate(kz.G2, ZU, 1, tau, 0, 2), ML, 0).reshape(2, 200)
+                vk = kz.VerifierKey(g=pwk[0], gamma_g=pwk[5], h=g2p[0], beta_h=g2p[1])
+                pws = kz.Powers(powers_of_g=pwk, powers_of_gamma_g=pwk[:1])
+                poly = [int(x) for x in np.random.default_rng(2).integers(1, 1 << 62, size=16)]
+                comm = kz.KZG10.commit(pws, poly, ctx=ctx)
+                val, prf, _ = kz.KZG10.open(pws, poly, 12345, ctx=ctx)
+                for _ in range(2):
+                    okv = kz.KZG10.check_many(vk, np.tile(comm, (nk, 1)), [12345] * nk, [val] * nk, np.tile(prf, (nk, 1)), ctx=ctx)
+                assert okv.all()
+                kms = ctx.timing()["kernel_ms"][0]
+                extra["kzg10_check_2^14(pairings, kernel only)"] = {
+                    "openings": nk, "ms": kms, "openings_per_s": nk / (kms / 1e3),
+                    "note": "per opening: [v]g and [z]h scalar multiplications, two Miller loops, one final exponentiation"}
+            except Exception as e:
+                extra["kzg10_check_2^14(pairings, kernel only)"] = {"error": repr(e)}
             hb = extra["g1_reencode_only(hbm)"]
             line["roofline_hbm"] = {"bound": "hbm", "kernel": "zcash->ark re-encode only (no checks)",
                                     "achieved": hb["GBps"], "peak": 6552.0, "unit": "GB/s",
