@@ -25,34 +25,47 @@ struct Fq12 {
   Fq6 c0, c1;
 };
 
-#ifdef __CUDACC__
-__constant__ uint32_t K_PM2_PAIR[12] = {0xffffaaa9u, 0xb9feffffu, 0xb153ffffu, 0x1eabfffeu, 0xf6b0f624u, 0x6730d2a0u,
-                                        0xf38512bfu, 0x64774b84u, 0x434bacd7u, 0x4b1ba7b6u, 0x397fe69au, 0x1a0111eau};
+// Like the rest of csrc/, everything here also compiles for the host (tests/host_emul) so that the CPU-only
+// suite runs the exact limb-level code against the oracle.
+#define PTAU_PM2_INIT                                                                                       \
+  {0xffffaaa9u, 0xb9feffffu, 0xb153ffffu, 0x1eabfffeu, 0xf6b0f624u, 0x6730d2a0u, 0xf38512bfu, 0x64774b84u, \
+   0x434bacd7u, 0x4b1ba7b6u, 0x397fe69au, 0x1a0111eau}
 // (z-1)^2 / 3 = 0x396c8c005555e1568c00aaab0000aaab (126 bits)
-__constant__ uint32_t K_H1[4] = {0x0000aaabu, 0x8c00aaabu, 0x5555e156u, 0x396c8c00u};
+#define PTAU_H1_INIT {0x0000aaabu, 0x8c00aaabu, 0x5555e156u, 0x396c8c00u}
+#ifdef __CUDACC__
+__constant__ uint32_t K_PM2_PAIR_D[12] = PTAU_PM2_INIT;
+__constant__ uint32_t K_H1_D[4] = PTAU_H1_INIT;
+#endif
+static const uint32_t K_PM2_PAIR_H[12] = PTAU_PM2_INIT;
+static const uint32_t K_H1_H[4] = PTAU_H1_INIT;
 
 // a^(p-2)
-static __device__ __noinline__ Fq fq_inv_fermat(Fq a) {
+PTAU_HD_NOINLINE Fq fq_inv_fermat(Fq a) {
+#ifdef __CUDA_ARCH__
+  const uint32_t* e = K_PM2_PAIR_D;
+#else
+  const uint32_t* e = K_PM2_PAIR_H;
+#endif
   Fq acc = a;
 #pragma unroll 1
   for (int i = 379; i >= 0; --i) {
     acc = fq_sqr(acc);
-    if ((K_PM2_PAIR[i >> 5] >> (i & 31)) & 1u) acc = fq_mul(acc, a);
+    if ((e[i >> 5] >> (i & 31)) & 1u) acc = fq_mul(acc, a);
   }
   return acc;
 }
-static __device__ __noinline__ Fq2 fq2_inv(const Fq2& a) {
+PTAU_HD_NOINLINE Fq2 fq2_inv(const Fq2& a) {
   Fq n = fq_inv_fermat(fq_add(fq_sqr(a.c0), fq_sqr(a.c1)));
   Fq2 r;
   r.c0 = fq_mul(a.c0, n);
   r.c1 = fq_neg(fq_mul(a.c1, n));
   return r;
 }
-static __device__ __forceinline__ Fq finv(const Fq& a) { return fq_inv_fermat(a); }
-static __device__ __forceinline__ Fq2 finv(const Fq2& a) { return fq2_inv(a); }
+PTAU_HD Fq finv(const Fq& a) { return fq_inv_fermat(a); }
+PTAU_HD Fq2 finv(const Fq2& a) { return fq2_inv(a); }
 
 // a * (1 + u)
-static __device__ __forceinline__ Fq2 fq2_mul_xi(const Fq2& a) {
+PTAU_HD Fq2 fq2_mul_xi(const Fq2& a) {
   Fq2 r;
   r.c0 = fq_sub(a.c0, a.c1);
   r.c1 = fq_add(a.c0, a.c1);
@@ -60,23 +73,23 @@ static __device__ __forceinline__ Fq2 fq2_mul_xi(const Fq2& a) {
 }
 
 // ---- Fq6 ----------------------------------------------------------------------------------------
-static __device__ __forceinline__ void fq6_add(Fq6& r, const Fq6& a, const Fq6& b) {
+PTAU_HD void fq6_add(Fq6& r, const Fq6& a, const Fq6& b) {
   r.c0 = fq2_add(a.c0, b.c0);
   r.c1 = fq2_add(a.c1, b.c1);
   r.c2 = fq2_add(a.c2, b.c2);
 }
-static __device__ __forceinline__ void fq6_sub(Fq6& r, const Fq6& a, const Fq6& b) {
+PTAU_HD void fq6_sub(Fq6& r, const Fq6& a, const Fq6& b) {
   r.c0 = fq2_sub(a.c0, b.c0);
   r.c1 = fq2_sub(a.c1, b.c1);
   r.c2 = fq2_sub(a.c2, b.c2);
 }
-static __device__ __forceinline__ void fq6_neg(Fq6& r, const Fq6& a) {
+PTAU_HD void fq6_neg(Fq6& r, const Fq6& a) {
   r.c0 = fq2_neg(a.c0);
   r.c1 = fq2_neg(a.c1);
   r.c2 = fq2_neg(a.c2);
 }
 // Karatsuba, 6 Fq2 multiplications; r may alias a or b
-static __device__ __noinline__ void fq6_mul(Fq6& r, const Fq6& a, const Fq6& b) {
+PTAU_HD_NOINLINE void fq6_mul(Fq6& r, const Fq6& a, const Fq6& b) {
   Fq2 v0 = fq2_mul(a.c0, b.c0), v1 = fq2_mul(a.c1, b.c1), v2 = fq2_mul(a.c2, b.c2);
   Fq2 t0 = fq2_sub(fq2_sub(fq2_mul(fq2_add(a.c1, a.c2), fq2_add(b.c1, b.c2)), v1), v2);
   Fq2 t1 = fq2_sub(fq2_sub(fq2_mul(fq2_add(a.c0, a.c1), fq2_add(b.c0, b.c1)), v0), v1);
@@ -86,13 +99,13 @@ static __device__ __noinline__ void fq6_mul(Fq6& r, const Fq6& a, const Fq6& b) 
   r.c2 = fq2_add(t2, v1);
 }
 // a * v
-static __device__ __forceinline__ void fq6_mul_v(Fq6& r, const Fq6& a) {
+PTAU_HD void fq6_mul_v(Fq6& r, const Fq6& a) {
   Fq2 t = fq2_mul_xi(a.c2);
   r.c2 = a.c1;
   r.c1 = a.c0;
   r.c0 = t;
 }
-static __device__ __noinline__ void fq6_inv(Fq6& r, const Fq6& a) {
+PTAU_HD_NOINLINE void fq6_inv(Fq6& r, const Fq6& a) {
   Fq2 t0 = fq2_sub(fq2_sqr(a.c0), fq2_mul_xi(fq2_mul(a.c1, a.c2)));
   Fq2 t1 = fq2_sub(fq2_mul_xi(fq2_sqr(a.c2)), fq2_mul(a.c0, a.c1));
   Fq2 t2 = fq2_sub(fq2_sqr(a.c1), fq2_mul(a.c0, a.c2));
@@ -103,7 +116,7 @@ static __device__ __noinline__ void fq6_inv(Fq6& r, const Fq6& a) {
   r.c2 = fq2_mul(t2, di);
 }
 // Frobenius: conjugate the Fq2 coefficients, times xi^((p-1)/3), xi^(2(p-1)/3)
-static __device__ __noinline__ void fq6_frob(Fq6& r, const Fq6& a) {
+PTAU_HD_NOINLINE void fq6_frob(Fq6& r, const Fq6& a) {
   Fq2 g1, g2;
   g1.c0 = k_frob6_1_c0_mont();
   g1.c1 = k_frob6_1_c1_mont();
@@ -115,7 +128,7 @@ static __device__ __noinline__ void fq6_frob(Fq6& r, const Fq6& a) {
 }
 
 // ---- Fq12 ---------------------------------------------------------------------------------------
-static __device__ __forceinline__ void fq12_one(Fq12& r) {
+PTAU_HD void fq12_one(Fq12& r) {
   r.c0.c0 = fq2_one();
   r.c0.c1 = fq2_zero();
   r.c0.c2 = fq2_zero();
@@ -124,7 +137,7 @@ static __device__ __forceinline__ void fq12_one(Fq12& r) {
   r.c1.c2 = fq2_zero();
 }
 // r = a * b (3 Fq6 multiplications); r may alias a or b
-static __device__ __noinline__ void fq12_mul(Fq12& r, const Fq12& a, const Fq12& b) {
+PTAU_HD_NOINLINE void fq12_mul(Fq12& r, const Fq12& a, const Fq12& b) {
   Fq6 v0, v1, s, t;
   fq6_mul(v0, a.c0, b.c0);
   fq6_mul(v1, a.c1, b.c1);
@@ -136,11 +149,11 @@ static __device__ __noinline__ void fq12_mul(Fq12& r, const Fq12& a, const Fq12&
   fq6_mul_v(t, v1);
   fq6_add(r.c0, v0, t);
 }
-static __device__ __forceinline__ void fq12_conj(Fq12& r, const Fq12& a) {
+PTAU_HD void fq12_conj(Fq12& r, const Fq12& a) {
   r.c0 = a.c0;
   fq6_neg(r.c1, a.c1);
 }
-static __device__ __noinline__ void fq12_inv(Fq12& r, const Fq12& a) {
+PTAU_HD_NOINLINE void fq12_inv(Fq12& r, const Fq12& a) {
   Fq6 t, u;
   fq6_mul(t, a.c0, a.c0);
   fq6_mul(u, a.c1, a.c1);
@@ -151,7 +164,7 @@ static __device__ __noinline__ void fq12_inv(Fq12& r, const Fq12& a) {
   fq6_mul(r.c0, a.c0, t);
   fq6_neg(r.c1, u);
 }
-static __device__ __noinline__ void fq12_frob(Fq12& r, const Fq12& a) {
+PTAU_HD_NOINLINE void fq12_frob(Fq12& r, const Fq12& a) {
   Fq2 g;
   g.c0 = k_frob12_c0_mont();
   g.c1 = k_frob12_c1_mont();
@@ -162,14 +175,14 @@ static __device__ __noinline__ void fq12_frob(Fq12& r, const Fq12& a) {
   r.c1.c1 = fq2_mul(t.c1, g);
   r.c1.c2 = fq2_mul(t.c2, g);
 }
-static __device__ __noinline__ bool fq12_is_one(const Fq12& a) {
+PTAU_HD_NOINLINE bool fq12_is_one(const Fq12& a) {
   bool ok = fq2_eq(a.c0.c0, fq2_one());
   ok = ok && fq2_is_zero(a.c0.c1) && fq2_is_zero(a.c0.c2);
   ok = ok && fq2_is_zero(a.c1.c0) && fq2_is_zero(a.c1.c1) && fq2_is_zero(a.c1.c2);
   return ok;
 }
 // r = a^e, e = nbits-bit exponent in 32-bit words, top bit set
-static __device__ __noinline__ void fq12_pow(Fq12& r, const Fq12& a, const uint32_t* e, int nbits) {
+PTAU_HD_NOINLINE void fq12_pow(Fq12& r, const Fq12& a, const uint32_t* e, int nbits) {
   Fq12 acc = a;
 #pragma unroll 1
   for (int i = nbits - 2; i >= 0; --i) {
@@ -179,7 +192,7 @@ static __device__ __noinline__ void fq12_pow(Fq12& r, const Fq12& a, const uint3
   r = acc;
 }
 // a^z for a in the cyclotomic subgroup (z < 0: inverse = conjugate)
-static __device__ __noinline__ void fq12_exp_z(Fq12& r, const Fq12& a) {
+PTAU_HD_NOINLINE void fq12_exp_z(Fq12& r, const Fq12& a) {
   const uint32_t za[2] = {0x00010000u, 0xd2010000u};
   Fq12 t;
   fq12_pow(t, a, za, 64);
@@ -187,7 +200,7 @@ static __device__ __noinline__ void fq12_exp_z(Fq12& r, const Fq12& a) {
 }
 
 // f^((p^12 - 1) / r)
-static __device__ __noinline__ void final_exponentiation(Fq12& r, const Fq12& f) {
+PTAU_HD_NOINLINE void final_exponentiation(Fq12& r, const Fq12& f) {
   Fq12 m, t, a, b, c;
   fq12_conj(t, f);
   fq12_inv(m, f);
@@ -197,8 +210,13 @@ static __device__ __noinline__ void final_exponentiation(Fq12& r, const Fq12& f)
   fq12_mul(m, t, m);  // ^(p^2 + 1): m is in the cyclotomic subgroup from here on
   {
     uint32_t h1[4];
+#ifdef __CUDA_ARCH__
+    const uint32_t* hc = K_H1_D;
+#else
+    const uint32_t* hc = K_H1_H;
+#endif
 #pragma unroll
-    for (int i = 0; i < 4; i++) h1[i] = K_H1[i];
+    for (int i = 0; i < 4; i++) h1[i] = hc[i];
     fq12_pow(a, m, h1, 126);  // ^((z-1)^2 / 3)
   }
   fq12_exp_z(b, a);
@@ -222,7 +240,7 @@ struct EllCoeff {
   Fq2 c0, c1, c2;
 };
 
-static __device__ __noinline__ void doubling_step(G2Hom& r, EllCoeff& co) {
+PTAU_HD_NOINLINE void doubling_step(G2Hom& r, EllCoeff& co) {
   const Fq two_inv = k_half_mont();
   Fq2 a = fq2_mul_fq(fq2_mul(r.x, r.y), two_inv);
   Fq2 b = fq2_sqr(r.y);
@@ -244,7 +262,7 @@ static __device__ __noinline__ void doubling_step(G2Hom& r, EllCoeff& co) {
   co.c1 = fq2_add(fq2_dbl(j), j);
   co.c2 = fq2_neg(h);
 }
-static __device__ __noinline__ void addition_step(G2Hom& r, const Fq2& qx, const Fq2& qy, EllCoeff& co) {
+PTAU_HD_NOINLINE void addition_step(G2Hom& r, const Fq2& qx, const Fq2& qy, EllCoeff& co) {
   Fq2 theta = fq2_sub(r.y, fq2_mul(qy, r.z));
   Fq2 lambda = fq2_sub(r.x, fq2_mul(qx, r.z));
   Fq2 c = fq2_sqr(theta);
@@ -261,7 +279,7 @@ static __device__ __noinline__ void addition_step(G2Hom& r, const Fq2& qx, const
   co.c2 = lambda;
 }
 // f *= (c0 + c1 px v) + (c2 py v) w     (ark: mul_by_014)
-static __device__ __noinline__ void ell(Fq12& f, const EllCoeff& co, const Fq& px, const Fq& py) {
+PTAU_HD_NOINLINE void ell(Fq12& f, const EllCoeff& co, const Fq& px, const Fq& py) {
   Fq12 s;
   s.c0.c0 = co.c0;
   s.c0.c1 = fq2_mul_fq(co.c1, px);
@@ -274,7 +292,7 @@ static __device__ __noinline__ void ell(Fq12& f, const EllCoeff& co, const Fq& p
 
 // Miller value of up to two pairs (P_k affine in G1, Q_k affine on the twist); a pair with use[k] == false
 // (P or Q at infinity) contributes 1, like ark's filter in miller_loop.
-static __device__ __noinline__ void miller_loop2(Fq12& f, const Fq* px, const Fq* py, const Fq2* qx, const Fq2* qy,
+PTAU_HD_NOINLINE void miller_loop2(Fq12& f, const Fq* px, const Fq* py, const Fq2* qx, const Fq2* qy,
                                                  const bool* use) {
   fq12_one(f);
   G2Hom r[2];
@@ -308,7 +326,7 @@ static __device__ __noinline__ void miller_loop2(Fq12& f, const Fq* px, const Fq
 
 // ---- group operations with every special case, generic over the field -----------------------------------
 template <class F>
-static __device__ __noinline__ void jac_madd_complete_t(Jac<F>& acc, const F& x, const F& y, const F& one) {
+PTAU_HD_NOINLINE void jac_madd_complete_t(Jac<F>& acc, const F& x, const F& y, const F& one) {
   if (fis_zero(acc.Z)) {
     acc.X = x;
     acc.Y = y;
@@ -338,7 +356,7 @@ static __device__ __noinline__ void jac_madd_complete_t(Jac<F>& acc, const F& x,
 }
 // acc = [k] (x, y), k = 8 little-endian words (< 2^255); double-and-add
 template <class F>
-static __device__ __noinline__ void jac_scalar_mul_t(Jac<F>& acc, const F& x, const F& y, const uint32_t* k, const F& one) {
+PTAU_HD_NOINLINE void jac_scalar_mul_t(Jac<F>& acc, const F& x, const F& y, const uint32_t* k, const F& one) {
   acc.X = fsub(one, one);
   acc.Y = one;
   acc.Z = acc.X;
@@ -350,7 +368,7 @@ static __device__ __noinline__ void jac_scalar_mul_t(Jac<F>& acc, const F& x, co
 }
 // Jacobian -> affine; returns false for the point at infinity
 template <class F>
-static __device__ __noinline__ bool jac_to_affine_t(const Jac<F>& p, F& x, F& y) {
+PTAU_HD_NOINLINE bool jac_to_affine_t(const Jac<F>& p, F& x, F& y) {
   if (fis_zero(p.Z)) return false;
   F zi = finv(p.Z);
   F zi2 = fsqr(zi);
@@ -358,6 +376,142 @@ static __device__ __noinline__ bool jac_to_affine_t(const Jac<F>& p, F& x, F& y)
   y = fmul(p.Y, fmul(zi2, zi));
   return true;
 }
-#endif  // __CUDACC__
+// p += q, both Jacobian, every special case
+template <class F>
+PTAU_HD_NOINLINE void jac_add_complete_t(Jac<F>& p, const Jac<F>& q) {
+  if (fis_zero(q.Z)) return;
+  if (fis_zero(p.Z)) {
+    p = q;
+    return;
+  }
+  F z1z1 = fsqr(p.Z), z2z2 = fsqr(q.Z);
+  F u1 = fmul(p.X, z2z2), u2 = fmul(q.X, z1z1);
+  F s1 = fmul(fmul(p.Y, q.Z), z2z2), s2 = fmul(fmul(q.Y, p.Z), z1z1);
+  if (feq(u1, u2)) {
+    if (feq(s1, s2)) {
+      jac_dbl(p);
+    } else {
+      p.Z = fsub(p.Z, p.Z);
+    }
+    return;
+  }
+  F H = fsub(u2, u1);
+  F I = fsqr(fdbl(H));
+  F J = fmul(H, I);
+  F rr = fdbl(fsub(s2, s1));
+  F V = fmul(u1, I);
+  F X3 = fsub(fsub(fsqr(rr), J), fdbl(V));
+  p.Y = fsub(fmul(rr, fsub(V, X3)), fdbl(fmul(s1, J)));
+  p.Z = fmul(fdbl(fmul(p.Z, q.Z)), H);
+  p.X = X3;
+}
+
+// ---- ARK_MONT_LIMBS records ----------------------------------------------------------------------
+PTAU_HD void load_g1_rec(const uint32_t* rec, Fq& x, Fq& y, bool& inf) {
+#pragma unroll
+  for (int i = 0; i < 12; i++) {
+    x.l[i] = rec[i];
+    y.l[i] = rec[12 + i];
+  }
+  inf = (rec[24] & 0xffu) != 0;
+}
+PTAU_HD void load_g2_rec(const uint32_t* rec, Fq2& x, Fq2& y, bool& inf) {
+#pragma unroll
+  for (int i = 0; i < 12; i++) {
+    x.c0.l[i] = rec[i];
+    x.c1.l[i] = rec[12 + i];
+    y.c0.l[i] = rec[24 + i];
+    y.c1.l[i] = rec[36 + i];
+  }
+  inf = (rec[48] & 0xffu) != 0;
+}
+// GT element -> 12 x 48 canonical little-endian bytes in arkworks' Fq12 order (c0.c0.c0, c0.c0.c1, c0.c1.c0, ...)
+PTAU_HD_NOINLINE void store_gt(uint32_t* out, const Fq12& f) {
+  const Fq2* c[6] = {&f.c0.c0, &f.c0.c1, &f.c0.c2, &f.c1.c0, &f.c1.c1, &f.c1.c2};
+#pragma unroll 1
+  for (int k = 0; k < 6; k++) {
+    Fq a = fq_from_mont(c[k]->c0), b = fq_from_mont(c[k]->c1);
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+      out[k * 24 + i] = a.l[i];
+      out[k * 24 + 12 + i] = b.l[i];
+    }
+  }
+}
+
+// ---- one item of the two public operations --------------------------------------------------------
+// prod_{k<2} e(P_k, Q_k): g1 = 2 G1 records (26 words each), g2 = 2 G2 records (50 words each);
+// gt_out (144 words) may be null.  Returns whether the product is 1.
+PTAU_HD_NOINLINE bool pairing_product2_item(const uint32_t* g1, const uint32_t* g2, uint32_t* gt_out) {
+  Fq px[2], py[2];
+  Fq2 qx[2], qy[2];
+  bool use[2];
+#pragma unroll
+  for (int k = 0; k < 2; k++) {
+    bool pi, qi;
+    load_g1_rec(g1 + k * 26, px[k], py[k], pi);
+    load_g2_rec(g2 + k * 50, qx[k], qy[k], qi);
+    use[k] = !pi && !qi;
+  }
+  Fq12 f;
+  miller_loop2(f, px, py, qx, qy, use);
+  final_exponentiation(f, f);
+  if (gt_out) store_gt(gt_out, f);
+  return fq12_is_one(f);
+}
+
+// KZG10::check of one opening: e(C - [v]g - [rv]gamma_g, h) == e(w, beta_h - [z]h), evaluated as
+// e(inner, h) * e(-w, beta_h - [z]h) == 1.  Scalars: 8 little-endian words, < r; random_v may be null.
+PTAU_HD_NOINLINE bool kzg_check_item(const uint32_t* vk_g1, const uint32_t* vk_g2, const uint32_t* comm, const uint32_t* point,
+                                     const uint32_t* value, const uint32_t* proof_w, const uint32_t* random_v) {
+  Fq px[2], py[2];
+  Fq2 qx[2], qy[2];
+  bool use[2];
+  uint32_t k[8];
+  bool hinf;
+  load_g2_rec(vk_g2, qx[0], qy[0], hinf);
+  {  // inner = C - [v] g - [rv] gamma_g
+    Fq gx, gy;
+    bool ginf;
+    load_g1_rec(vk_g1, gx, gy, ginf);
+    Jac<Fq> acc;
+#pragma unroll
+    for (int w = 0; w < 8; w++) k[w] = ginf ? 0u : value[w];
+    jac_scalar_mul_t(acc, gx, gy, k, fq_one());
+    if (random_v) {
+      load_g1_rec(vk_g1 + 26, gx, gy, ginf);
+#pragma unroll
+      for (int w = 0; w < 8; w++) k[w] = ginf ? 0u : random_v[w];
+      Jac<Fq> t;
+      jac_scalar_mul_t(t, gx, gy, k, fq_one());
+      jac_add_complete_t(acc, t);
+    }
+    acc.Y = fq_neg(acc.Y);
+    Fq cx, cy;
+    bool cinf;
+    load_g1_rec(comm, cx, cy, cinf);
+    if (!cinf) jac_madd_complete_t(acc, cx, cy, fq_one());
+    use[0] = jac_to_affine_t(acc, px[0], py[0]) && !hinf;
+  }
+  {  // Q = beta_h - [z] h
+    Jac<Fq2> acc;
+#pragma unroll
+    for (int w = 0; w < 8; w++) k[w] = hinf ? 0u : point[w];
+    jac_scalar_mul_t(acc, qx[0], qy[0], k, fq2_one());
+    acc.Y = fq2_neg(acc.Y);
+    Fq2 bx, by;
+    bool binf;
+    load_g2_rec(vk_g2 + 50, bx, by, binf);
+    if (!binf) jac_madd_complete_t(acc, bx, by, fq2_one());
+    bool winf;
+    load_g1_rec(proof_w, px[1], py[1], winf);
+    py[1] = fq_neg(py[1]);
+    use[1] = jac_to_affine_t(acc, qx[1], qy[1]) && !winf;
+  }
+  Fq12 f;
+  miller_loop2(f, px, py, qx, qy, use);
+  final_exponentiation(f, f);
+  return fq12_is_one(f);
+}
 
 }  // namespace ptau

@@ -4,6 +4,7 @@
 // against the oracle.  libptau_b200.so never links or calls this.
 #include <cstring>
 #include "../../kzg_setup_powersoftau_b200/csrc/point.cuh"
+#include "../../kzg_setup_powersoftau_b200/csrc/pairing.cuh"
 
 using namespace ptau;
 
@@ -58,4 +59,30 @@ extern "C" void hostemul_fq_op(int op, const uint32_t* a, const uint32_t* b, uin
     default: r = fq_zero();
   }
   std::memcpy(out, r.l, 48);
+}
+
+// the product's pairing code (csrc/pairing.cuh) on the host: same limb arithmetic, same formulas
+extern "C" void hostemul_pairing_product2(const uint8_t* g1, const uint8_t* g2, size_t n, uint8_t* gt_out, uint8_t* is_one) {
+  for (size_t i = 0; i < n; i++) {
+    uint32_t a[52], b[100], gt[144];
+    std::memcpy(a, g1 + i * 208, 208);
+    std::memcpy(b, g2 + i * 400, 400);
+    is_one[i] = pairing_product2_item(a, b, gt) ? 1 : 0;
+    std::memcpy(gt_out + i * 576, gt, 576);
+  }
+}
+extern "C" void hostemul_kzg_check(const uint8_t* vk_g1, const uint8_t* vk_g2, const uint8_t* comms, const uint8_t* points,
+                                   const uint8_t* values, const uint8_t* proofs, const uint8_t* random_v, size_t n, uint8_t* ok) {
+  uint32_t v1[52], v2[100];
+  std::memcpy(v1, vk_g1, 208);
+  std::memcpy(v2, vk_g2, 400);
+  for (size_t i = 0; i < n; i++) {
+    uint32_t c[26], w[26], z[8], v[8], rv[8];
+    std::memcpy(c, comms + i * 104, 104);
+    std::memcpy(w, proofs + i * 104, 104);
+    std::memcpy(z, points + i * 32, 32);
+    std::memcpy(v, values + i * 32, 32);
+    if (random_v) std::memcpy(rv, random_v + i * 32, 32);
+    ok[i] = kzg_check_item(v1, v2, c, z, v, w, random_v ? rv : nullptr) ? 1 : 0;
+  }
 }

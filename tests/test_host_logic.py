@@ -332,3 +332,53 @@ def test_world_size_2_gloo(cref, tmp_path):
     line = [l for l in p.stdout.splitlines() if l.startswith("RESULT")][0].split()
     assert int(line[1]) == 11 and int(line[2]) == 4  # lowest bad index wins, NOT_ON_CURVE
     assert float(line[3]) == 20.0 and int(line[4]) == 37
+
+
+def test_limb_pairing_code_vs_oracle(hostemul):
+    """csrc/pairing.cuh compiled for the host (same limb arithmetic, same formulas as the kernels): GT bytes of a
+    pairing product against the independent CPU pairing, and KZG10::check accepting / rejecting."""
+    import pairing_oracle as po
+
+    def g1r(q):
+        return o.g1_mont_record(0, 1, True) if q is None else o.g1_mont_record(q[0], q[1], False)
+
+    def g2r(q):
+        return o.g2_mont_record((0, 0), (1, 0), True) if q is None else o.g2_mont_record(q[0], q[1], False)
+
+    P1, Q1 = o.g1_mul(o.G1_GEN, 0xABCDEF), o.g2_mul(o.G2_GEN, 0x123457)
+    P2, Q2 = o.g1_mul(o.G1_GEN, 77), o.g2_mul(o.G2_GEN, 99)
+    items = [((P1, Q1), (P2, Q2)), ((P1, Q1), (None, Q2))]
+    g1 = b"".join(g1r(p) for it in items for p, _ in it)
+    g2 = b"".join(g2r(q) for it in items for _, q in it)
+    gt = ctypes.create_string_buffer(576 * len(items))
+    one = ctypes.create_string_buffer(len(items))
+    hostemul.hostemul_pairing_product2(g1, g2, ctypes.c_size_t(len(items)), gt, one)
+    assert one.raw == b"\x00\x00"
+
+    def flat(rec):
+        return po.f12_from_tower([int.from_bytes(rec[48 * i:48 * i + 48], "little") for i in range(12)])
+
+    e1 = po.pairing(P1, Q1)
+    assert flat(gt.raw[576:]) == e1
+    assert flat(gt.raw[:576]) == po.f12_mul(e1, po.pairing(P2, Q2))
+    # KZG10::check with a known tau
+    R = o.R_ORDER
+    tau, alpha = 0x1234567, 0x7654321
+    coeffs, blind, zpt = [5, 7, 11, 13], [17, 19], 99
+    ev = lambda c, x: sum(v * pow(x, i, R) for i, v in enumerate(c)) % R  # noqa: E731
+    quot = lambda c, x: [sum(c[j] * pow(x, j - i - 1, R) for j in range(i + 1, len(c))) % R for i in range(len(c) - 1)]  # noqa: E731
+    comm = o.g1_mul(o.G1_GEN, (ev(coeffs, tau) + alpha * ev(blind, tau)) % R)
+    w = o.g1_mul(o.G1_GEN, (ev(quot(coeffs, zpt), tau) + alpha * ev(quot(blind, zpt), tau)) % R)
+    vk1 = g1r(o.G1_GEN) + g1r(o.g1_mul(o.G1_GEN, alpha))
+    vk2 = g2r(o.G2_GEN) + g2r(o.g2_mul(o.G2_GEN, tau))
+    le = lambda v: (v % R).to_bytes(32, "little")  # noqa: E731
+    ok = ctypes.create_string_buffer(2)
+    hostemul.hostemul_kzg_check(vk1, vk2, g1r(comm) * 2, le(zpt) * 2, le(ev(coeffs, zpt)) + le(ev(coeffs, zpt) + 1), g1r(w) * 2,
+                                le(ev(blind, zpt)) * 2, ctypes.c_size_t(2), ok)
+    assert ok.raw == b"\x01\x00"
+    # without hiding
+    comm0 = o.g1_mul(o.G1_GEN, ev(coeffs, tau))
+    w0 = o.g1_mul(o.G1_GEN, ev(quot(coeffs, zpt), tau))
+    hostemul.hostemul_kzg_check(vk1, vk2, g1r(comm0) * 2, le(zpt) + le(zpt + 1), le(ev(coeffs, zpt)) * 2, g1r(w0) * 2, None,
+                                ctypes.c_size_t(2), ok)
+    assert ok.raw == b"\x01\x00"
