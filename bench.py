@@ -404,6 +404,41 @@ def main():
                 extra["preprocess_kgz_2^21_fused(host->host)"] = {
                     "points": npts, "ms": dt * 1e3, "points_per_s": npts / dt,
                     "note": "ptau_preprocess on pinned host buffers: 4.2M+2.1M compressed G1, 2.1M compressed G2, all checks"}
+                # the drop-in binary on files, as a user of the reference would run it (wall clock, process start included)
+                try:
+                    import shutil
+                    import tempfile
+
+                    tmpd = tempfile.mkdtemp(prefix="ptau_bench_")
+                    resp.array.tofile(os.path.join(tmpd, "powersoftau"))
+                    exe = os.path.join(ROOT, "kzg_setup_powersoftau_b200", "bin", "preprocess-kgz")
+                    import hashlib
+
+                    hexd = hashlib.blake2b(memoryview(resp.array), digest_size=64).hexdigest()
+                    runs = {}
+                    for tag, flags in (("like_reference(blake2b+uncompressed_file)", ["--expect-digest", hexd]),
+                                       ("no_digest_no_intermediate", ["--skip-digest", "--no-uncompressed"])):
+                        for f in ("powersoftau_uncompressed", "kzg_setup"):
+                            if os.path.exists(os.path.join(tmpd, f)):
+                                os.remove(os.path.join(tmpd, f))
+                        t0 = time.perf_counter()
+                        r = subprocess.run([exe, "--dir", tmpd, "--log2-powers", str(k)] + flags,
+                                           capture_output=True, text=True)
+                        runs[tag] = {"wall_s": time.perf_counter() - t0, "rc": r.returncode}
+                    same = open(os.path.join(tmpd, "kzg_setup"), "rb").read() == setup.array.tobytes()
+                    t0 = time.perf_counter()
+                    pw_l, vk_l = kz.load_kzg_setup(os.path.join(tmpd, "kzg_setup"), ctx=ctx)
+                    t_load = time.perf_counter() - t0
+                    t0 = time.perf_counter()
+                    kz.load_kzg_setup(os.path.join(tmpd, "kzg_setup"), ctx=ctx, checks=STRICT)
+                    t_loadv = time.perf_counter() - t0
+                    extra["cli_preprocess_kgz_2^21(file->file)"] = {
+                        "runs": runs, "output_equals_host_path": same, "load_kzg_setup_s": t_load,
+                        "load_kzg_setup_validated_s": t_loadv, "tmpdir_fs": tmpd,
+                        "note": "604 MB response file -> kzg_setup (604 MB), 8.4 M points, all checks; wall clock of the binary"}
+                    shutil.rmtree(tmpd, ignore_errors=True)
+                except Exception as e:
+                    extra["cli_preprocess_kgz_2^21(file->file)"] = {"error": repr(e)}
                 resp.free()
                 setup.free()
             except Exception as e:  # pinned allocation of 1.2 GB may be refused on small hosts
