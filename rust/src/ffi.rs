@@ -50,6 +50,14 @@ extern "C" {
         g1_out: *mut c_void, g1_out_len: u64, g2_out: *mut c_void, g2_out_len: u64, bad_index: *mut u64,
         bad_kind: *mut c_int,
     ) -> c_int;
+    pub fn ptau_kzg_commit(ctx: *mut ptau_ctx, powers: *const c_void, coeffs: *const c_void, n: usize, commitment: *mut c_void) -> c_int;
+    pub fn ptau_kzg_check(
+        ctx: *mut ptau_ctx, vk_g1: *const c_void, vk_g2: *const c_void, comms: *const c_void, points: *const c_void,
+        values: *const c_void, proofs_w: *const c_void, random_v: *const c_void, n: usize, ok: *mut u8,
+    ) -> c_int;
+    pub fn ptau_pairing_product2(
+        ctx: *mut ptau_ctx, g1: *const c_void, g2: *const c_void, n: usize, gt_out: *mut c_void, is_one: *mut u8,
+    ) -> c_int;
     pub fn ptau_load_phase1(
         ctx: *mut ptau_ctx, data: *const c_void, len: u64, m: u64, checks: c_uint, g1_out: *mut c_void,
         g1_out_len: u64, g2_out: *mut c_void, g2_out_len: u64, bad_index: *mut u64, bad_kind: *mut c_int,

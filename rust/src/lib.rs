@@ -44,6 +44,35 @@ fn g2_from_record(rec: &[u8]) -> ArkG2Affine {
     )
 }
 
+/// G1Affine -> 104-byte record: the Montgomery limbs as they sit in memory (`Fp384.0.0`), then the infinity byte.
+fn g1_to_record(p: &ArkG1Affine) -> Vec<u8> {
+    let mut r = Vec::with_capacity(104);
+    for f in [&p.x, &p.y] {
+        for limb in (f.0).0.iter() {
+            r.extend_from_slice(&limb.to_le_bytes());
+        }
+    }
+    r.extend_from_slice(&[p.infinity as u8, 0, 0, 0, 0, 0, 0, 0]);
+    r
+}
+
+fn g2_to_record(p: &ArkG2Affine) -> Vec<u8> {
+    let mut r = Vec::with_capacity(200);
+    for f in [&p.x.c0, &p.x.c1, &p.y.c0, &p.y.c1] {
+        for limb in (f.0).0.iter() {
+            r.extend_from_slice(&limb.to_le_bytes());
+        }
+    }
+    r.extend_from_slice(&[p.infinity as u8, 0, 0, 0, 0, 0, 0, 0]);
+    r
+}
+
+unsafe fn new_ctx() -> *mut ffi::ptau_ctx {
+    let mut ctx = std::ptr::null_mut();
+    assert_eq!(ffi::ptau_create(&mut ctx, 1, std::ptr::null(), 0), 0, "a B200 is required");
+    ctx
+}
+
 fn load(variant: i32) -> (Vec<ArkG1Affine>, Vec<ArkG2Affine>) {
     let data = std::fs::read(KZG_SETUP_FILE).unwrap();
     let n = TAU_POWERS_LENGTH as u64;
@@ -105,4 +134,52 @@ pub fn load_fastkzg_setup() -> (UniversalParams<Bls12_381>, Vec<ArkG2Affine>) {
         prepared_beta_h: g2[1].into(),
     };
     (params, powers_of_h)
+}
+
+/// ark-poly-commit 0.2 `KZG10::{commit, check}` on the GPU (what the reference's own test exercises,
+/// /root/reference/src/lib.rs:266-286).  Points travel as the Montgomery-limb records the loader produces
+/// (`Fp384` in memory), scalars as `Fr::into_repr()` little-endian bytes.
+pub mod kzg {
+    use super::*;
+    use ark_bls12_381::Fr;
+    use ark_ff::{BigInteger, PrimeField};
+    use ark_poly_commit::kzg10::{Commitment, Proof};
+
+    fn le32(v: &[Fr]) -> Vec<u8> {
+        v.iter().flat_map(|s| s.into_repr().to_bytes_le()).collect()
+    }
+
+    /// sum_i coeffs[i] * powers[i]  (the MSM inside `KZG10::commit` / `open`)
+    pub fn commit(powers: &[ArkG1Affine], coeffs: &[Fr]) -> ArkG1Affine {
+        let recs: Vec<u8> = powers[..coeffs.len()].iter().flat_map(g1_to_record).collect();
+        let mut out = [0u8; 104];
+        unsafe {
+            let ctx = new_ctx();
+            let rc = ffi::ptau_kzg_commit(ctx, recs.as_ptr() as *const _, le32(coeffs).as_ptr() as *const _, coeffs.len(), out.as_mut_ptr() as *mut _);
+            ffi::ptau_destroy(ctx);
+            assert_eq!(rc, 0);
+        }
+        g1_from_record(&out)
+    }
+
+    /// `KZG10::check(&vk, &comm, point, value, &proof)` for many openings at once (one GPU thread per opening)
+    pub fn check_many(vk: &VerifierKey<Bls12_381>, comms: &[Commitment<Bls12_381>], points: &[Fr], values: &[Fr],
+                      proofs: &[Proof<Bls12_381>]) -> Vec<bool> {
+        let n = comms.len();
+        let g1: Vec<u8> = [vk.g, vk.gamma_g].iter().flat_map(g1_to_record).collect();
+        let g2: Vec<u8> = [vk.h, vk.beta_h].iter().flat_map(g2_to_record).collect();
+        let c: Vec<u8> = comms.iter().flat_map(|c| g1_to_record(&c.0)).collect();
+        let w: Vec<u8> = proofs.iter().flat_map(|p| g1_to_record(&p.w)).collect();
+        let rv: Vec<Fr> = proofs.iter().map(|p| p.random_v.unwrap_or_default()).collect(); // None == 0: [0]gamma_g = O
+        let mut ok = vec![0u8; n];
+        unsafe {
+            let ctx = new_ctx();
+            let rc = ffi::ptau_kzg_check(ctx, g1.as_ptr() as *const _, g2.as_ptr() as *const _, c.as_ptr() as *const _,
+                                         le32(points).as_ptr() as *const _, le32(values).as_ptr() as *const _,
+                                         w.as_ptr() as *const _, le32(&rv).as_ptr() as *const _, n, ok.as_mut_ptr());
+            ffi::ptau_destroy(ctx);
+            assert_eq!(rc, 0);
+        }
+        ok.into_iter().map(|b| b != 0).collect()
+    }
 }
