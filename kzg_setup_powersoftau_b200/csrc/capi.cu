@@ -679,9 +679,10 @@ int ptau_kzg_commit(ptau_ctx* ctx, const void* powers, const void* coeffs, size_
   }
   GpuSlot& s = ctx->gpu[0];
   CUDA_TRY(ctx, cudaSetDevice(s.device));
-  if (n >= (1ull << 31)) return PTAU_ERR_ARG;  // point indices travel in 31 bits
   ptau::MsmPlan plan;
   ptau::msm_g1_plan(n, &plan);
+  // point indices travel in 31 bits and the bucket lists (n x W entries) are addressed with 32-bit offsets
+  if (n >= (1ull << 31) || (uint64_t)n * (uint64_t)plan.W >= (1ull << 32)) return PTAU_ERR_ARG;
   int launches = 0;
   void *d_pts = nullptr, *d_sc = nullptr, *d_part = nullptr, *d_out = nullptr;
   cudaError_t e = cudaMalloc(&d_pts, n * 104 + 16);
