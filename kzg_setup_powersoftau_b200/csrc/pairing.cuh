@@ -181,12 +181,46 @@ PTAU_HD_NOINLINE bool fq12_is_one(const Fq12& a) {
   ok = ok && fq2_is_zero(a.c1.c0) && fq2_is_zero(a.c1.c1) && fq2_is_zero(a.c1.c2);
   return ok;
 }
-// r = a^e, e = nbits-bit exponent in 32-bit words, top bit set
-PTAU_HD_NOINLINE void fq12_pow(Fq12& r, const Fq12& a, const uint32_t* e, int nbits) {
+// a^2 for a in the cyclotomic subgroup (Granger-Scott: three Fq4 squarings, 6 Fq2 multiplications instead of 18);
+// r may alias a
+PTAU_HD_NOINLINE void fq12_cyclotomic_sqr(Fq12& r, const Fq12& a) {
+  Fq2 z0 = a.c0.c0, z4 = a.c0.c1, z3 = a.c0.c2, z2 = a.c1.c0, z1 = a.c1.c1, z5 = a.c1.c2;
+  // (x + y s)^2 in Fq4 = Fq2[s]/(s^2 - xi): t_even = x^2 + xi y^2 = (x + y)(x + xi y) - xy - xi xy, t_odd = 2xy
+  Fq2 tmp = fq2_mul(z0, z1);
+  Fq2 t0 = fq2_sub(fq2_sub(fq2_mul(fq2_add(z0, z1), fq2_add(z0, fq2_mul_xi(z1))), tmp), fq2_mul_xi(tmp));
+  Fq2 t1 = fq2_dbl(tmp);
+  tmp = fq2_mul(z2, z3);
+  Fq2 t2 = fq2_sub(fq2_sub(fq2_mul(fq2_add(z2, z3), fq2_add(z2, fq2_mul_xi(z3))), tmp), fq2_mul_xi(tmp));
+  Fq2 t3 = fq2_dbl(tmp);
+  tmp = fq2_mul(z4, z5);
+  Fq2 t4 = fq2_sub(fq2_sub(fq2_mul(fq2_add(z4, z5), fq2_add(z4, fq2_mul_xi(z5))), tmp), fq2_mul_xi(tmp));
+  Fq2 t5 = fq2_dbl(tmp);
+  z0 = fq2_sub(t0, z0);  // 3 t0 - 2 z0
+  z0 = fq2_add(fq2_dbl(z0), t0);
+  z1 = fq2_add(t1, z1);  // 3 t1 + 2 z1
+  z1 = fq2_add(fq2_dbl(z1), t1);
+  tmp = fq2_mul_xi(t5);  // 3 xi t5 + 2 z2
+  z2 = fq2_add(tmp, z2);
+  z2 = fq2_add(fq2_dbl(z2), tmp);
+  z3 = fq2_sub(t4, z3);  // 3 t4 - 2 z3
+  z3 = fq2_add(fq2_dbl(z3), t4);
+  z4 = fq2_sub(t2, z4);  // 3 t2 - 2 z4
+  z4 = fq2_add(fq2_dbl(z4), t2);
+  z5 = fq2_add(t3, z5);  // 3 t3 + 2 z5
+  z5 = fq2_add(fq2_dbl(z5), t3);
+  r.c0.c0 = z0;
+  r.c0.c1 = z4;
+  r.c0.c2 = z3;
+  r.c1.c0 = z2;
+  r.c1.c1 = z1;
+  r.c1.c2 = z5;
+}
+// r = a^e for a in the cyclotomic subgroup; e = nbits-bit exponent in 32-bit words, top bit set
+PTAU_HD_NOINLINE void fq12_pow_cyclotomic(Fq12& r, const Fq12& a, const uint32_t* e, int nbits) {
   Fq12 acc = a;
 #pragma unroll 1
   for (int i = nbits - 2; i >= 0; --i) {
-    fq12_mul(acc, acc, acc);
+    fq12_cyclotomic_sqr(acc, acc);
     if ((e[i >> 5] >> (i & 31)) & 1u) fq12_mul(acc, acc, a);
   }
   r = acc;
@@ -195,7 +229,7 @@ PTAU_HD_NOINLINE void fq12_pow(Fq12& r, const Fq12& a, const uint32_t* e, int nb
 PTAU_HD_NOINLINE void fq12_exp_z(Fq12& r, const Fq12& a) {
   const uint32_t za[2] = {0x00010000u, 0xd2010000u};
   Fq12 t;
-  fq12_pow(t, a, za, 64);
+  fq12_pow_cyclotomic(t, a, za, 64);
   fq12_conj(r, t);
 }
 
@@ -217,7 +251,7 @@ PTAU_HD_NOINLINE void final_exponentiation(Fq12& r, const Fq12& f) {
 #endif
 #pragma unroll
     for (int i = 0; i < 4; i++) h1[i] = hc[i];
-    fq12_pow(a, m, h1, 126);  // ^((z-1)^2 / 3)
+    fq12_pow_cyclotomic(a, m, h1, 126);  // ^((z-1)^2 / 3)
   }
   fq12_exp_z(b, a);
   fq12_frob(t, a);
@@ -278,16 +312,35 @@ PTAU_HD_NOINLINE void addition_step(G2Hom& r, const Fq2& qx, const Fq2& qy, EllC
   co.c1 = fq2_neg(theta);
   co.c2 = lambda;
 }
-// f *= (c0 + c1 px v) + (c2 py v) w     (ark: mul_by_014)
+// Fq6 times the sparse b0 + b1 v (5 Fq2 multiplications); r may alias a
+PTAU_HD_NOINLINE void fq6_mul_by_01(Fq6& r, const Fq6& a, const Fq2& b0, const Fq2& b1) {
+  Fq2 v0 = fq2_mul(a.c0, b0), v1 = fq2_mul(a.c1, b1);
+  Fq2 t0 = fq2_add(v0, fq2_mul_xi(fq2_sub(fq2_mul(fq2_add(a.c1, a.c2), b1), v1)));
+  Fq2 t1 = fq2_sub(fq2_sub(fq2_mul(fq2_add(a.c0, a.c1), fq2_add(b0, b1)), v0), v1);
+  Fq2 t2 = fq2_add(fq2_sub(fq2_mul(fq2_add(a.c0, a.c2), b0), v0), v1);
+  r.c0 = t0;
+  r.c1 = t1;
+  r.c2 = t2;
+}
+// Fq6 times b1 v (3 Fq2 multiplications); r may alias a
+PTAU_HD void fq6_mul_by_1(Fq6& r, const Fq6& a, const Fq2& b1) {
+  Fq2 t0 = fq2_mul_xi(fq2_mul(a.c2, b1)), t1 = fq2_mul(a.c0, b1), t2 = fq2_mul(a.c1, b1);
+  r.c0 = t0;
+  r.c1 = t1;
+  r.c2 = t2;
+}
+// f *= (c0 + c1 px v) + (c2 py v) w     (ark: mul_by_014; 13 Fq2 multiplications instead of 18)
 PTAU_HD_NOINLINE void ell(Fq12& f, const EllCoeff& co, const Fq& px, const Fq& py) {
-  Fq12 s;
-  s.c0.c0 = co.c0;
-  s.c0.c1 = fq2_mul_fq(co.c1, px);
-  s.c0.c2 = fq2_zero();
-  s.c1.c0 = fq2_zero();
-  s.c1.c1 = fq2_mul_fq(co.c2, py);
-  s.c1.c2 = fq2_zero();
-  fq12_mul(f, f, s);
+  const Fq2 c0 = co.c0, c1 = fq2_mul_fq(co.c1, px), c4 = fq2_mul_fq(co.c2, py);
+  Fq6 aa, bb, s;
+  fq6_mul_by_01(aa, f.c0, c0, c1);
+  fq6_mul_by_1(bb, f.c1, c4);
+  fq6_add(s, f.c1, f.c0);
+  fq6_mul_by_01(s, s, c0, fq2_add(c1, c4));
+  fq6_sub(s, s, aa);
+  fq6_sub(f.c1, s, bb);
+  fq6_mul_v(bb, bb);
+  fq6_add(f.c0, bb, aa);
 }
 
 // Miller value of up to two pairs (P_k affine in G1, Q_k affine on the twist); a pair with use[k] == false
