@@ -44,6 +44,9 @@ struct ptau_ctx {
   GpuSlot gpu[kMaxGpus];
   ptau_timing timing;
   std::string last_error;
+  // KZG10::check: fixed-base tables of the verifier key's g, gamma_g, h on GPU 0, rebuilt when the key changes
+  void* d_kzg_tbl = nullptr;
+  std::string kzg_tbl_key;
 };
 
 namespace {
@@ -246,6 +249,7 @@ void ptau_destroy(ptau_ctx* ctx) {
       if (s.d_tbl[t]) cudaFree(s.d_tbl[t]);
     if (s.ev_first) cudaEventDestroy(s.ev_first);
     if (s.ev_last) cudaEventDestroy(s.ev_last);
+    if (g == 0 && ctx->d_kzg_tbl) cudaFree(ctx->d_kzg_tbl);
   }
   delete ctx;
 }
@@ -795,8 +799,19 @@ int ptau_kzg_check(ptau_ctx* ctx, const void* vk_g1, const void* vk_g2, const vo
   if (e == cudaSuccess) e = a.push(proofs_w, n * 104, st, &dw);
   if (e == cudaSuccess && random_v) e = a.push(random_v, n * 32, st, &drv);
   if (e == cudaSuccess) e = a.push(nullptr, n, st, &dok);
+  int launches = 1;
+  if (e == cudaSuccess) {  // fixed-base tables of g, gamma_g, h: kept while the key stays the same
+    std::string key((const char*)vk_g1, 2 * 104);
+    key.append((const char*)vk_g2, 200);
+    if (!ctx->d_kzg_tbl) e = cudaMalloc(&ctx->d_kzg_tbl, ptau::kzg_tables_bytes());
+    if (e == cudaSuccess && key != ctx->kzg_tbl_key) {
+      e = ptau::launch_kzg_tables(dv1, dv2, ctx->d_kzg_tbl, st);
+      if (e == cudaSuccess) ctx->kzg_tbl_key = key;
+      launches++;
+    }
+  }
   if (e == cudaSuccess) e = cudaEventRecord(s.ev_k0[0], st);
-  if (e == cudaSuccess) e = ptau::launch_kzg_check(dv1, dv2, dc, dz, dv, dw, drv, n, dok, st);
+  if (e == cudaSuccess) e = ptau::launch_kzg_check(dv1, dv2, dc, dz, dv, dw, drv, ctx->d_kzg_tbl, n, dok, st);
   if (e == cudaSuccess) e = cudaEventRecord(s.ev_k1[0], st);
   if (e == cudaSuccess) e = cudaMemcpyAsync(ok, dok, n, cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
@@ -810,7 +825,7 @@ int ptau_kzg_check(ptau_ctx* ctx, const void* vk_g1, const void* vk_g2, const vo
   ctx->timing.n_gpus = ctx->n_gpus;
   ctx->timing.kernel_ms[0] = ms;
   ctx->timing.gpu_ms[0] = ms;
-  ctx->timing.kernel_launches = 1;
+  ctx->timing.kernel_launches = launches;
   ctx->timing.h2d_bytes[0] = 608 + n * (104 + 32 + 32 + 104 + (random_v ? 32 : 0));
   ctx->timing.d2h_bytes[0] = n;
   return PTAU_OK;

@@ -34,9 +34,12 @@ cudaError_t launch_msm_g1(const void* d_pts, const void* d_scalars, uint64_t n, 
 // KZG10::check for n openings (d_random_v may be null: no hiding), one item per thread
 cudaError_t launch_pairing_product2(const void* d_g1, const void* d_g2, uint64_t n, void* d_gt, void* d_is_one,
                                     cudaStream_t stream);
+// d_tbl: kzg_tables_bytes() of fixed-base tables of g, gamma_g, h built by launch_kzg_tables for this key
+size_t kzg_tables_bytes();
+cudaError_t launch_kzg_tables(const void* d_vk_g1, const void* d_vk_g2, void* d_tbl, cudaStream_t stream);
 cudaError_t launch_kzg_check(const void* d_vk_g1, const void* d_vk_g2, const void* d_comms, const void* d_points,
-                             const void* d_values, const void* d_proofs, const void* d_random_v, uint64_t n, void* d_ok,
-                             cudaStream_t stream);
+                             const void* d_values, const void* d_proofs, const void* d_random_v, const void* d_tbl,
+                             uint64_t n, void* d_ok, cudaStream_t stream);
 
 cudaError_t launch_fq_op(int op, const void* d_a, const void* d_b, void* d_out, uint64_t n, cudaStream_t stream);
 

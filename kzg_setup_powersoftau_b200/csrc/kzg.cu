@@ -18,16 +18,27 @@ __global__ void __launch_bounds__(PTAU_PAIR_BLOCK) pairing_product2_kernel(const
   if (is_one) is_one[i] = one ? 1 : 0;
 }
 
+// fixed-base tables of g, gamma_g (blocks 0, 1) and h (block 2): one window per thread.  tbl = [g | gamma_g | h]
+__global__ void __launch_bounds__(PTAU_FB_WINDOWS) kzg_tables_kernel(const uint32_t* __restrict__ vk_g1, const uint32_t* __restrict__ vk_g2,
+                                                                     uint32_t* __restrict__ tbl) {
+  const int w = threadIdx.x;
+  if (blockIdx.x < 2)
+    fixed_base_window<Fq>(tbl + (size_t)blockIdx.x * PTAU_FB_ENTRIES * 26, vk_g1 + blockIdx.x * 26, w, fq_one());
+  else
+    fixed_base_window<Fq2>(tbl + (size_t)2 * PTAU_FB_ENTRIES * 26, vk_g2, w, fq2_one());
+}
+
 // KZG10::check for n openings, one per thread
 __global__ void __launch_bounds__(PTAU_PAIR_BLOCK) kzg_check_kernel(const uint32_t* __restrict__ vk_g1, const uint32_t* __restrict__ vk_g2,
                                                                     const uint32_t* __restrict__ comms, const uint32_t* __restrict__ points,
                                                                     const uint32_t* __restrict__ values, const uint32_t* __restrict__ proofs,
-                                                                    const uint32_t* __restrict__ random_v, uint64_t n,
-                                                                    uint8_t* __restrict__ ok) {
+                                                                    const uint32_t* __restrict__ random_v, const uint32_t* __restrict__ tbl,
+                                                                    uint64_t n, uint8_t* __restrict__ ok) {
   const uint64_t i = (uint64_t)blockIdx.x * PTAU_PAIR_BLOCK + threadIdx.x;
   if (i >= n) return;
   ok[i] = kzg_check_item(vk_g1, vk_g2, comms + i * 26, points + i * 8, values + i * 8, proofs + i * 26,
-                         random_v ? random_v + i * 8 : nullptr)
+                         random_v ? random_v + i * 8 : nullptr, tbl, tbl + (size_t)PTAU_FB_ENTRIES * 26,
+                         tbl + (size_t)2 * PTAU_FB_ENTRIES * 26)
               ? 1
               : 0;
 }
@@ -40,13 +51,21 @@ cudaError_t launch_pairing_product2(const void* d_g1, const void* d_g2, uint64_t
   return cudaGetLastError();
 }
 
+size_t kzg_tables_bytes() { return (size_t)PTAU_FB_ENTRIES * (26 + 26 + 50) * 4; }
+
+cudaError_t launch_kzg_tables(const void* d_vk_g1, const void* d_vk_g2, void* d_tbl, cudaStream_t stream) {
+  kzg_tables_kernel<<<3, PTAU_FB_WINDOWS, 0, stream>>>((const uint32_t*)d_vk_g1, (const uint32_t*)d_vk_g2, (uint32_t*)d_tbl);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_kzg_check(const void* d_vk_g1, const void* d_vk_g2, const void* d_comms, const void* d_points,
-                             const void* d_values, const void* d_proofs, const void* d_random_v, uint64_t n, void* d_ok,
-                             cudaStream_t stream) {
+                             const void* d_values, const void* d_proofs, const void* d_random_v, const void* d_tbl,
+                             uint64_t n, void* d_ok, cudaStream_t stream) {
   if (n == 0) return cudaSuccess;
   kzg_check_kernel<<<(unsigned)((n + PTAU_PAIR_BLOCK - 1) / PTAU_PAIR_BLOCK), PTAU_PAIR_BLOCK, 0, stream>>>(
       (const uint32_t*)d_vk_g1, (const uint32_t*)d_vk_g2, (const uint32_t*)d_comms, (const uint32_t*)d_points,
-      (const uint32_t*)d_values, (const uint32_t*)d_proofs, (const uint32_t*)d_random_v, n, (uint8_t*)d_ok);
+      (const uint32_t*)d_values, (const uint32_t*)d_proofs, (const uint32_t*)d_random_v, (const uint32_t*)d_tbl, n,
+      (uint8_t*)d_ok);
   return cudaGetLastError();
 }
 

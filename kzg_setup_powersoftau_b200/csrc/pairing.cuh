@@ -492,6 +492,105 @@ PTAU_HD_NOINLINE void store_gt(uint32_t* out, const Fq12& f) {
   }
 }
 
+// ---- fixed-base windowed multiplication -----------------------------------------------------------------
+// g, gamma_g and h are the same for every opening of a call (and, in practice, of a context), so [v]g, [rv]gamma_g
+// and [z]h use a table T[w][j-1] = [j 16^w] B, w < 64, j = 1..15 (ARK_MONT_LIMBS records): 64 mixed additions instead
+// of 255 doublings + ~127 additions.  One window per thread builds it: 4w doublings, 14 additions, and one inversion
+// shared by the 15 points (Montgomery's trick).
+#define PTAU_FB_WINDOWS 64
+#define PTAU_FB_ENTRIES (PTAU_FB_WINDOWS * 15)
+PTAU_HD void store_rec(uint32_t* rec, const Fq& x, const Fq& y, bool inf) {
+#pragma unroll
+  for (int i = 0; i < 12; i++) {
+    rec[i] = inf ? 0u : x.l[i];
+    rec[12 + i] = inf ? 0u : y.l[i];
+  }
+  rec[24] = inf ? 1u : 0u;
+  rec[25] = 0;
+}
+PTAU_HD void store_rec(uint32_t* rec, const Fq2& x, const Fq2& y, bool inf) {
+#pragma unroll
+  for (int i = 0; i < 12; i++) {
+    rec[i] = inf ? 0u : x.c0.l[i];
+    rec[12 + i] = inf ? 0u : x.c1.l[i];
+    rec[24 + i] = inf ? 0u : y.c0.l[i];
+    rec[36 + i] = inf ? 0u : y.c1.l[i];
+  }
+  rec[48] = inf ? 1u : 0u;
+  rec[49] = 0;
+}
+PTAU_HD void load_rec(const uint32_t* rec, Fq& x, Fq& y, bool& inf) { load_g1_rec(rec, x, y, inf); }
+PTAU_HD void load_rec(const uint32_t* rec, Fq2& x, Fq2& y, bool& inf) { load_g2_rec(rec, x, y, inf); }
+template <class F>
+struct RecWords;
+template <>
+struct RecWords<Fq> {
+  static constexpr int value = 26;
+};
+template <>
+struct RecWords<Fq2> {
+  static constexpr int value = 50;
+};
+
+// window w of the table of the base given as a record
+template <class F>
+PTAU_HD_NOINLINE void fixed_base_window(uint32_t* tbl, const uint32_t* base_rec, int w, const F& one) {
+  constexpr int REC = RecWords<F>::value;
+  uint32_t* out = tbl + (size_t)w * 15 * REC;
+  F bx, by;
+  bool binf;
+  load_rec(base_rec, bx, by, binf);
+  Jac<F> m[15];
+  m[0].X = bx;
+  m[0].Y = by;
+  m[0].Z = binf ? fsub(one, one) : one;
+#pragma unroll 1
+  for (int i = 0; i < 4 * w; i++)
+    if (!fis_zero(m[0].Z)) jac_dbl(m[0]);
+#pragma unroll 1
+  for (int j = 1; j < 15; j++) {
+    m[j] = m[j - 1];
+    jac_add_complete_t(m[j], m[0]);
+  }
+  // one inversion for the 15 Z coordinates
+  F pre[15];
+  F acc = one;
+#pragma unroll 1
+  for (int j = 0; j < 15; j++) {
+    pre[j] = acc;
+    if (!fis_zero(m[j].Z)) acc = fmul(acc, m[j].Z);
+  }
+  F inv = finv(acc);
+#pragma unroll 1
+  for (int j = 14; j >= 0; --j) {
+    if (fis_zero(m[j].Z)) {
+      store_rec(out + j * REC, bx, by, true);
+      continue;
+    }
+    F zi = fmul(inv, pre[j]);
+    inv = fmul(inv, m[j].Z);
+    F zi2 = fsqr(zi);
+    store_rec(out + j * REC, fmul(m[j].X, zi2), fmul(m[j].Y, fmul(zi2, zi)), false);
+  }
+}
+// acc = [k] B from B's table; k = 8 little-endian words
+template <class F>
+PTAU_HD_NOINLINE void fixed_base_mul(Jac<F>& acc, const uint32_t* tbl, const uint32_t* k, const F& one) {
+  constexpr int REC = RecWords<F>::value;
+  acc.X = fsub(one, one);
+  acc.Y = one;
+  acc.Z = acc.X;
+#pragma unroll 1
+  for (int w = 0; w < PTAU_FB_WINDOWS; w++) {
+    const uint32_t d = (k[w >> 3] >> ((w & 7) * 4)) & 15u;
+    if (!d) continue;
+    F x, y;
+    bool inf;
+    load_rec(tbl + ((size_t)w * 15 + d - 1) * REC, x, y, inf);
+    if (!inf) jac_madd_complete_t(acc, x, y, one);
+  }
+}
+
 // ---- one item of the two public operations --------------------------------------------------------
 // prod_{k<2} e(P_k, Q_k): g1 = 2 G1 records (26 words each), g2 = 2 G2 records (50 words each);
 // gt_out (144 words) may be null.  Returns whether the product is 1.
@@ -515,8 +614,11 @@ PTAU_HD_NOINLINE bool pairing_product2_item(const uint32_t* g1, const uint32_t* 
 
 // KZG10::check of one opening: e(C - [v]g - [rv]gamma_g, h) == e(w, beta_h - [z]h), evaluated as
 // e(inner, h) * e(-w, beta_h - [z]h) == 1.  Scalars: 8 little-endian words, < r; random_v may be null.
+// tbl_g / tbl_gg / tbl_h: fixed-base tables of g, gamma_g, h (fixed_base_window), or null for plain double-and-add.
 PTAU_HD_NOINLINE bool kzg_check_item(const uint32_t* vk_g1, const uint32_t* vk_g2, const uint32_t* comm, const uint32_t* point,
-                                     const uint32_t* value, const uint32_t* proof_w, const uint32_t* random_v) {
+                                     const uint32_t* value, const uint32_t* proof_w, const uint32_t* random_v,
+                                     const uint32_t* tbl_g = nullptr, const uint32_t* tbl_gg = nullptr,
+                                     const uint32_t* tbl_h = nullptr) {
   Fq px[2], py[2];
   Fq2 qx[2], qy[2];
   bool use[2];
@@ -530,13 +632,19 @@ PTAU_HD_NOINLINE bool kzg_check_item(const uint32_t* vk_g1, const uint32_t* vk_g
     Jac<Fq> acc;
 #pragma unroll
     for (int w = 0; w < 8; w++) k[w] = ginf ? 0u : value[w];
-    jac_scalar_mul_t(acc, gx, gy, k, fq_one());
+    if (tbl_g)
+      fixed_base_mul(acc, tbl_g, k, fq_one());
+    else
+      jac_scalar_mul_t(acc, gx, gy, k, fq_one());
     if (random_v) {
       load_g1_rec(vk_g1 + 26, gx, gy, ginf);
 #pragma unroll
       for (int w = 0; w < 8; w++) k[w] = ginf ? 0u : random_v[w];
       Jac<Fq> t;
-      jac_scalar_mul_t(t, gx, gy, k, fq_one());
+      if (tbl_gg)
+        fixed_base_mul(t, tbl_gg, k, fq_one());
+      else
+        jac_scalar_mul_t(t, gx, gy, k, fq_one());
       jac_add_complete_t(acc, t);
     }
     acc.Y = fq_neg(acc.Y);
@@ -550,7 +658,10 @@ PTAU_HD_NOINLINE bool kzg_check_item(const uint32_t* vk_g1, const uint32_t* vk_g
     Jac<Fq2> acc;
 #pragma unroll
     for (int w = 0; w < 8; w++) k[w] = hinf ? 0u : point[w];
-    jac_scalar_mul_t(acc, qx[0], qy[0], k, fq2_one());
+    if (tbl_h)
+      fixed_base_mul(acc, tbl_h, k, fq2_one());
+    else
+      jac_scalar_mul_t(acc, qx[0], qy[0], k, fq2_one());
     acc.Y = fq2_neg(acc.Y);
     Fq2 bx, by;
     bool binf;

@@ -71,11 +71,21 @@ extern "C" void hostemul_pairing_product2(const uint8_t* g1, const uint8_t* g2, 
     std::memcpy(gt_out + i * 576, gt, 576);
   }
 }
+// use_tables != 0: fixed-base window tables for g, gamma_g, h (the path the library takes), else double-and-add
 extern "C" void hostemul_kzg_check(const uint8_t* vk_g1, const uint8_t* vk_g2, const uint8_t* comms, const uint8_t* points,
-                                   const uint8_t* values, const uint8_t* proofs, const uint8_t* random_v, size_t n, uint8_t* ok) {
+                                   const uint8_t* values, const uint8_t* proofs, const uint8_t* random_v, size_t n, uint8_t* ok,
+                                   int use_tables) {
   uint32_t v1[52], v2[100];
   std::memcpy(v1, vk_g1, 208);
   std::memcpy(v2, vk_g2, 400);
+  static uint32_t tg[PTAU_FB_ENTRIES * 26], tgg[PTAU_FB_ENTRIES * 26], th[PTAU_FB_ENTRIES * 50];
+  if (use_tables) {
+    for (int w = 0; w < PTAU_FB_WINDOWS; w++) {
+      fixed_base_window<Fq>(tg, v1, w, fq_one());
+      fixed_base_window<Fq>(tgg, v1 + 26, w, fq_one());
+      fixed_base_window<Fq2>(th, v2, w, fq2_one());
+    }
+  }
   for (size_t i = 0; i < n; i++) {
     uint32_t c[26], w[26], z[8], v[8], rv[8];
     std::memcpy(c, comms + i * 104, 104);
@@ -83,6 +93,9 @@ extern "C" void hostemul_kzg_check(const uint8_t* vk_g1, const uint8_t* vk_g2, c
     std::memcpy(z, points + i * 32, 32);
     std::memcpy(v, values + i * 32, 32);
     if (random_v) std::memcpy(rv, random_v + i * 32, 32);
-    ok[i] = kzg_check_item(v1, v2, c, z, v, w, random_v ? rv : nullptr) ? 1 : 0;
+    ok[i] = (use_tables ? kzg_check_item(v1, v2, c, z, v, w, random_v ? rv : nullptr, tg, tgg, th)
+                        : kzg_check_item(v1, v2, c, z, v, w, random_v ? rv : nullptr))
+                ? 1
+                : 0;
   }
 }

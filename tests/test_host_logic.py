@@ -373,12 +373,18 @@ def test_limb_pairing_code_vs_oracle(hostemul):
     vk2 = g2r(o.G2_GEN) + g2r(o.g2_mul(o.G2_GEN, tau))
     le = lambda v: (v % R).to_bytes(32, "little")  # noqa: E731
     ok = ctypes.create_string_buffer(2)
-    hostemul.hostemul_kzg_check(vk1, vk2, g1r(comm) * 2, le(zpt) * 2, le(ev(coeffs, zpt)) + le(ev(coeffs, zpt) + 1), g1r(w) * 2,
-                                le(ev(blind, zpt)) * 2, ctypes.c_size_t(2), ok)
-    assert ok.raw == b"\x01\x00"
-    # without hiding
     comm0 = o.g1_mul(o.G1_GEN, ev(coeffs, tau))
     w0 = o.g1_mul(o.G1_GEN, ev(quot(coeffs, zpt), tau))
-    hostemul.hostemul_kzg_check(vk1, vk2, g1r(comm0) * 2, le(zpt) + le(zpt + 1), le(ev(coeffs, zpt)) * 2, g1r(w0) * 2, None,
-                                ctypes.c_size_t(2), ok)
-    assert ok.raw == b"\x01\x00"
+    big = R - 12345  # a full-width evaluation point: every window of the fixed-base tables is used
+    wb = o.g1_mul(o.G1_GEN, ev(quot(coeffs, big), tau))
+    for use_tables in (0, 1):  # plain double-and-add, then the fixed-base window tables the library uses
+        hostemul.hostemul_kzg_check(vk1, vk2, g1r(comm) * 2, le(zpt) * 2, le(ev(coeffs, zpt)) + le(ev(coeffs, zpt) + 1),
+                                    g1r(w) * 2, le(ev(blind, zpt)) * 2, ctypes.c_size_t(2), ok, use_tables)
+        assert ok.raw == b"\x01\x00"
+        # without hiding
+        hostemul.hostemul_kzg_check(vk1, vk2, g1r(comm0) * 2, le(zpt) + le(zpt + 1), le(ev(coeffs, zpt)) * 2, g1r(w0) * 2, None,
+                                    ctypes.c_size_t(2), ok, use_tables)
+        assert ok.raw == b"\x01\x00"
+        hostemul.hostemul_kzg_check(vk1, vk2, g1r(comm0) * 2, le(big) * 2, le(ev(coeffs, big)) + le(ev(coeffs, big) - 1),
+                                    g1r(wb) * 2, None, ctypes.c_size_t(2), ok, use_tables)
+        assert ok.raw == b"\x01\x00"
