@@ -724,6 +724,18 @@ def test_kzg10_check_mirrors_reference_test(ctx, tmp_path):
     bad_rv = [None if r is None else (r + 1) % R for r in rvs]
     res = kz.KZG10.check_many(vk, comms, points, values, proofs, bad_rv, ctx=ctx)
     assert not res[hid].any() and res[[i for i in range(N) if rvs[i] is None]].all()
+    # the fixed-base tables are cached per verifier key: another key must rebuild them, and going back must too
+    vk_g = kz.VerifierKey(g=powers.powers_of_g[1], gamma_g=vk.gamma_g, h=vk.h, beta_h=vk.beta_h)
+    assert not kz.KZG10.check_many(vk_g, comms, points, values, proofs, rvs, ctx=ctx).any()
+    vk_gg = kz.VerifierKey(g=vk.g, gamma_g=powers.powers_of_g[2], h=vk.h, beta_h=vk.beta_h)
+    res = kz.KZG10.check_many(vk_gg, comms, points, values, proofs, rvs, ctx=ctx)
+    assert not res[hid].any() and res[[i for i in range(N) if rvs[i] is None]].all()
+    g2x = ctx.convert(2, ZU, ctx.generate(2, ZU, 5, tau, 0, 2), ML, 0).reshape(2, 200)   # (5H, 5 tau H): consistent pair
+    vk_h = kz.VerifierKey(g=vk.g, gamma_g=vk.gamma_g, h=g2x[0], beta_h=g2x[1])
+    assert kz.KZG10.check_many(vk_h, comms, points, values, proofs, rvs, ctx=ctx).all()
+    vk_hbad = kz.VerifierKey(g=vk.g, gamma_g=vk.gamma_g, h=g2x[0], beta_h=vk.beta_h)     # (5H, tau H): inconsistent
+    assert not kz.KZG10.check_many(vk_hbad, comms, points, values, proofs, rvs, ctx=ctx).any()
+    assert kz.KZG10.check_many(vk, comms, points, values, proofs, rvs, ctx=ctx).all()
     # same boolean as the CPU restatement of KZG10::check (slow: a few cases)
     ovk = (o.g1_mul(o.G1_GEN, 1), o.g1_mul(o.G1_GEN, alpha), o.G2_GEN, o.g2_mul(o.G2_GEN, tau))
 
