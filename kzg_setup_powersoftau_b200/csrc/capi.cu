@@ -34,6 +34,9 @@ struct GpuSlot {
   cudaEvent_t ev_first = nullptr, ev_last = nullptr;
   cudaEvent_t ev_k0[kBufs] = {nullptr, nullptr}, ev_k1[kBufs] = {nullptr, nullptr};
   uint32_t* d_tbl[2] = {nullptr, nullptr};  // fixed-base tables of the generator (G1, G2), built lazily
+  // KZG10::check: fixed-base tables of the verifier key's g, gamma_g, h, rebuilt when the key changes
+  void* d_kzg_tbl = nullptr;
+  std::string kzg_tbl_key;
 };
 
 }  // namespace
@@ -44,9 +47,6 @@ struct ptau_ctx {
   GpuSlot gpu[kMaxGpus];
   ptau_timing timing;
   std::string last_error;
-  // KZG10::check: fixed-base tables of the verifier key's g, gamma_g, h on GPU 0, rebuilt when the key changes
-  void* d_kzg_tbl = nullptr;
-  std::string kzg_tbl_key;
 };
 
 namespace {
@@ -249,7 +249,7 @@ void ptau_destroy(ptau_ctx* ctx) {
       if (s.d_tbl[t]) cudaFree(s.d_tbl[t]);
     if (s.ev_first) cudaEventDestroy(s.ev_first);
     if (s.ev_last) cudaEventDestroy(s.ev_last);
-    if (g == 0 && ctx->d_kzg_tbl) cudaFree(ctx->d_kzg_tbl);
+    if (s.d_kzg_tbl) cudaFree(s.d_kzg_tbl);
   }
   delete ctx;
 }
@@ -674,6 +674,45 @@ int ptau_load_phase1(ptau_ctx* ctx, const void* data, uint64_t len, uint64_t m, 
                       bad_kind, &sec);
 }
 
+namespace {
+// one multi-scalar multiplication on one GPU, issued asynchronously on the slot's first stream
+struct MsmJob {
+  void *d_pts = nullptr, *d_sc = nullptr, *d_part = nullptr, *d_out = nullptr;
+  int launches = 0;
+  uint8_t result[104];
+  ~MsmJob() {
+    cudaFree(d_pts);
+    cudaFree(d_sc);
+    cudaFree(d_part);
+    cudaFree(d_out);
+  }
+};
+cudaError_t msm_issue(GpuSlot& s, MsmJob& j, const void* pts, const void* sc, size_t n) {
+  cudaError_t e = cudaSetDevice(s.device);
+  ptau::MsmPlan plan;
+  ptau::msm_g1_plan(n, &plan);
+  if (e == cudaSuccess) e = cudaMalloc(&j.d_pts, n * 104 + 16);
+  if (e == cudaSuccess) e = cudaMalloc(&j.d_sc, n * 32 + 16);
+  if (e == cudaSuccess) e = cudaMalloc(&j.d_part, plan.scratch_bytes);
+  if (e == cudaSuccess) e = cudaMalloc(&j.d_out, 104);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(j.d_pts, pts, n * 104, cudaMemcpyHostToDevice, s.stream[0]);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(j.d_sc, sc, n * 32, cudaMemcpyHostToDevice, s.stream[0]);
+  if (e == cudaSuccess) e = cudaEventRecord(s.ev_k0[0], s.stream[0]);
+  if (e == cudaSuccess) e = ptau::launch_msm_g1(j.d_pts, j.d_sc, n, j.d_part, j.d_out, &j.launches, s.stream[0]);
+  if (e == cudaSuccess) e = cudaEventRecord(s.ev_k1[0], s.stream[0]);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(j.result, j.d_out, 104, cudaMemcpyDeviceToHost, s.stream[0]);
+  return e;
+}
+cudaError_t msm_wait(GpuSlot& s, float* ms) {
+  cudaError_t e = cudaSetDevice(s.device);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s.stream[0]);
+  if (e == cudaSuccess) e = cudaEventElapsedTime(ms, s.ev_k0[0], s.ev_k1[0]);
+  return e;
+}
+}  // namespace
+
+// With several GPUs in the context the terms are sharded by contiguous index range like every other call of the
+// library; the per-GPU partial sums (one point each) are added by one more tiny MSM with unit scalars on GPU 0.
 int ptau_kzg_commit(ptau_ctx* ctx, const void* powers, const void* coeffs, size_t n, void* commitment) {
   if (!ctx || (!powers && n) || (!coeffs && n) || !commitment) return PTAU_ERR_ARG;
   // scalars must be canonical (< r), like ark's Fr
@@ -681,42 +720,50 @@ int ptau_kzg_commit(ptau_ctx* ctx, const void* powers, const void* coeffs, size_
     Fr c = fr_from_le32((const uint8_t*)coeffs + i * 32);
     if (fr_ge_mod(c.l)) return PTAU_ERR_ARG;
   }
-  GpuSlot& s = ctx->gpu[0];
-  CUDA_TRY(ctx, cudaSetDevice(s.device));
   ptau::MsmPlan plan;
   ptau::msm_g1_plan(n, &plan);
   // point indices travel in 31 bits and the bucket lists (n x W entries) are addressed with 32-bit offsets
   if (n >= (1ull << 31) || (uint64_t)n * (uint64_t)plan.W >= (1ull << 32)) return PTAU_ERR_ARG;
-  int launches = 0;
-  void *d_pts = nullptr, *d_sc = nullptr, *d_part = nullptr, *d_out = nullptr;
-  cudaError_t e = cudaMalloc(&d_pts, n * 104 + 16);
-  if (e == cudaSuccess) e = cudaMalloc(&d_sc, n * 32 + 16);
-  if (e == cudaSuccess) e = cudaMalloc(&d_part, plan.scratch_bytes);
-  if (e == cudaSuccess) e = cudaMalloc(&d_out, 104);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(d_pts, powers, n * 104, cudaMemcpyHostToDevice, s.stream[0]);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(d_sc, coeffs, n * 32, cudaMemcpyHostToDevice, s.stream[0]);
-  if (e == cudaSuccess) e = cudaEventRecord(s.ev_k0[0], s.stream[0]);
-  if (e == cudaSuccess) e = ptau::launch_msm_g1(d_pts, d_sc, n, d_part, d_out, &launches, s.stream[0]);
-  if (e == cudaSuccess) e = cudaEventRecord(s.ev_k1[0], s.stream[0]);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(commitment, d_out, 104, cudaMemcpyDeviceToHost, s.stream[0]);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(s.stream[0]);
-  float ms = 0;
-  if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, s.ev_k0[0], s.ev_k1[0]);
-  cudaFree(d_pts);
-  cudaFree(d_sc);
-  cudaFree(d_part);
-  cudaFree(d_out);
+  const int G = (ctx->n_gpus > 1 && n >= (size_t)ctx->n_gpus * (1u << 12)) ? ctx->n_gpus : 1;
+  memset(&ctx->timing, 0, sizeof(ctx->timing));
+  ctx->timing.n_gpus = ctx->n_gpus;
+  MsmJob jobs[kMaxGpus];
+  cudaError_t e = cudaSuccess;
+  for (int g = 0; g < G && e == cudaSuccess; g++) {
+    const size_t lo = n * g / G, hi = n * (g + 1) / G;
+    e = msm_issue(ctx->gpu[g], jobs[g], (const uint8_t*)powers + lo * 104, (const uint8_t*)coeffs + lo * 32, hi - lo);
+    ctx->timing.h2d_bytes[g] = (hi - lo) * 136;
+    ctx->timing.d2h_bytes[g] = 104;
+  }
+  for (int g = 0; g < G && e == cudaSuccess; g++) {
+    float ms = 0;
+    e = msm_wait(ctx->gpu[g], &ms);
+    ctx->timing.kernel_ms[g] = ms;
+    ctx->timing.gpu_ms[g] = ms;
+    ctx->timing.kernel_launches += jobs[g].launches;
+  }
+  if (e == cudaSuccess && G > 1) {
+    uint8_t parts[kMaxGpus * 104], ones[kMaxGpus * 32];
+    memset(ones, 0, sizeof(ones));
+    for (int g = 0; g < G; g++) {
+      memcpy(parts + g * 104, jobs[g].result, 104);
+      ones[g * 32] = 1;
+    }
+    MsmJob fin;
+    float ms = 0;
+    e = msm_issue(ctx->gpu[0], fin, parts, ones, (size_t)G);
+    if (e == cudaSuccess) e = msm_wait(ctx->gpu[0], &ms);
+    ctx->timing.kernel_ms[0] += ms;
+    ctx->timing.gpu_ms[0] += ms;
+    ctx->timing.kernel_launches += fin.launches;
+    memcpy(commitment, fin.result, 104);
+  } else if (e == cudaSuccess) {
+    memcpy(commitment, jobs[0].result, 104);
+  }
   if (e != cudaSuccess) {
     ctx->last_error = std::string("kzg_commit: ") + cudaGetErrorString(e);
     return PTAU_ERR_CUDA;
   }
-  memset(&ctx->timing, 0, sizeof(ctx->timing));
-  ctx->timing.n_gpus = ctx->n_gpus;
-  ctx->timing.kernel_ms[0] = ms;
-  ctx->timing.gpu_ms[0] = ms;
-  ctx->timing.kernel_launches = launches;
-  ctx->timing.h2d_bytes[0] = n * 136;
-  ctx->timing.d2h_bytes[0] = 104;
   return PTAU_OK;
 }
 
@@ -786,48 +833,63 @@ int ptau_kzg_check(ptau_ctx* ctx, const void* vk_g1, const void* vk_g2, const vo
   // scalars must be canonical (< r), like ark's Fr
   if (!scalars_canonical(points, n) || !scalars_canonical(values, n) || (random_v && !scalars_canonical(random_v, n)))
     return PTAU_ERR_ARG;
-  GpuSlot& s = ctx->gpu[0];
-  CUDA_TRY(ctx, cudaSetDevice(s.device));
-  DevArgs a;
-  void *dv1 = nullptr, *dv2 = nullptr, *dc = nullptr, *dz = nullptr, *dv = nullptr, *dw = nullptr, *drv = nullptr, *dok = nullptr;
-  cudaStream_t st = s.stream[0];
-  cudaError_t e = a.push(vk_g1, 2 * 104, st, &dv1);
-  if (e == cudaSuccess) e = a.push(vk_g2, 2 * 200, st, &dv2);
-  if (e == cudaSuccess) e = a.push(comms, n * 104, st, &dc);
-  if (e == cudaSuccess) e = a.push(points, n * 32, st, &dz);
-  if (e == cudaSuccess) e = a.push(values, n * 32, st, &dv);
-  if (e == cudaSuccess) e = a.push(proofs_w, n * 104, st, &dw);
-  if (e == cudaSuccess && random_v) e = a.push(random_v, n * 32, st, &drv);
-  if (e == cudaSuccess) e = a.push(nullptr, n, st, &dok);
-  int launches = 1;
-  if (e == cudaSuccess) {  // fixed-base tables of g, gamma_g, h: kept while the key stays the same
-    std::string key((const char*)vk_g1, 2 * 104);
-    key.append((const char*)vk_g2, 200);
-    if (!ctx->d_kzg_tbl) e = cudaMalloc(&ctx->d_kzg_tbl, ptau::kzg_tables_bytes());
-    if (e == cudaSuccess && key != ctx->kzg_tbl_key) {
-      e = ptau::launch_kzg_tables(dv1, dv2, ctx->d_kzg_tbl, st);
-      if (e == cudaSuccess) ctx->kzg_tbl_key = key;
-      launches++;
+  // openings are independent: contiguous index ranges over the context's GPUs, no exchange
+  const int G = (ctx->n_gpus > 1 && n >= (size_t)ctx->n_gpus * 64) ? ctx->n_gpus : 1;
+  std::string key((const char*)vk_g1, 2 * 104);
+  key.append((const char*)vk_g2, 200);
+  memset(&ctx->timing, 0, sizeof(ctx->timing));
+  ctx->timing.n_gpus = ctx->n_gpus;
+  DevArgs args[kMaxGpus];
+  cudaError_t e = cudaSuccess;
+  for (int g = 0; g < G && e == cudaSuccess; g++) {
+    GpuSlot& s = ctx->gpu[g];
+    const size_t lo = n * g / G, cnt = n * (g + 1) / G - lo;
+    cudaStream_t st = s.stream[0];
+    DevArgs& a = args[g];
+    void *dv1 = nullptr, *dv2 = nullptr, *dc = nullptr, *dz = nullptr, *dv = nullptr, *dw = nullptr, *drv = nullptr, *dok = nullptr;
+    e = cudaSetDevice(s.device);
+    if (e == cudaSuccess) e = a.push(vk_g1, 2 * 104, st, &dv1);
+    if (e == cudaSuccess) e = a.push(vk_g2, 2 * 200, st, &dv2);
+    if (e == cudaSuccess) e = a.push((const uint8_t*)comms + lo * 104, cnt * 104, st, &dc);
+    if (e == cudaSuccess) e = a.push((const uint8_t*)points + lo * 32, cnt * 32, st, &dz);
+    if (e == cudaSuccess) e = a.push((const uint8_t*)values + lo * 32, cnt * 32, st, &dv);
+    if (e == cudaSuccess) e = a.push((const uint8_t*)proofs_w + lo * 104, cnt * 104, st, &dw);
+    if (e == cudaSuccess && random_v) e = a.push((const uint8_t*)random_v + lo * 32, cnt * 32, st, &drv);
+    if (e == cudaSuccess) e = a.push(nullptr, cnt, st, &dok);
+    int launches = 1;
+    if (e == cudaSuccess) {  // fixed-base tables of g, gamma_g, h: kept while the key stays the same
+      if (!s.d_kzg_tbl) e = cudaMalloc(&s.d_kzg_tbl, ptau::kzg_tables_bytes());
+      if (e == cudaSuccess && key != s.kzg_tbl_key) {
+        e = ptau::launch_kzg_tables(dv1, dv2, s.d_kzg_tbl, st);
+        if (e == cudaSuccess) s.kzg_tbl_key = key;
+        launches++;
+      }
     }
+    if (e == cudaSuccess) e = cudaEventRecord(s.ev_k0[0], st);
+    if (e == cudaSuccess) e = ptau::launch_kzg_check(dv1, dv2, dc, dz, dv, dw, drv, s.d_kzg_tbl, cnt, dok, st);
+    if (e == cudaSuccess) e = cudaEventRecord(s.ev_k1[0], st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ok + lo, dok, cnt, cudaMemcpyDeviceToHost, st);
+    ctx->timing.kernel_launches += launches;
+    ctx->timing.h2d_bytes[g] = 608 + cnt * (104 + 32 + 32 + 104 + (random_v ? 32 : 0));
+    ctx->timing.d2h_bytes[g] = cnt;
   }
-  if (e == cudaSuccess) e = cudaEventRecord(s.ev_k0[0], st);
-  if (e == cudaSuccess) e = ptau::launch_kzg_check(dv1, dv2, dc, dz, dv, dw, drv, ctx->d_kzg_tbl, n, dok, st);
-  if (e == cudaSuccess) e = cudaEventRecord(s.ev_k1[0], st);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(ok, dok, n, cudaMemcpyDeviceToHost, st);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-  float ms = 0;
-  if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, s.ev_k0[0], s.ev_k1[0]);
+  for (int g = 0; g < G && e == cudaSuccess; g++) {
+    GpuSlot& s = ctx->gpu[g];
+    float ms = 0;
+    e = cudaSetDevice(s.device);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s.stream[0]);
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, s.ev_k0[0], s.ev_k1[0]);
+    ctx->timing.kernel_ms[g] = ms;
+    ctx->timing.gpu_ms[g] = ms;
+  }
   if (e != cudaSuccess) {
+    for (int g = 0; g < G; g++) {  // nothing may still be reading the buffers DevArgs is about to free
+      cudaSetDevice(ctx->gpu[g].device);
+      cudaStreamSynchronize(ctx->gpu[g].stream[0]);
+    }
     ctx->last_error = std::string("kzg_check: ") + cudaGetErrorString(e);
     return PTAU_ERR_CUDA;
   }
-  memset(&ctx->timing, 0, sizeof(ctx->timing));
-  ctx->timing.n_gpus = ctx->n_gpus;
-  ctx->timing.kernel_ms[0] = ms;
-  ctx->timing.gpu_ms[0] = ms;
-  ctx->timing.kernel_launches = launches;
-  ctx->timing.h2d_bytes[0] = 608 + n * (104 + 32 + 32 + 104 + (random_v ? 32 : 0));
-  ctx->timing.d2h_bytes[0] = n;
   return PTAU_OK;
 }
 

@@ -790,3 +790,41 @@ def test_multi_gpu_sharding_is_invisible(cref):
                 c.convert(2, ZC, zc, AU, STRICT)
             codes.append((e.value.index, e.value.code))
         assert codes[0] == codes[1] and codes[0][0] == 30_000
+
+
+def test_multi_gpu_consumer_ops():
+    """KZG10 commit (MSM) and check sharded by index range over every GPU of the box: same commitment bytes and same
+    booleans as with one GPU."""
+    from kzg_setup_powersoftau_b200 import _ffi
+
+    ngpu = _ffi.lib().ptau_device_count()
+    if ngpu < 2:
+        pytest.skip("single-GPU box")
+    R = o.R_ORDER
+    tau = o.derive_scalars(11)[0]
+    n = 70_001
+    rnd = random.Random(3)
+    with kz.Context(1) as c1, kz.Context(ngpu) as cn:
+        pts = c1.convert(1, ZU, c1.generate(1, ZU, 1, tau, 0, n), ML, 0).reshape(n, 104)
+        sc = [rnd.randrange(R) for _ in range(n)]
+        pw = kz.Powers(powers_of_g=pts, powers_of_gamma_g=pts[:1])
+        a = kz.KZG10.commit(pw, sc, ctx=c1)
+        b = kz.KZG10.commit(pw, sc, ctx=cn)
+        assert a.tobytes() == b.tobytes()
+        q = o.g1_mul(o.G1_GEN, sum(c * pow(tau, i, R) for i, c in enumerate(sc[:2000])) % R)
+        assert kz.KZG10.commit(pw, sc[:2000], ctx=cn).tobytes() == o.g1_mont_record(q[0], q[1], False)   # small: one GPU
+        g2p = c1.convert(2, ZU, c1.generate(2, ZU, 1, tau, 0, 2), ML, 0).reshape(2, 200)
+        vk = kz.VerifierKey(g=pts[0], gamma_g=pts[5], h=g2p[0], beta_h=g2p[1])
+        poly = [rnd.randrange(R) for _ in range(12)]
+        comm = kz.KZG10.commit(pw, poly, ctx=c1)
+        m = 3000
+        zs = [rnd.randrange(R) for _ in range(m)]
+        opened = [kz.KZG10.open(pw, poly, z, ctx=c1) for z in zs[:8]]
+        vals = [opened[i % 8][0] for i in range(m)]
+        prfs = [opened[i % 8][1] for i in range(m)]
+        zs = [zs[i % 8] for i in range(m)]
+        vals[1234] = (vals[1234] + 1) % R
+        vals[2999] = (vals[2999] + 1) % R
+        r1 = kz.KZG10.check_many(vk, [comm] * m, zs, vals, prfs, ctx=c1)
+        rn = kz.KZG10.check_many(vk, [comm] * m, zs, vals, prfs, ctx=cn)
+        assert (r1 == rn).all() and r1.sum() == m - 2 and not r1[1234] and not r1[2999]
