@@ -209,7 +209,7 @@ int ptau_load_setup_file(ptau_ctx* ctx, int variant, const char* setup_path, uin
 /* unkeyed BLAKE2b-512 of a file as 128 hex chars + NUL (blake2b_simd, src/lib.rs:128-131) */
 int ptau_blake2b_file(const char* path, char out_hex[129]);
 
-/* ---- consumer side (first step) ---------------------------------------- */
+/* ---- consumer side: KZG10 commit / check --------------------------------- */
 /* KZG10 commitment without hiding: commitment = sum_i [coeffs_i] powers_i, the multi-scalar
  * multiplication inside ark-poly-commit 0.2 KZG10::commit (used at src/lib.rs:268-275).
  * powers: n PTAU_FMT_ARK_MONT_LIMBS G1 records (e.g. Powers.powers_of_g from ptau_load_setup);
