@@ -269,11 +269,13 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     stream = torch.cuda.current_stream()
 
-    def timed_steps(group, in_fmt, out_fmt, checks, din, dout, n, steps, warmup):
+    def timed_steps(group, in_fmt, out_fmt, checks, din, dout, n, steps, warmup, all_ranks=True):
+        # all_ranks=False: called by rank 0 alone (extra legs) -- no collective may be issued there
+        sync = barrier if all_ranks else torch.cuda.synchronize
         for _ in range(warmup):
             ctx.convert_device(group, in_fmt, din.data_ptr(), out_fmt, dout.data_ptr(), n, checks, status.data_ptr(),
                                base_index=first, stream=stream.cuda_stream)
-        barrier()
+        sync()
         total = 0.0
         for _ in range(steps):
             flush.fill_(1)  # evict L2 between timed iterations (outside the timed events)
@@ -284,7 +286,7 @@ def main():
             e1.record(stream)
             e1.synchronize()
             total += e0.elapsed_time(e1)
-        barrier()
+        sync()
         return total  # ms for `steps` launches
 
     clocks, stop = [], threading.Event()
@@ -355,7 +357,9 @@ def main():
         }
         # ---- other kernels of the path (not the headline) ----
         extra = {}
-        if not args.no_extra:
+        # the other kernels of the path, the whole-job legs and the CPU baseline are reported at N=1 only: under
+        # torchrun the other ranks would sit in the closing barrier while rank 0 runs them
+        if not args.no_extra and world == 1:
             def leg(name, group, in_fmt, out_fmt, checks, n, key):
                 ri = kz._ffi.lib().ptau_record_size(group, in_fmt)
                 ro = kz._ffi.lib().ptau_record_size(group, out_fmt)
@@ -368,7 +372,7 @@ def main():
                     ctx.convert_device(group, ZU, din.data_ptr(), AU, tmp.data_ptr(), n, 0, status.data_ptr())
                     torch.cuda.synchronize()
                     din = tmp
-                t = timed_steps(group, in_fmt, out_fmt, checks, din, dout, n, 5, 3) / 5
+                t = timed_steps(group, in_fmt, out_fmt, checks, din, dout, n, 5, 3, all_ranks=False) / 5
                 r = {"points": n, "ms": t, "points_per_s": n / (t / 1e3), "GBps": n * (ri + ro) / (t / 1e3) / 1e9}
                 if key:
                     r["imad_frac"] = n * FQMUL[key] * IMAD_PER_FQMUL / (t / 1e3) / mb["imad32"]
@@ -489,9 +493,11 @@ def main():
                                     "achieved": hb["GBps"], "peak": 6552.0, "unit": "GB/s",
                                     "frac": hb["GBps"] / 6552.0, "traffic": None}
         line["extra"] = extra
-        # ---- CPU baseline: the reference's algorithms on this box's host cores ----
+        # ---- CPU baseline: the reference's algorithms on this box's host cores (rank 0, N=1 only) ----
         threads = os.cpu_count() or 1
         try:
+            if world > 1:
+                raise RuntimeError("cpu_baseline is measured at N=1 only")
             rate1, _ = cpu_baseline(1 << 10, 1, tau)
             n_s = 1 << 13  # probe, then size the sample to ~15 s of host work (capped at the whole 2^20 workload)
             rate, dt = cpu_baseline(n_s, threads, tau)
@@ -507,7 +513,7 @@ def main():
             }
         except Exception as e:  # the oracle is optional for the product, never for correctness claims
             line["cpu_baseline"] = {"value": None, "unit": "points/s", "cores": threads, "kind": "port",
-                                    "sample": "unavailable: %r" % (e,)}
+                                    "sample": "not measured in this run: %s" % (e,)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
