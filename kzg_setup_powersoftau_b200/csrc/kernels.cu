@@ -14,6 +14,7 @@
 
 #include "kernels.h"
 #include "point.cuh"
+#include "msm_digits.cuh"
 
 namespace ptau {
 
@@ -647,32 +648,6 @@ static __device__ __forceinline__ Jac<Fq> jac_load(const uint32_t* s) {
   return q;
 }
 
-// window geometry shared by the kernels: windows [0, a) are c bits wide with NB = 2^(c-1) buckets,
-// windows [a, W) are c - 1 bits wide with NB / 2 buckets
-struct MsmGeom {
-  int c, W, a, lgL;
-  uint32_t NB;
-};
-static __device__ __forceinline__ int msm_bitoff(const MsmGeom& g, int w) { return w < g.a ? w * g.c : g.a * g.c + (w - g.a) * (g.c - 1); }
-static __device__ __forceinline__ uint32_t msm_bucket_base(const MsmGeom& g, int w) {
-  return w < g.a ? (uint32_t)w * g.NB : (uint32_t)g.a * g.NB + (uint32_t)(w - g.a) * (g.NB >> 1);
-}
-
-// signed digit of the cw-bit window (cw <= 16) starting at `bit` of the 256-bit little-endian scalar k, with the
-// carry of the windows below.  v in [0, 2^cw]; v > 2^(cw-1) becomes v - 2^cw with a carry into the next window.
-static __device__ __forceinline__ int msm_digit(const uint32_t* __restrict__ k, int bit, int cw, uint32_t& carry) {
-  const int wi = bit >> 5, sh = bit & 31;
-  uint64_t t = k[wi];
-  if (wi + 1 < 8) t |= (uint64_t)k[wi + 1] << 32;
-  uint32_t v = ((uint32_t)(t >> sh) & ((1u << cw) - 1u)) + carry;
-  if (v > (1u << (cw - 1))) {
-    carry = 1;
-    return (int)v - (1 << cw);
-  }
-  carry = 0;
-  return (int)v;
-}
-
 // pts: ARK_MONT_LIMBS records (26 words); scalars: 8 x u32 LE each, < r.  SCATTER = false: histogram
 // into cnt[]; SCATTER = true: cnt[] holds the running cursor of every bucket, entries[] receives the indices.
 template <bool SCATTER>
@@ -867,15 +842,12 @@ __global__ void msm_finish(const uint32_t* __restrict__ wsum, int W, uint32_t* _
 }
 
 void msm_g1_plan(uint64_t n, MsmPlan* p) {
-  int lg = 0;
-  while (lg < 63 && (1ull << lg) < n) lg++;
-  int c = lg - 4;  // about 32 points per bucket
-  c = c < 3 ? 3 : c > 16 ? 16 : c;
-  p->c = c;
-  p->W = (256 + c - 1) / c;
-  p->a = 256 - (c - 1) * p->W;  // windows of width c; the other W - a are c - 1 wide: a c + (W - a)(c - 1) = 256
-  p->NB = 1u << (c - 1);
-  p->lgL = c - 2 < 4 ? c - 2 : 4;
+  const MsmGeom g = msm_geometry(n);
+  p->c = g.c;
+  p->W = g.W;
+  p->a = g.a;
+  p->NB = g.NB;
+  p->lgL = g.lgL;
   p->buckets = (uint64_t)p->a * p->NB + (uint64_t)(p->W - p->a) * (p->NB >> 1);
   p->segments = p->buckets >> p->lgL;
   const uint64_t a256 = 256;

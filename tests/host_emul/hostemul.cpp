@@ -5,6 +5,7 @@
 #include <cstring>
 #include "../../kzg_setup_powersoftau_b200/csrc/point.cuh"
 #include "../../kzg_setup_powersoftau_b200/csrc/pairing.cuh"
+#include "../../kzg_setup_powersoftau_b200/csrc/msm_digits.cuh"
 
 using namespace ptau;
 
@@ -98,4 +99,27 @@ extern "C" void hostemul_kzg_check(const uint8_t* vk_g1, const uint8_t* vk_g2, c
                 ? 1
                 : 0;
   }
+}
+
+// bucket-MSM recoding: geometry for n terms and the signed digits of one scalar (digits[w], bit offsets, bucket bases);
+// returns the final carry (must be 0 for scalars < 2^255)
+extern "C" int hostemul_msm_recode(uint64_t n, const uint32_t* k, int* geom /*c, W, a, lgL, NB*/, int* digits, int* bitoff,
+                                   uint32_t* bases) {
+  MsmGeom g = msm_geometry(n);
+  geom[0] = g.c;
+  geom[1] = g.W;
+  geom[2] = g.a;
+  geom[3] = g.lgL;
+  geom[4] = (int)g.NB;
+  uint32_t carry = 0;
+  int bit = 0;
+  for (int w = 0; w < g.W; w++) {
+    const int cw = w < g.a ? g.c : g.c - 1;
+    digits[w] = msm_digit(k, bit, cw, carry);
+    bitoff[w] = msm_bitoff(g, w);
+    bases[w] = msm_bucket_base(g, w);
+    if (bitoff[w] != bit) return -1;
+    bit += cw;
+  }
+  return bit == 256 ? (int)carry : -2;
 }

@@ -388,3 +388,46 @@ def test_limb_pairing_code_vs_oracle(hostemul):
         hostemul.hostemul_kzg_check(vk1, vk2, g1r(comm0) * 2, le(big) * 2, le(ev(coeffs, big)) + le(ev(coeffs, big) - 1),
                                     g1r(wb) * 2, None, ctypes.c_size_t(2), ok, use_tables)
         assert ok.raw == b"\x01\x00"
+
+
+def test_msm_signed_window_recoding(hostemul):
+    """The bucket MSM's window geometry and signed-digit recoding (csrc/msm_digits.cuh, the code the kernels run):
+    widths add up to 256, digits stay within [-(2^(cw-1) - 1), 2^(cw-1)], the top digit is non-negative with no carry
+    out, bucket bases are contiguous, and the digits recompose the scalar -- for every window width and for scalars
+    that stress the carries."""
+    R = o.R_ORDER
+    rnd = random.Random(9)
+    widths = set()
+    for n in [1, 2, 100, 200, 300, 600, 2047, 4096, 5000, 10_000, 32768, 40_000, 65537, 131073, 262149, 1 << 20, 1 << 24]:
+        geom = (ctypes.c_int * 5)()
+        digits = (ctypes.c_int * 128)()
+        bitoff = (ctypes.c_int * 128)()
+        bases = (ctypes.c_uint32 * 128)()
+        scalars = [0, 1, R - 1, (1 << 255) - 1, (1 << 254) + 12345] + [rnd.randrange(R) for _ in range(20)]
+        for k in scalars:
+            kw = (ctypes.c_uint32 * 8)(*[(k >> (32 * i)) & 0xFFFFFFFF for i in range(8)])
+            carry = hostemul.hostemul_msm_recode(ctypes.c_uint64(n), kw, geom, digits, bitoff, bases)
+            c, W, a, lgL, NB = list(geom)
+            assert carry == 0, (n, hex(k), carry)
+            assert 3 <= c <= 16 and W == -(-256 // c) and 0 <= a <= W and a * c + (W - a) * (c - 1) == 256
+            assert (NB >> 1) % (1 << lgL) == 0
+            widths.add(c)
+            base = 0
+            for w in range(W):
+                cw = c if w < a else c - 1
+                assert -(1 << (cw - 1)) < digits[w] <= (1 << (cw - 1)), (n, w, digits[w])
+                assert bases[w] == base
+                base += 1 << (cw - 1)
+            assert digits[W - 1] >= 0
+            assert sum(digits[w] << bitoff[w] for w in range(W)) == k, (n, hex(k))
+        # boundary digits: exactly 2^(cw-1) stays positive, one more goes negative with a carry
+        for delta in (0, 1):
+            k = sum(((1 << ((c if w < a else c - 1) - 1)) + delta) << bitoff[w] for w in range(W - 2))
+            kw = (ctypes.c_uint32 * 8)(*[(k >> (32 * i)) & 0xFFFFFFFF for i in range(8)])
+            assert hostemul.hostemul_msm_recode(ctypes.c_uint64(n), kw, geom, digits, bitoff, bases) == 0
+            assert sum(digits[w] << bitoff[w] for w in range(W)) == k
+            if delta == 0:
+                assert all(digits[w] == 1 << ((c if w < a else c - 1) - 1) for w in range(W - 2))
+            else:
+                assert digits[0] < 0
+    assert widths == set(range(3, 17))
