@@ -258,6 +258,16 @@ def test_pairing_oracle_pins():
     assert po.product_of_pairings([(o.G1_GEN, None), (None, o.G2_GEN)]) == po.F12_ONE
     negg = (o.G1_GEN[0], (-o.G1_GEN[1]) % o.P)
     assert po.product_of_pairings([(o.G1_GEN, o.G2_GEN), (negg, o.G2_GEN)]) == po.F12_ONE
+    # External known answer: the generator of Gt published in the zkcrypto `bls12_381` crate (pairings.rs,
+    # Gt::generator()) starts with the Montgomery limbs below for c0.c0.c0.  That crate's final exponentiation
+    # (Hayashida-Hayasaka-Teruya) raises to 3 (p^4 - p^2 + 1) / r, so its generator is the CUBE of the reduced
+    # pairing e(G1, G2) computed here.  (c0 is invariant under conjugation, so this pins the value up to the
+    # inversion that the sign convention for z < 0 decides.)
+    cube = po.f12_pow(e, 3)
+    c000_c0 = (cube[0] + cube[6]) % o.P   # flat basis -> tower: a0 + a1 u sits at (a0 - a1) + a1 w^6
+    mont = c000_c0 * o.MONT_R % o.P
+    assert [(mont >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(6)] == [
+        0x1972E433A01F85C5, 0x97D32B76FD772538, 0xC8CE546FC96BCDF9, 0xCEF63E7366D40614, 0xA611342781843780, 0x13F3448A3FC6D825]
     z, p, r = o.Z, o.P, o.R_ORDER
     assert (z - 1) ** 2 % 3 == 0 and (z - 1) ** 2 // 3 == 0x396C8C005555E1568C00AAAB0000AAAB
     assert (p ** 4 - p ** 2 + 1) % r == 0
