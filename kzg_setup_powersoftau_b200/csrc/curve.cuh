@@ -155,6 +155,30 @@ PTAU_HD bool jac_eq_affine(const Jac<F>& p, const F& x, const F& y) {
 // ---- constants (Montgomery form) --------------------------------------------
 #include "consts.inc"
 
+// ---- Fermat inversion a^(p-2), host- and device-callable -------------------------------------------------
+#define PTAU_PM2_INIT                                                                                       \
+  {0xffffaaa9u, 0xb9feffffu, 0xb153ffffu, 0x1eabfffeu, 0xf6b0f624u, 0x6730d2a0u, 0xf38512bfu, 0x64774b84u, \
+   0x434bacd7u, 0x4b1ba7b6u, 0x397fe69au, 0x1a0111eau}
+#ifdef __CUDACC__
+__constant__ uint32_t K_PM2_PAIR_D[12] = PTAU_PM2_INIT;
+#endif
+static const uint32_t K_PM2_PAIR_H[12] = PTAU_PM2_INIT;
+PTAU_HD_NOINLINE Fq fq_inv_fermat(Fq a) {
+#ifdef __CUDA_ARCH__
+  const uint32_t* e = K_PM2_PAIR_D;
+#else
+  const uint32_t* e = K_PM2_PAIR_H;
+#endif
+  Fq acc = a;
+#pragma unroll 1
+  for (int i = 379; i >= 0; --i) {
+    acc = fq_sqr(acc);
+    if ((e[i >> 5] >> (i & 31)) & 1u) acc = fq_mul(acc, a);
+  }
+  return acc;
+}
+
+
 // y^2 == x^3 + 4
 PTAU_HD_NOINLINE bool g1_on_curve(const Fq& x, const Fq& y) {
   Fq rhs = fq_add(fq_mul(fq_sqr(x), x), k_b1_mont());

@@ -14,7 +14,7 @@
 
 #include "kernels.h"
 #include "point.cuh"
-#include "msm_digits.cuh"
+#include "msm.cuh"
 
 namespace ptau {
 
@@ -564,90 +564,6 @@ cudaError_t launch_generate_win(int group, int fmt, const uint32_t* s0_mont, con
 // infinity and zero scalars all occur in the tests), not ladders with known-safe scalars.
 // =============================================================================
 
-// acc += (x, y) with every special case of the group law (madd-2007-bl, 7M + 4S; the quantities that
-// decide the special cases are the ones the formula needs anyway)
-static __device__ __noinline__ void g1_madd_complete(Jac<Fq>& acc, const Fq& x, const Fq& y) {
-  if (fq_is_zero(acc.Z)) {
-    acc.X = x;
-    acc.Y = y;
-    acc.Z = fq_one();
-    return;
-  }
-  Fq zz = fq_sqr(acc.Z);
-  Fq u2 = fq_mul(x, zz);
-  Fq s2 = fq_mul(fq_mul(y, acc.Z), zz);
-  if (fq_eq(u2, acc.X)) {
-    if (fq_eq(s2, acc.Y)) {
-      jac_dbl(acc);
-    } else {
-      acc.Z = fq_zero();  // P + (-P)
-    }
-    return;
-  }
-  Fq H = fq_sub(u2, acc.X);
-  Fq I = fq_sqr(fq_dbl(H));
-  Fq J = fq_mul(H, I);
-  Fq rr = fq_dbl(fq_sub(s2, acc.Y));
-  Fq V = fq_mul(acc.X, I);
-  Fq X3 = fq_sub(fq_sub(fq_sqr(rr), J), fq_dbl(V));
-  acc.Y = fq_sub(fq_mul(rr, fq_sub(V, X3)), fq_dbl(fq_mul(acc.Y, J)));
-  acc.Z = fq_dbl(fq_mul(acc.Z, H));
-  acc.X = X3;
-}
-// p += q, both Jacobian (add-2007-bl, 11M + 5S), every special case
-static __device__ __noinline__ void g1_add_complete(Jac<Fq>& p, const Jac<Fq>& q) {
-  if (fq_is_zero(q.Z)) return;
-  if (fq_is_zero(p.Z)) {
-    p = q;
-    return;
-  }
-  Fq z1z1 = fq_sqr(p.Z), z2z2 = fq_sqr(q.Z);
-  Fq u1 = fq_mul(p.X, z2z2), u2 = fq_mul(q.X, z1z1);
-  Fq s1 = fq_mul(fq_mul(p.Y, q.Z), z2z2), s2 = fq_mul(fq_mul(q.Y, p.Z), z1z1);
-  if (fq_eq(u1, u2)) {
-    if (fq_eq(s1, s2)) {
-      jac_dbl(p);
-    } else {
-      p.Z = fq_zero();
-    }
-    return;
-  }
-  Fq H = fq_sub(u2, u1);
-  Fq I = fq_sqr(fq_dbl(H));
-  Fq J = fq_mul(H, I);
-  Fq rr = fq_dbl(fq_sub(s2, s1));
-  Fq V = fq_mul(u1, I);
-  Fq X3 = fq_sub(fq_sub(fq_sqr(rr), J), fq_dbl(V));
-  p.Y = fq_sub(fq_mul(rr, fq_sub(V, X3)), fq_dbl(fq_mul(s1, J)));
-  p.Z = fq_mul(fq_dbl(fq_mul(p.Z, q.Z)), H);
-  p.X = X3;
-}
-static __device__ __forceinline__ Jac<Fq> jac_infinity() {
-  Jac<Fq> a;
-  a.X = fq_zero();
-  a.Y = fq_one();
-  a.Z = fq_zero();
-  return a;
-}
-static __device__ __forceinline__ void jac_store(uint32_t* o, const Jac<Fq>& a) {
-#pragma unroll
-  for (int w = 0; w < 12; w++) {
-    o[w] = a.X.l[w];
-    o[12 + w] = a.Y.l[w];
-    o[24 + w] = a.Z.l[w];
-  }
-}
-static __device__ __forceinline__ Jac<Fq> jac_load(const uint32_t* s) {
-  Jac<Fq> q;
-#pragma unroll
-  for (int w = 0; w < 12; w++) {
-    q.X.l[w] = s[w];
-    q.Y.l[w] = s[12 + w];
-    q.Z.l[w] = s[24 + w];
-  }
-  return q;
-}
-
 // pts: ARK_MONT_LIMBS records (26 words); scalars: 8 x u32 LE each, < r.  SCATTER = false: histogram
 // into cnt[]; SCATTER = true: cnt[] holds the running cursor of every bucket, entries[] receives the indices.
 template <bool SCATTER>
@@ -729,52 +645,15 @@ __global__ void __launch_bounds__(PTAU_BLOCK) msm_bucket_sum(const uint32_t* __r
                                                              uint32_t* __restrict__ buckets /* 36 words each */) {
   const uint32_t b = blockIdx.x * PTAU_BLOCK + threadIdx.x;
   if (b >= m) return;
-  Jac<Fq> acc = jac_infinity();
-  const uint32_t e1 = off[b + 1];
-#pragma unroll 1
-  for (uint32_t e = off[b]; e < e1; e++) {
-    const uint32_t v = entries[e];
-    const uint32_t* rec = pts + (uint64_t)(v & 0x7fffffffu) * 26;
-    Fq x = load_tbl_field<Fq>(rec), y = load_tbl_field<Fq>(rec + 12);
-    if (v >> 31) y = fq_neg(y);
-    g1_madd_complete(acc, x, y);
-  }
-  jac_store(buckets + (uint64_t)b * 36, acc);
+  msm_bucket_item(pts, entries, off, b, buckets);
 }
 
-// one thread per run of L = 2^lgL consecutive buckets of one window: sum_{j in run} j * B_j, where bucket
-// index j0 (0-based) holds the points of digit magnitude j0 + 1.  Running sums from the top give
-// sum (j0 - lo + 1) B_j0 and t = sum B_j0; the run's offset adds [lo] t.
+// one thread per run of L = 2^lgL consecutive buckets of one window (msm.cuh: msm_segment_item)
 __global__ void __launch_bounds__(PTAU_BLOCK) msm_window_segments(const uint32_t* __restrict__ buckets, MsmGeom g, uint32_t nseg_total,
                                                                   uint32_t* __restrict__ seg /* 36 words each */) {
   const uint32_t t_id = blockIdx.x * PTAU_BLOCK + threadIdx.x;
   if (t_id >= nseg_total) return;
-  // runs are laid out exactly like the buckets, L buckets per run
-  const uint32_t lo_abs = t_id << g.lgL;
-  const uint32_t wide = (uint32_t)g.a * g.NB;
-  const uint32_t in_window = lo_abs < wide ? lo_abs % g.NB : (lo_abs - wide) % (g.NB >> 1);
-  const uint32_t sidx = in_window >> g.lgL;
-  const uint32_t* base = buckets + (uint64_t)lo_abs * 36;
-  Jac<Fq> t = jac_infinity(), sacc = jac_infinity();
-#pragma unroll 1
-  for (int j = (1 << g.lgL) - 1; j >= 0; --j) {
-    Jac<Fq> q = jac_load(base + (uint64_t)j * 36);
-    g1_add_complete(t, q);
-    g1_add_complete(sacc, t);
-  }
-  if (sidx) {  // sacc += [lo] t = [2^lgL] [sidx] t
-    Jac<Fq> m = jac_infinity();
-#pragma unroll 1
-    for (int bit = 31 - __clz(sidx); bit >= 0; --bit) {
-      if (!fq_is_zero(m.Z)) jac_dbl(m);
-      if ((sidx >> bit) & 1u) g1_add_complete(m, t);
-    }
-#pragma unroll 1
-    for (int k = 0; k < g.lgL; k++)
-      if (!fq_is_zero(m.Z)) jac_dbl(m);
-    g1_add_complete(sacc, m);
-  }
-  jac_store(seg + (uint64_t)t_id * 36, sacc);
+  msm_segment_item(buckets, g, t_id, seg);
 }
 
 // one block per window: adds the window's runs up (strided per thread, then a shared-memory tree) and applies
@@ -801,44 +680,15 @@ __global__ void __launch_bounds__(PTAU_BLOCK) msm_window_sum(const uint32_t* __r
     __syncthreads();
   }
   if (threadIdx.x == 0) {
-    const int nd = msm_bitoff(g, w);
-#pragma unroll 1
-    for (int k = 0; k < nd; k++)
-      if (!fq_is_zero(acc.Z)) jac_dbl(acc);
+    msm_window_weight(acc, g, w);
     jac_store(wsum + (uint64_t)w * 36, acc);
   }
 }
 
-// sum of the weighted window sums, then one ARK_MONT_LIMBS record (affine, or ark zero() = (0, 1, infinity))
+// sum of the weighted window sums, one inversion, one record (msm.cuh: msm_finish_item)
 __global__ void msm_finish(const uint32_t* __restrict__ wsum, int W, uint32_t* __restrict__ out) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  Jac<Fq> acc = jac_infinity();
-#pragma unroll 1
-  for (int w = 0; w < W; w++) {
-    Jac<Fq> q = jac_load(wsum + (uint64_t)w * 36);
-    g1_add_complete(acc, q);
-  }
-  if (fq_is_zero(acc.Z)) {
-    Fq one = fq_one();
-#pragma unroll
-    for (int w = 0; w < 12; w++) {
-      out[w] = 0;
-      out[12 + w] = one.l[w];
-    }
-    out[24] = 1;
-    out[25] = 0;
-  } else {
-    Fq zi = fq_inv(acc.Z);
-    Fq zi2 = fq_sqr(zi);
-    Fq x = fq_mul(acc.X, zi2), y = fq_mul(acc.Y, fq_mul(zi2, zi));
-#pragma unroll
-    for (int w = 0; w < 12; w++) {
-      out[w] = x.l[w];
-      out[12 + w] = y.l[w];
-    }
-    out[24] = 0;
-    out[25] = 0;
-  }
+  msm_finish_item(wsum, W, out);
 }
 
 void msm_g1_plan(uint64_t n, MsmPlan* p) {

@@ -27,33 +27,13 @@ struct Fq12 {
 
 // Like the rest of csrc/, everything here also compiles for the host (tests/host_emul) so that the CPU-only
 // suite runs the exact limb-level code against the oracle.
-#define PTAU_PM2_INIT                                                                                       \
-  {0xffffaaa9u, 0xb9feffffu, 0xb153ffffu, 0x1eabfffeu, 0xf6b0f624u, 0x6730d2a0u, 0xf38512bfu, 0x64774b84u, \
-   0x434bacd7u, 0x4b1ba7b6u, 0x397fe69au, 0x1a0111eau}
 // (z-1)^2 / 3 = 0x396c8c005555e1568c00aaab0000aaab (126 bits)
 #define PTAU_H1_INIT {0x0000aaabu, 0x8c00aaabu, 0x5555e156u, 0x396c8c00u}
 #ifdef __CUDACC__
-__constant__ uint32_t K_PM2_PAIR_D[12] = PTAU_PM2_INIT;
 __constant__ uint32_t K_H1_D[4] = PTAU_H1_INIT;
 #endif
-static const uint32_t K_PM2_PAIR_H[12] = PTAU_PM2_INIT;
 static const uint32_t K_H1_H[4] = PTAU_H1_INIT;
 
-// a^(p-2)
-PTAU_HD_NOINLINE Fq fq_inv_fermat(Fq a) {
-#ifdef __CUDA_ARCH__
-  const uint32_t* e = K_PM2_PAIR_D;
-#else
-  const uint32_t* e = K_PM2_PAIR_H;
-#endif
-  Fq acc = a;
-#pragma unroll 1
-  for (int i = 379; i >= 0; --i) {
-    acc = fq_sqr(acc);
-    if ((e[i >> 5] >> (i & 31)) & 1u) acc = fq_mul(acc, a);
-  }
-  return acc;
-}
 PTAU_HD_NOINLINE Fq2 fq2_inv(const Fq2& a) {
   Fq n = fq_inv_fermat(fq_add(fq_sqr(a.c0), fq_sqr(a.c1)));
   Fq2 r;

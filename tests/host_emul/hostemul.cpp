@@ -5,7 +5,8 @@
 #include <cstring>
 #include "../../kzg_setup_powersoftau_b200/csrc/point.cuh"
 #include "../../kzg_setup_powersoftau_b200/csrc/pairing.cuh"
-#include "../../kzg_setup_powersoftau_b200/csrc/msm_digits.cuh"
+#include "../../kzg_setup_powersoftau_b200/csrc/msm.cuh"
+#include <vector>
 
 using namespace ptau;
 
@@ -122,4 +123,53 @@ extern "C" int hostemul_msm_recode(uint64_t n, const uint32_t* k, int* geom /*c,
     bit += cw;
   }
   return bit == 256 ? (int)carry : -2;
+}
+
+// the whole bucket MSM with the product's per-item code (csrc/msm.cuh), the kernels' loops run serially
+extern "C" void hostemul_msm_g1(const uint8_t* pts8, const uint8_t* sc8, size_t n, uint8_t* out104) {
+  std::vector<uint32_t> pts(n * 26 + 1), sc(n * 8 + 1);
+  std::memcpy(pts.data(), pts8, n * 104);
+  std::memcpy(sc.data(), sc8, n * 32);
+  const MsmGeom g = msm_geometry(n);
+  const uint32_t m = (uint32_t)g.a * g.NB + (uint32_t)(g.W - g.a) * (g.NB >> 1);
+  std::vector<uint32_t> cnt(m + 1, 0), off(m + 1, 0), cur(m + 1, 0), entries(n * (size_t)g.W + 1);
+  auto digits = [&](bool scatter) {
+    for (size_t i = 0; i < n; i++) {
+      if (pts[i * 26 + 24] & 0xffu) continue;
+      uint32_t carry = 0, base = 0;
+      int bit = 0;
+      for (int w = 0; w < g.W; w++) {
+        const int cw = w < g.a ? g.c : g.c - 1;
+        int d = msm_digit(&sc[i * 8], bit, cw, carry);
+        if (d != 0) {
+          uint32_t b = base + (uint32_t)(d < 0 ? -d : d) - 1u;
+          if (scatter) entries[cur[b]++] = (uint32_t)i | (d < 0 ? 0x80000000u : 0u);
+          else cnt[b]++;
+        }
+        bit += cw;
+        base += 1u << (cw - 1);
+      }
+    }
+  };
+  digits(false);
+  for (uint32_t b = 0; b < m; b++) off[b + 1] = off[b] + cnt[b];
+  cur = off;
+  digits(true);
+  std::vector<uint32_t> buckets((size_t)m * 36), segs(((size_t)m >> g.lgL) * 36), wsum((size_t)g.W * 36);
+  for (uint32_t b = 0; b < m; b++) msm_bucket_item(pts.data(), entries.data(), off.data(), b, buckets.data());
+  const uint32_t nseg = m >> g.lgL;
+  for (uint32_t t = 0; t < nseg; t++) msm_segment_item(buckets.data(), g, t, segs.data());
+  for (int w = 0; w < g.W; w++) {
+    const uint32_t first = msm_bucket_base(g, w) >> g.lgL, count = (w < g.a ? g.NB : g.NB >> 1) >> g.lgL;
+    Jac<Fq> acc = jac_infinity();
+    for (uint32_t i = 0; i < count; i++) {
+      Jac<Fq> q = jac_load(segs.data() + (size_t)(first + i) * 36);
+      g1_add_complete(acc, q);
+    }
+    msm_window_weight(acc, g, w);
+    jac_store(wsum.data() + (size_t)w * 36, acc);
+  }
+  uint32_t out[26];
+  msm_finish_item(wsum.data(), g.W, out);
+  std::memcpy(out104, out, 104);
 }

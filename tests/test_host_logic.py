@@ -431,3 +431,39 @@ def test_msm_signed_window_recoding(hostemul):
             else:
                 assert digits[0] < 0
     assert widths == set(range(3, 17))
+
+
+def test_limb_msm_code_vs_known_tau(hostemul):
+    """The bucket MSM's per-item code (csrc/msm.cuh: bucket sums with complete additions, running-sum window
+    reduction, window weights, final inversion) run serially on the host: sum c_i [tau^i]G == [sum c_i tau^i]G,
+    plus repeated points, cancellation, zero scalars and infinity records."""
+    R = o.R_ORDER
+    tau = 0xABCDEF123
+    rnd = random.Random(13)
+
+    def rec(q):
+        return o.g1_mont_record(0, 1, True) if q is None else o.g1_mont_record(q[0], q[1], False)
+
+    def msm(points, scalars):
+        out = ctypes.create_string_buffer(104)
+        hostemul.hostemul_msm_g1(b"".join(points), b"".join(int(s).to_bytes(32, "little") for s in scalars),
+                                 ctypes.c_size_t(len(scalars)), out)
+        return out.raw
+
+    n = 300   # c = 5: 52 windows of 5 and 4 bits
+    pts, q = [], o.G1_GEN
+    tp = [1]
+    for i in range(n):
+        pts.append(rec(q))
+        q = o.g1_mul(q, tau)
+        tp.append(tp[-1] * tau % R)
+    for m in (1, 7, 130, n):   # c = 3, 3, 4, 5
+        sc = [rnd.randrange(R) for _ in range(m)]
+        assert msm(pts[:m], sc) == rec(o.g1_mul(o.G1_GEN, sum(c * t for c, t in zip(sc, tp)) % R)), m
+    assert msm(pts[:50], [R - 1] * 50) == rec(o.g1_mul(o.G1_GEN, (-sum(tp[:50])) % R))
+    assert msm(pts[:50], [0] * 50) == rec(None)
+    assert msm([pts[3]] * 40, [7] * 40) == rec(o.g1_mul(o.G1_GEN, 280 * tp[3] % R))          # P + P inside a bucket
+    assert msm([pts[3]] * 40, [9, R - 9] * 20) == rec(None)                                  # P + (-P)
+    holes = [p if i % 3 else p[:96] + b"\x01" + p[97:] for i, p in enumerate(pts[:60])]
+    sc = [rnd.randrange(R) for _ in range(60)]
+    assert msm(holes, sc) == rec(o.g1_mul(o.G1_GEN, sum(c * t for i, (c, t) in enumerate(zip(sc, tp)) if i % 3) % R))
