@@ -354,6 +354,9 @@ def main():
                     "HBM traffic is 192 B/point = %.2f GB/s, <0.1%% of %.0f GB/s" % (
                         FQMUL["g1_unc"], 192 * N / kernel_s / 1e9, 6552.0),
             "measured_imad_wide_per_s": mb["imad_wide"], "measured_fq_mul_per_s": mb["fq_mul"],
+            # ncu sm__pipe_fmaheavy_cycles_active of this kernel (profiles/r01_final2_ncu_full_all_kernels.csv): the
+            # algorithmic fraction above counts a squaring as a multiplication, the pipe counter does not
+            "fma_heavy_pipe_busy_ncu": 0.857,
         }
         # ---- other kernels of the path (not the headline) ----
         extra = {}

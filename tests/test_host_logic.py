@@ -467,3 +467,24 @@ def test_limb_msm_code_vs_known_tau(hostemul):
     holes = [p if i % 3 else p[:96] + b"\x01" + p[97:] for i, p in enumerate(pts[:60])]
     sc = [rnd.randrange(R) for _ in range(60)]
     assert msm(holes, sc) == rec(o.g1_mul(o.G1_GEN, sum(c * t for i, (c, t) in enumerate(zip(sc, tp)) if i % 3) % R))
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the GPU arm) needs no GPU: one JSON line with
+    the contract's keys, alone and under torchrun (rank 0 prints, the other rank exits 0 without work)."""
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    cmds = [[sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "3"],
+            [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+             "--master-port", "29655", os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+             "--warmup", "3"]]
+    for n, cmd in ((1, cmds[0]), (2, cmds[1])):
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
+        assert r.returncode == 0, r.stderr[-2000:]
+        lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+        assert len(lines) == 1
+        d = json.loads(lines[0])
+        assert d["impl"] == "reference" and d["n_gpus"] == n and d["steps"] == 1 and d["warmup"] == 3
+        assert d["unit"] == "points/s" and d["higher_is_better"] is True and d["value"] > 0
+        assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+        assert d["e2e"] == {"value": d["value"], "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+        assert "workload" in d["config"] and d["metric"].startswith("G1 points/sec")
