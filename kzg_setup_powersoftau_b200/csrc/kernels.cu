@@ -18,7 +18,9 @@
 
 namespace ptau {
 
+#ifndef PTAU_BLOCK
 #define PTAU_BLOCK 128
+#endif
 // A/B-measured on B200 (tools/ab_bench.py): G1 ladders with the doubling expanded in place
 // (PTAU_G1_DBL_INLINE) run best at 2 blocks/SM (30.1 M pts/s); with calls, 3-4 blocks/SM
 // (29.1-29.4 M pts/s).
@@ -27,6 +29,13 @@ namespace ptau {
 #endif
 #ifndef PTAU_MINBLOCKS_G2
 #define PTAU_MINBLOCKS_G2 2
+#endif
+// threads per block of the convert kernels, per group (A/B knob; the staging buffer is BLK records)
+#ifndef PTAU_BLOCK_G1
+#define PTAU_BLOCK_G1 PTAU_BLOCK
+#endif
+#ifndef PTAU_BLOCK_G2
+#define PTAU_BLOCK_G2 PTAU_BLOCK
 #endif
 
 __device__ __forceinline__ uint4 ld_stream(const uint4* p) {
@@ -38,35 +47,38 @@ __device__ __forceinline__ uint4 ld_stream(const uint4* p) {
 }
 
 // global -> shared, nwords u32 words (block-cooperative, 128-bit where possible)
+template <int BLK>
 __device__ __forceinline__ void stage_in(const uint32_t* __restrict__ g, uint32_t* sm, int nwords) {
   int nvec = nwords >> 2;
   const uint4* g4 = reinterpret_cast<const uint4*>(g);
   uint4* s4 = reinterpret_cast<uint4*>(sm);
-  for (int i = threadIdx.x; i < nvec; i += PTAU_BLOCK) s4[i] = ld_stream(g4 + i);
-  for (int i = (nvec << 2) + threadIdx.x; i < nwords; i += PTAU_BLOCK) sm[i] = g[i];
+  for (int i = threadIdx.x; i < nvec; i += BLK) s4[i] = ld_stream(g4 + i);
+  for (int i = (nvec << 2) + threadIdx.x; i < nwords; i += BLK) sm[i] = g[i];
 }
+template <int BLK>
 __device__ __forceinline__ void stage_out(uint32_t* __restrict__ g, const uint32_t* sm, int nwords) {
   int nvec = nwords >> 2;
   uint4* g4 = reinterpret_cast<uint4*>(g);
   const uint4* s4 = reinterpret_cast<const uint4*>(sm);
-  for (int i = threadIdx.x; i < nvec; i += PTAU_BLOCK) g4[i] = s4[i];
-  for (int i = (nvec << 2) + threadIdx.x; i < nwords; i += PTAU_BLOCK) g[i] = sm[i];
+  for (int i = threadIdx.x; i < nvec; i += BLK) g4[i] = s4[i];
+  for (int i = (nvec << 2) + threadIdx.x; i < nwords; i += BLK) g[i] = sm[i];
 }
 
 template <int G, int INFMT, int OUTFMT, bool HEAVY>
-__global__ void __launch_bounds__(PTAU_BLOCK, (G == PTAU_G1 ? PTAU_MINBLOCKS_G1 : PTAU_MINBLOCKS_G2))
+__global__ void __launch_bounds__((G == PTAU_G1 ? PTAU_BLOCK_G1 : PTAU_BLOCK_G2), (G == PTAU_G1 ? PTAU_MINBLOCKS_G1 : PTAU_MINBLOCKS_G2))
     convert_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint64_t n, uint32_t checks,
                    uint64_t base_index, unsigned long long* __restrict__ status) {
+  constexpr int BLK = G == PTAU_G1 ? PTAU_BLOCK_G1 : PTAU_BLOCK_G2;
   constexpr int WIN = record_bytes(G, INFMT) / 4;
   constexpr int WOUT = record_bytes(G, OUTFMT) / 4;
   constexpr int WMAX = WIN > WOUT ? WIN : WOUT;
-  __shared__ __align__(16) uint32_t sm[PTAU_BLOCK * WMAX];
+  __shared__ __align__(16) uint32_t sm[BLK * WMAX];
 
-  const uint64_t rec0 = (uint64_t)blockIdx.x * PTAU_BLOCK;
-  const int nrec = (int)((n - rec0) < (uint64_t)PTAU_BLOCK ? (n - rec0) : (uint64_t)PTAU_BLOCK);
+  const uint64_t rec0 = (uint64_t)blockIdx.x * BLK;
+  const int nrec = (int)((n - rec0) < (uint64_t)BLK ? (n - rec0) : (uint64_t)BLK);
   const int tid = threadIdx.x;
 
-  stage_in(in + rec0 * WIN, sm, nrec * WIN);
+  stage_in<BLK>(in + rec0 * WIN, sm, nrec * WIN);
   __syncthreads();
 
   uint32_t win[WIN];
@@ -103,24 +115,25 @@ __global__ void __launch_bounds__(PTAU_BLOCK, (G == PTAU_G1 ? PTAU_MINBLOCKS_G1 
     if (st != PTAU_OK) atomicMin(status, (unsigned long long)(((base_index + rec0 + tid) << 8) | st));
   }
   __syncthreads();
-  stage_out(out + rec0 * WOUT, sm, nrec * WOUT);
+  stage_out<BLK>(out + rec0 * WOUT, sm, nrec * WOUT);
 }
 
 template <int G, int INFMT, int OUTFMT>
 static cudaError_t launch_one(const void* d_in, void* d_out, uint64_t n, uint32_t checks, uint64_t base_index,
                               unsigned long long* d_status, cudaStream_t stream) {
   if (n == 0) return cudaSuccess;
-  unsigned grid = (unsigned)((n + PTAU_BLOCK - 1) / PTAU_BLOCK);
+  constexpr int BLK = G == PTAU_G1 ? PTAU_BLOCK_G1 : PTAU_BLOCK_G2;
+  unsigned grid = (unsigned)((n + BLK - 1) / BLK);
   // no curve checks requested on an uncompressed input: the lightweight instance
   // (compressed input is on the curve by construction, so only the subgroup bit matters there)
   const bool light = INFMT == PTAU_FMT_ZCASH_COMPRESSED
                          ? !(checks & PTAU_CHECK_SUBGROUP)
                          : !(checks & (PTAU_CHECK_ON_CURVE | PTAU_CHECK_SUBGROUP));
   if (light)
-    convert_kernel<G, INFMT, OUTFMT, false><<<grid, PTAU_BLOCK, 0, stream>>>(
+    convert_kernel<G, INFMT, OUTFMT, false><<<grid, BLK, 0, stream>>>(
         (const uint32_t*)d_in, (uint32_t*)d_out, n, checks, base_index, d_status);
   else
-    convert_kernel<G, INFMT, OUTFMT, true><<<grid, PTAU_BLOCK, 0, stream>>>(
+    convert_kernel<G, INFMT, OUTFMT, true><<<grid, BLK, 0, stream>>>(
         (const uint32_t*)d_in, (uint32_t*)d_out, n, checks, base_index, d_status);
   return cudaGetLastError();
 }
@@ -274,7 +287,7 @@ __global__ void __launch_bounds__(PTAU_BLOCK)
     }
   }
   __syncthreads();
-  stage_out(out + rec0 * WOUT, sm, nrec * WOUT);
+  stage_out<PTAU_BLOCK>(out + rec0 * WOUT, sm, nrec * WOUT);
 }
 
 cudaError_t launch_generate(int group, int fmt, const uint32_t* d_scalars, void* d_out, uint64_t n,
@@ -516,7 +529,7 @@ __global__ void __launch_bounds__(PTAU_BLOCK)
     __syncthreads();
     if (rec0 < n) {
       const int nrec = (int)((n - rec0) < (uint64_t)PTAU_BLOCK ? (n - rec0) : (uint64_t)PTAU_BLOCK);
-      stage_out(out + rec0 * WOUT, sm, nrec * WOUT);
+      stage_out<PTAU_BLOCK>(out + rec0 * WOUT, sm, nrec * WOUT);
     }
     __syncthreads();
   }
