@@ -828,3 +828,28 @@ def test_multi_gpu_consumer_ops():
         r1 = kz.KZG10.check_many(vk, [comm] * m, zs, vals, prfs, ctx=c1)
         rn = kz.KZG10.check_many(vk, [comm] * m, zs, vals, prfs, ctx=cn)
         assert (r1 == rn).all() and r1.sum() == m - 2 and not r1[1234] and not r1[2999]
+
+
+def test_pairing_golden_vectors(ctx):
+    """tests/golden/pairing_vectors.json through the C ABI on the GPU."""
+    import pairing_oracle as po
+
+    with open(os.path.join(GOLDEN, "pairing_vectors.json")) as f:
+        vec = json.load(f)
+    g1 = np.stack([np.stack([_g1_rec(o.g1_mul(o.G1_GEN, int(s, 16)) if int(s, 16) else None) for s in pv["g1_scalars"]])
+                   for pv in vec["products"]])
+    g2 = np.stack([np.stack([_g2_rec(o.g2_mul(o.G2_GEN, int(s, 16)) if int(s, 16) else None) for s in pv["g2_scalars"]])
+                   for pv in vec["products"]])
+    gt, one = kz.KZG10.pairing_product2(g1, g2, ctx=ctx)
+    for i, pv in enumerate(vec["products"]):
+        flat = po.f12_from_tower([int.from_bytes(gt[i][48 * k:48 * k + 48].tobytes(), "little") for k in range(12)])
+        assert flat == [int(v, 16) for v in pv["gt_flat"]] and bool(one[i]) == pv["is_one"]
+    tau, alpha, _ = o.derive_scalars(0xB200)
+    g2v = ctx.convert(2, ZU, ctx.generate(2, ZU, 1, tau, 0, 2), ML, 0).reshape(2, 200)
+    vk = kz.VerifierKey(g=_g1_rec(o.G1_GEN), gamma_g=_g1_rec(o.g1_mul(o.G1_GEN, alpha)), h=g2v[0], beta_h=g2v[1])
+    ks = vec["kzg_checks"]
+    comms = [_g1_rec(o.g1_mul(o.G1_GEN, int(k["commitment_scalar"], 16))) for k in ks]
+    prfs = [_g1_rec(o.g1_mul(o.G1_GEN, int(k["proof_scalar"], 16)) if int(k["proof_scalar"], 16) else None) for k in ks]
+    res = kz.KZG10.check_many(vk, comms, [int(k["point"], 16) for k in ks], [int(k["value"], 16) for k in ks], prfs,
+                              [None if k["random_v"] is None else int(k["random_v"], 16) for k in ks], ctx=ctx)
+    assert list(res) == [k["expect"] for k in ks]

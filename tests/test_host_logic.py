@@ -488,3 +488,45 @@ def test_bench_reference_arm_contract():
         assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
         assert d["e2e"] == {"value": d["value"], "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
         assert "workload" in d["config"] and d["metric"].startswith("G1 points/sec")
+
+
+def _pairing_vectors():
+    with open(os.path.join(GOLDEN, "pairing_vectors.json")) as f:
+        return json.load(f)
+
+
+def _g1r(q):
+    return o.g1_mont_record(0, 1, True) if q is None else o.g1_mont_record(q[0], q[1], False)
+
+
+def _g2r(q):
+    return o.g2_mont_record((0, 0), (1, 0), True) if q is None else o.g2_mont_record(q[0], q[1], False)
+
+
+def test_limb_pairing_code_on_golden_vectors(hostemul):
+    """tests/golden/pairing_vectors.json (made by tools/make_golden_pairing.py from the independent CPU pairing)
+    against csrc/pairing.cuh compiled for the host: GT values of pairing products and KZG10::check booleans."""
+    import pairing_oracle as po
+
+    vec = _pairing_vectors()
+    for pv in vec["products"]:
+        g1 = b"".join(_g1r(o.g1_mul(o.G1_GEN, int(s, 16)) if int(s, 16) else None) for s in pv["g1_scalars"])
+        g2 = b"".join(_g2r(o.g2_mul(o.G2_GEN, int(s, 16)) if int(s, 16) else None) for s in pv["g2_scalars"])
+        gt = ctypes.create_string_buffer(576)
+        one = ctypes.create_string_buffer(1)
+        hostemul.hostemul_pairing_product2(g1, g2, ctypes.c_size_t(1), gt, one)
+        flat = po.f12_from_tower([int.from_bytes(gt.raw[48 * i:48 * i + 48], "little") for i in range(12)])
+        assert flat == [int(v, 16) for v in pv["gt_flat"]]
+        assert (one.raw == b"\x01") == pv["is_one"]
+    tau, alpha, _ = o.derive_scalars(0xB200)
+    vk1 = _g1r(o.G1_GEN) + _g1r(o.g1_mul(o.G1_GEN, alpha))
+    vk2 = _g2r(o.G2_GEN) + _g2r(o.g2_mul(o.G2_GEN, tau))
+    le = lambda v: int(v, 16).to_bytes(32, "little")  # noqa: E731
+    for kc in vec["kzg_checks"]:
+        comm = o.g1_mul(o.G1_GEN, int(kc["commitment_scalar"], 16))
+        ws = int(kc["proof_scalar"], 16)
+        ok = ctypes.create_string_buffer(1)
+        hostemul.hostemul_kzg_check(vk1, vk2, _g1r(comm), le(kc["point"]), le(kc["value"]),
+                                    _g1r(o.g1_mul(o.G1_GEN, ws) if ws else None),
+                                    le(kc["random_v"]) if kc["random_v"] else None, ctypes.c_size_t(1), ok, 1)
+        assert (ok.raw == b"\x01") == kc["expect"], kc
