@@ -22,6 +22,7 @@
 namespace {
 
 constexpr int kMaxGpus = 8;
+constexpr size_t kEdgePoints = 148 * 2 * 128;  // one wave of convert-kernel blocks on a B200
 constexpr int kBufs = 2;  // double buffering per GPU
 
 struct GpuSlot {
@@ -347,7 +348,18 @@ int ptau_convert(ptau_ctx* ctx, int group, int in_fmt, const void* in, int out_f
       GpuSlot& s = ctx->gpu[g];
       CUDA_TRY(ctx, cudaSetDevice(s.device));
       const int b = r.issued % kBufs;
-      size_t npts = r.hi - r.next < chunk ? r.hi - r.next : chunk;
+      // The first H2D copy and the last D2H copy of a range have nothing to overlap with, so the first and the
+      // last chunk are one wave of blocks (148 SMs x 2 blocks x 128 points) instead of a full chunk.
+      const size_t rem = r.hi - r.next;
+      size_t npts;
+      if (r.issued == 0 && rem > 2 * kEdgePoints && chunk > kEdgePoints)
+        npts = kEdgePoints;
+      else if (rem > chunk + kEdgePoints || chunk <= kEdgePoints)
+        npts = rem < chunk ? rem : chunk;
+      else if (rem > 2 * kEdgePoints)
+        npts = rem - kEdgePoints;  // at most `chunk`; leaves exactly one wave for the last chunk
+      else
+        npts = rem < chunk ? rem : chunk;
       if (r.issued >= kBufs) {
         // the event pair of this buffer is about to be reused: harvest its time
         CUDA_TRY(ctx, cudaEventSynchronize(s.ev_k1[b]));
