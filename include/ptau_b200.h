@@ -218,6 +218,12 @@ int ptau_blake2b_file(const char* path, char out_hex[129]);
  * commit(blinding, powers_of_gamma_g): pass both (point, scalar) lists concatenated. */
 int ptau_kzg_commit(ptau_ctx* ctx, const void* powers, const void* coeffs, size_t n, void* commitment);
 
+/* The polynomial side of KZG10::open (ark-poly-commit 0.2 kzg10 `open` -> `compute_witness_polynomial`, reached from
+ * /root/reference/src/lib.rs:276): quotient = (p(X) - p(z)) / (X - z), value = p(z).  coeffs: n scalars (32 bytes LE,
+ * < r), quotient_out: (n - 1) scalars, value_out: 32 bytes.  Host arithmetic (a sequential recurrence over Fr); the
+ * proof is ptau_kzg_commit(powers, quotient).  No context needed. */
+int ptau_kzg_quotient(const void* coeffs, size_t n, const void* point, void* quotient_out, void* value_out);
+
 /* KZG10::check for n openings in parallel -- ark-poly-commit 0.2 kzg10 `check`, the call the reference's
  * consumer code makes at /root/reference/src/lib.rs:276-286:
  *     e(C_i - [v_i] g - [rv_i] gamma_g, h) == e(w_i, beta_h - [z_i] h)

@@ -318,8 +318,19 @@ class KZG10:
 
     @staticmethod
     def _quotient(coeffs, z):
-        """(p(X) - p(z)) / (X - z) by synthetic division; returns (p(z), quotient coefficients)."""
+        """(p(X) - p(z)) / (X - z) by synthetic division; returns (p(z), quotient coefficients).
+        Long polynomials go through the library's host routine (ptau_kzg_quotient)."""
         n = len(coeffs)
+        if n >= 256:
+            cb = np.frombuffer(b"".join((int(c) % R_ORDER).to_bytes(32, "little") for c in coeffs), dtype=np.uint8)
+            zb = np.frombuffer((int(z) % R_ORDER).to_bytes(32, "little"), dtype=np.uint8)
+            qb = np.zeros((n - 1) * 32, dtype=np.uint8)
+            vb = np.zeros(32, dtype=np.uint8)
+            rc = _ffi.lib().ptau_kzg_quotient(_ptr(cb), n, _ptr(zb), _ptr(qb), _ptr(vb))
+            if rc != 0:
+                raise PtauError(rc)
+            raw = qb.tobytes()
+            return int.from_bytes(vb.tobytes(), "little"), [int.from_bytes(raw[32 * i:32 * i + 32], "little") for i in range(n - 1)]
         q = [0] * max(n - 1, 0)
         carry = 0
         for i in range(n - 1, 0, -1):

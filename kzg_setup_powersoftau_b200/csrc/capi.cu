@@ -161,6 +161,25 @@ Fr fr_to_mont(const Fr& a) {
   memcpy(r2.l, FR_R2, 32);
   return fr_mont_mul(a, r2);
 }
+// a + b mod r, both canonical
+Fr fr_add_mod(const Fr& a, const Fr& b) {
+  Fr r;
+  u128 c = 0;
+  for (int i = 0; i < 4; i++) {
+    c += (u128)a.l[i] + b.l[i];
+    r.l[i] = (uint64_t)c;
+    c >>= 64;
+  }
+  if (c || fr_ge_mod(r.l)) {
+    u128 bw = 0;
+    for (int i = 0; i < 4; i++) {
+      u128 d = (u128)r.l[i] - FR_MOD[i] - (uint64_t)bw;
+      r.l[i] = (uint64_t)d;
+      bw = (d >> 64) & 1;
+    }
+  }
+  return r;
+}
 struct Section {
   int group;
   uint64_t count;
@@ -902,6 +921,33 @@ int ptau_kzg_check(ptau_ctx* ctx, const void* vk_g1, const void* vk_g2, const vo
     ctx->last_error = std::string("kzg_check: ") + cudaGetErrorString(e);
     return PTAU_ERR_CUDA;
   }
+  return PTAU_OK;
+}
+
+// Witness polynomial of KZG10::open: (p(X) - p(z)) / (X - z) by synthetic division, and p(z).  A first-order
+// recurrence over Fr (one Montgomery multiplication per coefficient, carry kept canonical by multiplying with z R),
+// done on the host like ark-poly's division; the commitment to the result is ptau_kzg_commit.
+int ptau_kzg_quotient(const void* coeffs, size_t n, const void* point, void* quotient_out, void* value_out) {
+  if ((!coeffs && n) || !point || !value_out || (n > 1 && !quotient_out)) return PTAU_ERR_ARG;
+  Fr z = fr_from_le32((const uint8_t*)point);
+  if (fr_ge_mod(z.l)) return PTAU_ERR_ARG;
+  const Fr zm = fr_to_mont(z);
+  Fr carry;
+  memset(carry.l, 0, 32);
+  for (size_t i = n; i-- > 1;) {
+    Fr ci = fr_from_le32((const uint8_t*)coeffs + i * 32);
+    if (fr_ge_mod(ci.l)) return PTAU_ERR_ARG;
+    carry = fr_add_mod(ci, fr_mont_mul(carry, zm));
+    memcpy((uint8_t*)quotient_out + (i - 1) * 32, carry.l, 32);
+  }
+  Fr c0;
+  memset(c0.l, 0, 32);
+  if (n) {
+    c0 = fr_from_le32((const uint8_t*)coeffs);
+    if (fr_ge_mod(c0.l)) return PTAU_ERR_ARG;
+  }
+  Fr v = fr_add_mod(c0, fr_mont_mul(carry, zm));
+  memcpy(value_out, v.l, 32);
   return PTAU_OK;
 }
 

@@ -530,3 +530,40 @@ def test_limb_pairing_code_on_golden_vectors(hostemul):
                                     _g1r(o.g1_mul(o.G1_GEN, ws) if ws else None),
                                     le(kc["random_v"]) if kc["random_v"] else None, ctypes.c_size_t(1), ok, 1)
         assert (ok.raw == b"\x01") == kc["expect"], kc
+
+
+def test_kzg_quotient_host_routine():
+    """ptau_kzg_quotient (the polynomial side of KZG10::open) against plain big-integer synthetic division:
+    p(X) - p(z) == (X - z) q(X), including the empty, constant and linear polynomials and non-canonical input."""
+    import numpy as np
+    import kzg_setup_powersoftau_b200 as kz
+    from kzg_setup_powersoftau_b200 import _ffi
+
+    R = o.R_ORDER
+    rnd = random.Random(17)
+    L = _ffi.lib()
+
+    def run(coeffs, z):
+        n = len(coeffs)
+        cb = b"".join(int(c).to_bytes(32, "little") for c in coeffs)
+        q = ctypes.create_string_buffer(max(n - 1, 1) * 32)
+        v = ctypes.create_string_buffer(32)
+        rc = L.ptau_kzg_quotient(cb, n, int(z).to_bytes(32, "little"), q, v)
+        return rc, [int.from_bytes(q.raw[32 * i:32 * i + 32], "little") for i in range(max(n - 1, 0))], int.from_bytes(v.raw, "little")
+
+    for n in (0, 1, 2, 3, 17, 1000):
+        coeffs = [rnd.randrange(R) for _ in range(n)]
+        for z in (0, 1, R - 1, rnd.randrange(R)):
+            rc, q, v = run(coeffs, z)
+            assert rc == 0
+            assert v == sum(c * pow(z, i, R) for i, c in enumerate(coeffs)) % R
+            # (X - z) q(X) + v == p(X), coefficient by coefficient
+            for i in range(n):
+                lhs = ((q[i - 1] if 1 <= i <= n - 1 else 0) - z * (q[i] if i < n - 1 else 0) + (v if i == 0 else 0)) % R
+                assert lhs == coeffs[i], (n, i)
+    assert run([R, 1], 5)[0] == _ffi.ERR_ARG and run([1, 2], R)[0] == _ffi.ERR_ARG
+    # the Python mirror switches to it for long polynomials: same answer as its own loop
+    coeffs = [rnd.randrange(R) for _ in range(300)]
+    v1, q1 = kz.KZG10._quotient(coeffs, 12345)
+    v2, q2 = kz.KZG10._quotient(coeffs[:200], 12345)
+    assert v1 == sum(c * pow(12345, i, R) for i, c in enumerate(coeffs)) % R and len(q1) == 299 and len(q2) == 199
