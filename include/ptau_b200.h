@@ -218,6 +218,14 @@ int ptau_blake2b_file(const char* path, char out_hex[129]);
  * commit(blinding, powers_of_gamma_g): pass both (point, scalar) lists concatenated. */
 int ptau_kzg_commit(ptau_ctx* ctx, const void* powers, const void* coeffs, size_t n, void* commitment);
 
+/* Device-resident powers: a setup's powers are the same for every commitment, so they can be uploaded once (a copy
+ * on every GPU of the context) and later calls send only the scalars.  ptau_kzg_commit_resident commits to the first
+ * n <= n_uploaded powers; same result as ptau_kzg_commit. */
+typedef struct ptau_kzg_powers ptau_kzg_powers;
+int ptau_kzg_powers_upload(ptau_ctx* ctx, const void* powers, size_t n, ptau_kzg_powers** out);
+void ptau_kzg_powers_free(ptau_kzg_powers* powers);
+int ptau_kzg_commit_resident(ptau_ctx* ctx, const ptau_kzg_powers* powers, const void* coeffs, size_t n, void* commitment);
+
 /* The polynomial side of KZG10::open (ark-poly-commit 0.2 kzg10 `open` -> `compute_witness_polynomial`, reached from
  * /root/reference/src/lib.rs:276): quotient = (p(X) - p(z)) / (X - z), value = p(z).  coeffs: n scalars (32 bytes LE,
  * < r), quotient_out: (n - 1) scalars, value_out: 32 bytes.  Host arithmetic (a sequential recurrence over Fr); the

@@ -293,6 +293,21 @@ class KZG10:
 
     @staticmethod
     def _msm(ctx, pairs) -> np.ndarray:
+        if any(isinstance(p, ResidentPoints) for p, _ in pairs):
+            # device-resident operands: one MSM per (points, scalars) pair, partial results added by a two-term MSM
+            parts = []
+            for p, c in pairs:
+                if not len(c):
+                    continue
+                if isinstance(p, ResidentPoints):
+                    parts.append(p.msm(c))
+                else:
+                    parts.append(KZG10._msm(ctx, [(p, c)]))
+            if not parts:
+                return KZG10._msm(ctx, [])
+            if len(parts) == 1:
+                return parts[0]
+            return KZG10._msm(ctx, [(np.stack(parts), [1] * len(parts))])
         pts = np.concatenate([np.ascontiguousarray(p[: len(c)]).reshape(-1) for p, c in pairs if len(c)] or
                              [np.zeros(0, dtype=np.uint8)])
         sc = b"".join((int(v) % R_ORDER).to_bytes(32, "little") for _, c in pairs for v in c)
@@ -426,6 +441,39 @@ class KZG10:
         return bool(KZG10.pairing_product2(g1, g2, ctx=ctx)[1][0])
 
 
+class ResidentPoints:
+    """G1 powers kept on the GPU(s) of a context (ptau_kzg_powers_upload): commitments then send only the scalars.
+    Behaves like the array it was made from as far as KZG10.commit / open are concerned (len, prefix use)."""
+
+    def __init__(self, ctx: "Context", points: np.ndarray):
+        import weakref
+
+        pts = np.ascontiguousarray(np.asarray(points, dtype=np.uint8).reshape(-1, 104))
+        self._ctx = ctx
+        self._n = pts.shape[0]
+        h = C.c_void_p()
+        rc = _ffi.lib().ptau_kzg_powers_upload(ctx._h, _ptr(pts) if self._n else None, self._n, C.byref(h))
+        if rc != 0:
+            ctx._raise(rc)
+        self._h = h
+        weakref.finalize(self, _ffi.lib().ptau_kzg_powers_free, h)
+
+    def __len__(self) -> int:
+        return self._n
+
+    def msm(self, scalars) -> np.ndarray:
+        """sum_i scalars[i] * points[i] over the first len(scalars) resident points -> 104-byte record."""
+        n = len(scalars)
+        if n > self._n:
+            raise PtauError(_ffi.ERR_ARG, detail="more scalars than resident points")
+        sc = KZG10._scalars(scalars)
+        out = np.zeros(104, dtype=np.uint8)
+        rc = _ffi.lib().ptau_kzg_commit_resident(self._ctx._h, self._h, _ptr(sc) if n else None, n, _ptr(out))
+        if rc != 0:
+            self._ctx._raise(rc)
+        return out
+
+
 _default_ctx: Optional[Context] = None
 
 
@@ -458,6 +506,12 @@ class Powers:
     """kzg10::Powers { powers_of_g, powers_of_gamma_g } (src/lib.rs:186-189)."""
     powers_of_g: np.ndarray
     powers_of_gamma_g: np.ndarray
+
+    def to_device(self, ctx: Optional["Context"] = None) -> "Powers":
+        """The same powers kept resident on the context's GPU(s): KZG10.commit / open then upload only scalars."""
+        ctx = ctx or default_context()
+        return Powers(powers_of_g=ResidentPoints(ctx, self.powers_of_g),
+                      powers_of_gamma_g=ResidentPoints(ctx, self.powers_of_gamma_g))
 
 
 @dataclass

@@ -709,24 +709,31 @@ namespace {
 // one multi-scalar multiplication on one GPU, issued asynchronously on the slot's first stream
 struct MsmJob {
   void *d_pts = nullptr, *d_sc = nullptr, *d_part = nullptr, *d_out = nullptr;
+  bool own_pts = true;  // false: d_pts points into a resident copy (ptau_kzg_powers)
   int launches = 0;
   uint8_t result[104];
   ~MsmJob() {
-    cudaFree(d_pts);
+    if (own_pts) cudaFree(d_pts);
     cudaFree(d_sc);
     cudaFree(d_part);
     cudaFree(d_out);
   }
 };
-cudaError_t msm_issue(GpuSlot& s, MsmJob& j, const void* pts, const void* sc, size_t n) {
+// pts: host records, or (resident = true) device records already on this GPU
+cudaError_t msm_issue(GpuSlot& s, MsmJob& j, const void* pts, const void* sc, size_t n, bool resident = false) {
   cudaError_t e = cudaSetDevice(s.device);
   ptau::MsmPlan plan;
   ptau::msm_g1_plan(n, &plan);
-  if (e == cudaSuccess) e = cudaMalloc(&j.d_pts, n * 104 + 16);
+  if (resident) {
+    j.own_pts = false;
+    j.d_pts = const_cast<void*>(pts);
+  } else if (e == cudaSuccess) {
+    e = cudaMalloc(&j.d_pts, n * 104 + 16);
+  }
   if (e == cudaSuccess) e = cudaMalloc(&j.d_sc, n * 32 + 16);
   if (e == cudaSuccess) e = cudaMalloc(&j.d_part, plan.scratch_bytes);
   if (e == cudaSuccess) e = cudaMalloc(&j.d_out, 104);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(j.d_pts, pts, n * 104, cudaMemcpyHostToDevice, s.stream[0]);
+  if (e == cudaSuccess && !resident) e = cudaMemcpyAsync(j.d_pts, pts, n * 104, cudaMemcpyHostToDevice, s.stream[0]);
   if (e == cudaSuccess) e = cudaMemcpyAsync(j.d_sc, sc, n * 32, cudaMemcpyHostToDevice, s.stream[0]);
   if (e == cudaSuccess) e = cudaEventRecord(s.ev_k0[0], s.stream[0]);
   if (e == cudaSuccess) e = ptau::launch_msm_g1(j.d_pts, j.d_sc, n, j.d_part, j.d_out, &j.launches, s.stream[0]);
@@ -744,8 +751,55 @@ cudaError_t msm_wait(GpuSlot& s, float* ms) {
 
 // With several GPUs in the context the terms are sharded by contiguous index range like every other call of the
 // library; the per-GPU partial sums (one point each) are added by one more tiny MSM with unit scalars on GPU 0.
+struct ptau_kzg_powers {
+  ptau_ctx* ctx = nullptr;
+  size_t n = 0;
+  void* d_pts[kMaxGpus] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+};
+
+static int kzg_commit_impl(ptau_ctx* ctx, const void* powers, const ptau_kzg_powers* res, const void* coeffs, size_t n,
+                           void* commitment);
+
 int ptau_kzg_commit(ptau_ctx* ctx, const void* powers, const void* coeffs, size_t n, void* commitment) {
   if (!ctx || (!powers && n) || (!coeffs && n) || !commitment) return PTAU_ERR_ARG;
+  return kzg_commit_impl(ctx, powers, nullptr, coeffs, n, commitment);
+}
+
+// The powers of a setup are the same for every commitment: keep a copy on every GPU of the context and send only the
+// scalars per call.
+int ptau_kzg_powers_upload(ptau_ctx* ctx, const void* powers, size_t n, ptau_kzg_powers** out) {
+  if (!ctx || !out || (!powers && n)) return PTAU_ERR_ARG;
+  ptau_kzg_powers* p = new ptau_kzg_powers;
+  p->ctx = ctx;
+  p->n = n;
+  for (int g = 0; g < ctx->n_gpus; g++) {
+    cudaError_t e = cudaSetDevice(ctx->gpu[g].device);
+    if (e == cudaSuccess) e = cudaMalloc(&p->d_pts[g], n * 104 + 16);
+    if (e == cudaSuccess && n) e = cudaMemcpy(p->d_pts[g], powers, n * 104, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+      ctx->last_error = std::string("kzg_powers_upload: ") + cudaGetErrorString(e);
+      ptau_kzg_powers_free(p);
+      return PTAU_ERR_CUDA;
+    }
+  }
+  *out = p;
+  return PTAU_OK;
+}
+
+void ptau_kzg_powers_free(ptau_kzg_powers* p) {
+  if (!p) return;
+  for (int g = 0; g < kMaxGpus; g++)
+    if (p->d_pts[g]) cudaFree(p->d_pts[g]);
+  delete p;
+}
+
+int ptau_kzg_commit_resident(ptau_ctx* ctx, const ptau_kzg_powers* powers, const void* coeffs, size_t n, void* commitment) {
+  if (!ctx || !powers || powers->ctx != ctx || n > powers->n || (!coeffs && n) || !commitment) return PTAU_ERR_ARG;
+  return kzg_commit_impl(ctx, nullptr, powers, coeffs, n, commitment);
+}
+
+static int kzg_commit_impl(ptau_ctx* ctx, const void* powers, const ptau_kzg_powers* res, const void* coeffs, size_t n,
+                           void* commitment) {
   // scalars must be canonical (< r), like ark's Fr
   for (size_t i = 0; i < n; i++) {
     Fr c = fr_from_le32((const uint8_t*)coeffs + i * 32);
@@ -762,8 +816,11 @@ int ptau_kzg_commit(ptau_ctx* ctx, const void* powers, const void* coeffs, size_
   cudaError_t e = cudaSuccess;
   for (int g = 0; g < G && e == cudaSuccess; g++) {
     const size_t lo = n * g / G, hi = n * (g + 1) / G;
-    e = msm_issue(ctx->gpu[g], jobs[g], (const uint8_t*)powers + lo * 104, (const uint8_t*)coeffs + lo * 32, hi - lo);
-    ctx->timing.h2d_bytes[g] = (hi - lo) * 136;
+    if (res)
+      e = msm_issue(ctx->gpu[g], jobs[g], (const uint8_t*)res->d_pts[g] + lo * 104, (const uint8_t*)coeffs + lo * 32, hi - lo, true);
+    else
+      e = msm_issue(ctx->gpu[g], jobs[g], (const uint8_t*)powers + lo * 104, (const uint8_t*)coeffs + lo * 32, hi - lo);
+    ctx->timing.h2d_bytes[g] = (hi - lo) * (res ? 32 : 136);
     ctx->timing.d2h_bytes[g] = 104;
   }
   for (int g = 0; g < G && e == cudaSuccess; g++) {

@@ -51,6 +51,9 @@ extern "C" {
         bad_kind: *mut c_int,
     ) -> c_int;
     pub fn ptau_kzg_commit(ctx: *mut ptau_ctx, powers: *const c_void, coeffs: *const c_void, n: usize, commitment: *mut c_void) -> c_int;
+    pub fn ptau_kzg_powers_upload(ctx: *mut ptau_ctx, powers: *const c_void, n: usize, out: *mut *mut c_void) -> c_int;
+    pub fn ptau_kzg_powers_free(powers: *mut c_void);
+    pub fn ptau_kzg_commit_resident(ctx: *mut ptau_ctx, powers: *const c_void, coeffs: *const c_void, n: usize, commitment: *mut c_void) -> c_int;
     pub fn ptau_kzg_quotient(coeffs: *const c_void, n: usize, point: *const c_void, quotient_out: *mut c_void, value_out: *mut c_void) -> c_int;
     pub fn ptau_kzg_check(
         ctx: *mut ptau_ctx, vk_g1: *const c_void, vk_g2: *const c_void, comms: *const c_void, points: *const c_void,

@@ -557,6 +557,21 @@ def test_kzg10_commit_open_known_tau(ctx, tmp_path):
             _, bw = kz.KZG10._quotient(b, z)
             assert proof.tobytes() == rec(ev(w, tau) + alpha * ev(bw, tau))
             assert (ev(p, tau) - value) % R == (tau - z) * ev(w, tau) % R
+    # device-resident powers (uploaded once; only scalars travel): same commitments and proofs
+    dev = powers.to_device(ctx)
+    assert len(dev.powers_of_g) == 2 * n - 1 and len(dev.powers_of_gamma_g) == n
+    for _ in range(3):
+        p = [rnd.randrange(R) for _ in range(rnd.randrange(2, 2 * n - 1))]
+        b = [rnd.randrange(R) for _ in range(2)]
+        assert kz.KZG10.commit(dev, p, blinding=b, ctx=ctx).tobytes() == kz.KZG10.commit(powers, p, blinding=b, ctx=ctx).tobytes()
+        assert kz.KZG10.commit(dev, p, ctx=ctx).tobytes() == rec(ev(p, tau))
+        z = rnd.randrange(R)
+        v1, w1, r1 = kz.KZG10.open(dev, p, z, blinding=b, ctx=ctx)
+        v2, w2, r2 = kz.KZG10.open(powers, p, z, blinding=b, ctx=ctx)
+        assert (v1, r1) == (v2, r2) and w1.tobytes() == w2.tobytes()
+    assert kz.KZG10.commit(dev, [], ctx=ctx).tobytes() == o.g1_mont_record(0, 1, True)
+    with pytest.raises(kz.PtauError):
+        kz.KZG10.commit(dev, [1] * (2 * n), ctx=ctx)
     # special cases of the group law inside the MSM
     assert kz.KZG10.commit(powers, [0, 0, 0], ctx=ctx).tobytes() == o.g1_mont_record(0, 1, True)  # zero polynomial
     assert kz.KZG10.commit(powers, [], ctx=ctx).tobytes() == o.g1_mont_record(0, 1, True)
