@@ -371,6 +371,8 @@ class KZG10:
 
     @staticmethod
     def _scalars(vals) -> np.ndarray:
+        if isinstance(vals, np.ndarray) and vals.dtype == np.uint8 and vals.ndim == 2 and vals.shape[1] == 32:
+            return np.ascontiguousarray(vals).reshape(-1)  # already 32-byte LE scalars (must be < r)
         b = b"".join((int(v) % R_ORDER).to_bytes(32, "little") for v in vals)
         return np.frombuffer(b, dtype=np.uint8) if b else np.zeros(0, dtype=np.uint8)
 

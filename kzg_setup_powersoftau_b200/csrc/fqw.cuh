@@ -1,0 +1,247 @@
+// Unreduced ("wide") products in Fq and the Montgomery reduction of a 24-limb value, in the same
+// even/odd IMAD.WIDE scheme as fq.cuh -- the building blocks of lazy reduction in Fq2:
+//
+//   fq2_mul:  3 wide products (Karatsuba) + 2 reductions   = 3*144 + 2*156 = 744 MADs (fq.cuh: 3*300 = 900)
+//   fq2_sqr:  3 wide squarings            + 2 reductions   = 3*78  + 2*156 = 546 MADs (fq.cuh: 2*300 = 600)
+//
+// ark-ff 0.2 / pairing 0.14.2 reduce after every Fq multiplication; the values produced here are
+// the same field elements (the reduction is linear), checked limb for limb against the oracle in
+// tests/test_host_logic.py (host build of this file) and on the GPU through ptau_selftest_fq_op.
+//
+// A wide value T is 24 x u32 limbs, T < p * 2^384 whenever it is handed to fq_redc.
+#pragma once
+#include "fq.cuh"
+
+namespace ptau {
+
+// a + b without the conditional subtraction (result < 2p < 2^382 for reduced inputs)
+PTAU_HD Fq fq_add_nored(const Fq& a, const Fq& b) {
+  Fq r;
+  PX_DECL;
+  PX_ADD_CC(r.l[0], a.l[0], b.l[0]);
+#pragma unroll
+  for (int i = 1; i < 11; i++) PX_ADDC_CC(r.l[i], a.l[i], b.l[i]);
+  PX_ADDC(r.l[11], a.l[11], b.l[11]);
+  return r;
+}
+
+// ---- single-instruction steps used below (fq.cuh has the others) --------------------------------
+#ifdef __CUDA_ARCH__
+#define PX_SUB_CC(r, a, b) asm volatile("sub.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b))
+#define PX_SUBC_CC(r, a, b) asm volatile("subc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b))
+#define PX_SUBC(r, a, b) asm volatile("subc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b))
+#else
+#define PX_SUB_CC(r, a, b) do { px_cf = 0; r = emu::subc(a, b, px_cf); } while (0)
+#define PX_SUBC_CC(r, a, b) r = emu::subc(a, b, px_cf)
+#define PX_SUBC(r, a, b) do { r = emu::subc(a, b, px_cf); px_cf = 0; } while (0)
+#endif
+
+// t[0..23] = a * b.  Same rows as fq_mul_inl without the reduction rows: after row i the lowest limb of the
+// even-aligned accumulator is limb i of the product.
+PTAU_HD void fq_mul_wide(uint32_t* t, const Fq& a, const Fq& b) {
+  uint32_t ev[12], od[12];
+#pragma unroll
+  for (int j = 0; j < 12; j += 2) {
+    uint64_t t0 = (uint64_t)a.l[j] * b.l[0];
+    uint64_t t1 = (uint64_t)a.l[j + 1] * b.l[0];
+    ev[j] = (uint32_t)t0;
+    ev[j + 1] = (uint32_t)(t0 >> 32);
+    od[j] = (uint32_t)t1;
+    od[j + 1] = (uint32_t)(t1 >> 32);
+  }
+  t[0] = ev[0];
+#pragma unroll
+  for (int i = 1; i < 12; i++) {
+    uint32_t* E = (i & 1) ? od : ev;  // even-aligned accumulator of this row
+    uint32_t* X = (i & 1) ? ev : od;  // previous even accumulator: its limb 0 is already in t[i-1]
+    row_mac_odd_shift(X, E[0], a.l, b.l[i]);
+    row_mac_even(E, X[11], a.l, b.l[i]);
+    t[i] = E[0];
+  }
+  // last row had E = od, X = ev: high half = ev + (od >> 32)
+  {
+    PX_DECL;
+    PX_ADD_CC(t[12], ev[0], od[1]);
+#pragma unroll
+    for (int k = 1; k < 11; k++) PX_ADDC_CC(t[12 + k], ev[k], od[k + 1]);
+    PX_ADDC(t[23], ev[11], 0u);
+  }
+}
+
+// t[0..23] = a * a, a < 2^383 (so that the doubled multiplicand fits 384 bits): the rows of fq_sqr_inl
+// (78 product MADs) without the reduction rows.
+PTAU_HD void fq_sqr_wide(uint32_t* t, const Fq& a) {
+  uint32_t ev[12], od[12];
+  uint32_t c2[12], d1[12];
+  c2[0] = a.l[0];
+  d1[0] = a.l[0];
+#pragma unroll
+  for (int j = 1; j < 12; j++) {
+    d1[j] = a.l[j] << 1;
+    c2[j] = (a.l[j] << 1) | (a.l[j - 1] >> 31);
+  }
+#define SQ_M(i, j) ((j) == (i) ? a.l[j] : ((j) == (i) + 1 ? d1[j] : c2[j]))
+#pragma unroll
+  for (int j = 0; j < 12; j += 2) {
+    uint64_t t0 = (uint64_t)SQ_M(0, j) * a.l[0];
+    uint64_t t1 = (uint64_t)SQ_M(0, j + 1) * a.l[0];
+    ev[j] = (uint32_t)t0;
+    ev[j + 1] = (uint32_t)(t0 >> 32);
+    od[j] = (uint32_t)t1;
+    od[j + 1] = (uint32_t)(t1 >> 32);
+  }
+  t[0] = ev[0];
+#pragma unroll
+  for (int i = 1; i < 12; i++) {
+    uint32_t* E = (i & 1) ? od : ev;
+    uint32_t* X = (i & 1) ? ev : od;
+    const uint32_t bi = a.l[i];
+    PX_DECL;
+    PX_ADD_CC(E[0], E[0], X[1]);
+#pragma unroll
+    for (int k = 0; k < 10; k += 2) {
+      if (k + 1 >= i) {
+        PX_MADC_LO_CC(X[k], SQ_M(i, k + 1), bi, X[k + 2]);
+        PX_MADC_HI_CC(X[k + 1], SQ_M(i, k + 1), bi, X[k + 3]);
+      } else {
+        PX_ADDC_CC(X[k], X[k + 2], 0u);
+        PX_ADDC_CC(X[k + 1], X[k + 3], 0u);
+      }
+    }
+    PX_MADC_LO_CC(X[10], SQ_M(i, 11), bi, 0u);
+    PX_MADC_HI_CC(X[11], SQ_M(i, 11), bi, 0u);
+    const int j0 = (i & 1) ? i + 1 : i;
+    if (j0 <= 10) {
+      PX_MAD_LO_CC(E[j0], SQ_M(i, j0), bi, E[j0]);
+      PX_MADC_HI_CC(E[j0 + 1], SQ_M(i, j0), bi, E[j0 + 1]);
+#pragma unroll
+      for (int j = j0 + 2; j < 12; j += 2) {
+        PX_MADC_LO_CC(E[j], SQ_M(i, j), bi, E[j]);
+        PX_MADC_HI_CC(E[j + 1], SQ_M(i, j), bi, E[j + 1]);
+      }
+      PX_ADDC(X[11], X[11], 0u);
+    }
+    t[i] = E[0];
+  }
+#undef SQ_M
+  {
+    PX_DECL;
+    PX_ADD_CC(t[12], ev[0], od[1]);
+#pragma unroll
+    for (int k = 1; k < 11; k++) PX_ADDC_CC(t[12 + k], ev[k], od[k + 1]);
+    PX_ADDC(t[23], ev[11], 0u);
+  }
+}
+
+// a += b, a -= b over 24 limbs (callers guarantee no carry / borrow out, except fqw_sub_fix)
+PTAU_HD void fqw_add(uint32_t* a, const uint32_t* b) {
+  PX_DECL;
+  PX_ADD_CC(a[0], a[0], b[0]);
+#pragma unroll
+  for (int i = 1; i < 23; i++) PX_ADDC_CC(a[i], a[i], b[i]);
+  PX_ADDC(a[23], a[23], b[23]);
+}
+PTAU_HD void fqw_sub(uint32_t* a, const uint32_t* b) {
+  PX_DECL;
+  PX_SUB_CC(a[0], a[0], b[0]);
+#pragma unroll
+  for (int i = 1; i < 23; i++) PX_SUBC_CC(a[i], a[i], b[i]);
+  PX_SUBC(a[23], a[23], b[23]);
+}
+// a = a - b + (a < b ? p * 2^384 : 0): the difference of two products, made non-negative (< p * 2^384)
+PTAU_HD void fqw_sub_fix(uint32_t* a, const uint32_t* b) {
+  const uint32_t pl[12] = PTAU_P_LIMBS;
+  uint32_t mask;
+  {
+    PX_DECL;
+    PX_SUB_CC(a[0], a[0], b[0]);
+#pragma unroll
+    for (int i = 1; i < 24; i++) PX_SUBC_CC(a[i], a[i], b[i]);
+    PX_SUBC(mask, 0u, 0u);  // 0xffffffff on borrow
+  }
+  {
+    PX_DECL;
+    PX_ADD_CC(a[12], a[12], pl[0] & mask);
+#pragma unroll
+    for (int i = 1; i < 11; i++) PX_ADDC_CC(a[12 + i], a[12 + i], pl[i] & mask);
+    PX_ADDC(a[23], a[23], pl[11] & mask);
+  }
+}
+
+// One reduction row with the window shift fused in.  On entry X is the previous even-aligned accumulator whose limb 0
+// has just been zeroed (limb 1 is the left-over at the new position 0); E0 is limb 0 of the new even-aligned
+// accumulator.  E0 += left-over; m = E0 * (-p^-1); X = (X >> 64) + m * (odd limbs of p), carry chained from E0.
+PTAU_HD void row_red_odd_shift(uint32_t* X, uint32_t& E0, uint32_t& m) {
+#ifdef __CUDA_ARCH__
+  asm("add.cc.u32 %12, %12, %1;\n\t"
+      "mul.lo.u32 %13, %12, 0xfffcfffd;\n\t"
+      "madc.lo.cc.u32 %0, %13, " P1S ", %2;\n\t"
+      "madc.hi.cc.u32 %1, %13, " P1S ", %3;\n\t"
+      "madc.lo.cc.u32 %2, %13, " P3S ", %4;\n\t"
+      "madc.hi.cc.u32 %3, %13, " P3S ", %5;\n\t"
+      "madc.lo.cc.u32 %4, %13, " P5S ", %6;\n\t"
+      "madc.hi.cc.u32 %5, %13, " P5S ", %7;\n\t"
+      "madc.lo.cc.u32 %6, %13, " P7S ", %8;\n\t"
+      "madc.hi.cc.u32 %7, %13, " P7S ", %9;\n\t"
+      "madc.lo.cc.u32 %8, %13, " P9S ", %10;\n\t"
+      "madc.hi.cc.u32 %9, %13, " P9S ", %11;\n\t"
+      "madc.lo.cc.u32 %10, %13, " P11S ", 0;\n\t"
+      "madc.hi.cc.u32 %11, %13, " P11S ", 0;"
+      : "+r"(X[0]), "+r"(X[1]), "+r"(X[2]), "+r"(X[3]), "+r"(X[4]), "+r"(X[5]), "+r"(X[6]), "+r"(X[7]),
+        "+r"(X[8]), "+r"(X[9]), "+r"(X[10]), "+r"(X[11]), "+r"(E0), "=&r"(m));
+#else
+  uint32_t cf = 0;
+  E0 = emu::addc(E0, X[1], cf);
+  m = E0 * PTAU_M0;
+  for (int j = 0; j < 10; j += 2) {
+    X[j] = emu::madlo(m, emu::PL[j + 1], X[j + 2], cf);
+    X[j + 1] = emu::madhi(m, emu::PL[j + 1], X[j + 3], cf);
+  }
+  X[10] = emu::madlo(m, emu::PL[11], 0, cf);
+  X[11] = emu::madhi(m, emu::PL[11], 0, cf);
+#endif
+}
+
+// Montgomery reduction: T / 2^384 mod p for T = t[0..23] < p * 2^384; result < p.
+// Window of 12 (+1) limbs sliding up one limb per row; limb 12+i-1... of T enters at the top of the window in row i.
+PTAU_HD Fq fq_redc(const uint32_t* t) {
+  uint32_t ev[12], od[12];
+#pragma unroll
+  for (int j = 0; j < 12; j++) {
+    ev[j] = t[j];
+    od[j] = 0;
+  }
+  {
+    uint32_t m = ev[0] * PTAU_M0;
+    row_red_odd(od, m);
+    row_red_even(ev, od[11], m);
+  }
+#pragma unroll
+  for (int i = 1; i < 12; i++) {
+    uint32_t* E = (i & 1) ? od : ev;
+    uint32_t* X = (i & 1) ? ev : od;
+    uint32_t m;
+    row_red_odd_shift(X, E[0], m);
+    {  // limb 11+i of T enters at window position 11 (= X[10]); by the bound T + sum m p W^i < 2 p W^12 nothing leaves X[11]
+      PX_DECL;
+      PX_ADD_CC(X[10], X[10], t[11 + i]);
+      PX_ADDC(X[11], X[11], 0u);
+    }
+    row_red_even(E, X[11], m);
+  }
+  // last row had E = od, X = ev: result = ev + (od >> 32) + t[23] * W^11
+  {
+    PX_DECL;
+    PX_ADD_CC(ev[0], ev[0], od[1]);
+#pragma unroll
+    for (int k = 1; k < 11; k++) PX_ADDC_CC(ev[k], ev[k], od[k + 1]);
+    PX_ADDC(ev[11], ev[11], t[23]);
+  }
+  fq_cond_sub_p(ev);
+  Fq r;
+#pragma unroll
+  for (int i = 0; i < 12; i++) r.l[i] = ev[i];
+  return r;
+}
+
+}  // namespace ptau

@@ -63,6 +63,51 @@ extern "C" void hostemul_fq_op(int op, const uint32_t* a, const uint32_t* b, uin
   std::memcpy(out, r.l, 48);
 }
 
+// wide (lazy-reduction) building blocks of csrc/fqw.cuh and the Fq2 operations built from them.
+//   op 0: t[24] = a * b            (a, b: 12 limbs, any value < 2^384 whose product rows fit, i.e. < 2p)
+//   op 1: t[24] = a * a            (a < 2^383)
+//   op 2: out[12] = redc(t[24])    (t < p 2^384; passed in `a` as 24 limbs)
+//   op 3: out[24] = fq2_mul(a, b)  (a, b: c0 | c1, 24 limbs, reduced)
+//   op 4: out[24] = fq2_sqr(a)
+//   op 5: out[24] = a - b + (a < b ? p 2^384 : 0) over 24 limbs (fqw_sub_fix)
+extern "C" void hostemul_fqw_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
+  Fq x, y;
+  Fq2 u, v, w;
+  switch (op) {
+    case 0:
+      std::memcpy(x.l, a, 48);
+      std::memcpy(y.l, b, 48);
+      fq_mul_wide(out, x, y);
+      break;
+    case 1:
+      std::memcpy(x.l, a, 48);
+      fq_sqr_wide(out, x);
+      break;
+    case 2:
+      x = fq_redc(a);
+      std::memcpy(out, x.l, 48);
+      break;
+    case 3:
+      std::memcpy(&u, a, 96);
+      std::memcpy(&v, b, 96);
+      w = fq2_mul(u, v);
+      std::memcpy(out, &w, 96);
+      break;
+    case 4:
+      std::memcpy(&u, a, 96);
+      w = fq2_sqr(u);
+      std::memcpy(out, &w, 96);
+      break;
+    case 5: {
+      uint32_t t[24];
+      std::memcpy(t, a, 96);
+      fqw_sub_fix(t, b);
+      std::memcpy(out, t, 96);
+      break;
+    }
+  }
+}
+
 // the product's pairing code (csrc/pairing.cuh) on the host: same limb arithmetic, same formulas
 extern "C" void hostemul_pairing_product2(const uint8_t* g1, const uint8_t* g2, size_t n, uint8_t* gt_out, uint8_t* is_one) {
   for (size_t i = 0; i < n; i++) {

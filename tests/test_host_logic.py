@@ -86,6 +86,68 @@ def test_limb_field_ops_carry_stress(hostemul):
         assert op(2, a, b) == (a - b) % P
 
 
+def test_limb_wide_products_and_lazy_fq2(hostemul):
+    """csrc/fqw.cuh on the host: unreduced products (operands up to 2p, as the Karatsuba sums are), the
+    Montgomery reduction of a 24-limb value (every T < p 2^384, incl. the extremes), the sign fix of a difference of
+    products, and fq2_mul / fq2_sqr built from them, against big-int arithmetic."""
+    P = o.P
+    R = 1 << 384
+    rinv = pow(R, -1, P)
+
+    def limbs(v, n=12):
+        return (ctypes.c_uint32 * n)(*[(v >> (32 * i)) & 0xFFFFFFFF for i in range(n)])
+
+    def op(k, a, b, na, nb, nout):
+        out = (ctypes.c_uint32 * nout)()
+        hostemul.hostemul_fqw_op(k, limbs(a, na), limbs(b, nb), out)
+        return sum(int(out[i]) << (32 * i) for i in range(nout))
+
+    rnd = random.Random(2024)
+    pats = [0, 1, 0x7FFFFFFF, 0x80000000, 0xFFFFFFFE, 0xFFFFFFFF, 0xFFFF0000, 0x0000FFFF]
+
+    def patterned(bound):
+        v = 0
+        for i in range(12):
+            v |= rnd.choice(pats) << (32 * i)
+        return v % bound
+
+    ops = [0, 1, 2, P - 1, P, P + 1, 2 * P - 2, 2 * P - 1, (1 << 381) - 1, (1 << 382) - 1]
+    ops += [patterned(2 * P) for _ in range(150)] + [rnd.randrange(2 * P) for _ in range(300)]
+    for i, a in enumerate(ops):
+        b = ops[(5 * i + 1) % len(ops)]
+        assert op(0, a, b, 12, 12, 24) == a * b
+        assert op(1, a, 0, 12, 12, 24) == a * a
+    # reduction: extremes of the admissible range and random values
+    ts = [0, 1, R - 1, R, P * R - 1, P * R - P, (P - 1) * (P - 1), 4 * P * P - 1 if 4 * P * P < P * R else P * R - 2]
+    ts += [rnd.randrange(P * R) for _ in range(400)]
+    for k in range(24):
+        ts += [(0xFFFFFFFF << (32 * k)) % (P * R), ((1 << (32 * k)) - 1) % (P * R)]
+    for t in ts:
+        assert op(2, t, 0, 24, 12, 12) == t * rinv % P, hex(t)
+    # a - b (+ p R when negative) over products
+    for _ in range(200):
+        a, b = rnd.randrange(P) * rnd.randrange(P), rnd.randrange(P) * rnd.randrange(P)
+        want = a - b if a >= b else a - b + P * R
+        assert op(5, a, b, 24, 24, 24) == want
+    assert op(5, 0, (P - 1) ** 2, 24, 24, 24) == P * R - (P - 1) ** 2
+    # Fq2: values in Montgomery form, c0 | c1
+    def f2(v):
+        return v[0] | (v[1] << 384)
+
+    def unf2(x):
+        return (x & ((1 << 384) - 1), x >> 384)
+
+    edge = [0, 1, P - 1, P - 2, (P - 1) // 2, (P + 1) // 2, R % P, (1 << 380)]
+    vals = [(a, b) for a in edge for b in edge] + [(rnd.randrange(P), rnd.randrange(P)) for _ in range(400)]
+    vals += [(patterned(P), patterned(P)) for _ in range(200)]
+    for i, a in enumerate(vals):
+        b = vals[(3 * i + 7) % len(vals)]
+        got = unf2(op(3, f2(a), f2(b), 24, 24, 24))
+        assert got == ((a[0] * b[0] - a[1] * b[1]) * rinv % P, (a[0] * b[1] + a[1] * b[0]) * rinv % P)
+        got = unf2(op(4, f2(a), 0, 24, 24, 24))
+        assert got == ((a[0] * a[0] - a[1] * a[1]) * rinv % P, 2 * a[0] * a[1] * rinv % P)
+
+
 def test_limb_code_on_golden_files(hostemul):
     n = 8
     body = golden("n8_powersoftau.bin")[64:]
@@ -487,7 +549,7 @@ def test_bench_reference_arm_contract():
         assert d["unit"] == "points/s" and d["higher_is_better"] is True and d["value"] > 0
         assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
         assert d["e2e"] == {"value": d["value"], "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-        assert "workload" in d["config"] and d["metric"].startswith("G1 points/sec")
+        assert "workload" in d["config"] and d["metric"].startswith("G1+G2 points/sec") and d["scaling"] == "strong" and "configs[2]" in d["config"]["workload"]
 
 
 def _pairing_vectors():
