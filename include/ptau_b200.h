@@ -192,6 +192,7 @@ int ptau_load_phase1(ptau_ctx* ctx, const void* data, uint64_t len, uint64_t m, 
 /* ---- file to file (the two binaries' main()) --------------------------------- */
 #define PTAU_FILE_SKIP_DIGEST 1u     /* do not check the BLAKE2b digest of `powersoftau`           */
 #define PTAU_FILE_NO_UNCOMPRESSED 2u /* fused path: do not write `powersoftau_uncompressed`        */
+#define PTAU_FILE_FSYNC 4u           /* fsync the outputs before they are published                */
 /* Streams `response_path` through pinned slabs (memory O(slab), not O(N)): size check
  * (preprocess-kgz.rs:83), BLAKE2b-512 digest check against expected_digest_hex (NULL = the
  * ceremony digest of preprocess-kgz.rs:19), `uncompressed_path` created with create_new

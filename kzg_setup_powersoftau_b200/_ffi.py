@@ -24,7 +24,7 @@ CHECKS_STRICT = CHECK_ON_CURVE | CHECK_SUBGROUP | CHECK_REJECT_INFINITY
 OK = 0
 BAD_NON_CANONICAL, BAD_FLAGS, BAD_INFINITY, BAD_NOT_ON_CURVE, BAD_NOT_IN_SUBGROUP = 1, 2, 3, 4, 5
 ERR_CUDA, ERR_ARG, ERR_SIZE, ERR_NOMEM, ERR_IO, ERR_DIGEST, ERR_EXISTS = -1, -2, -3, -4, -5, -6, -7
-FILE_SKIP_DIGEST, FILE_NO_UNCOMPRESSED = 1, 2
+FILE_SKIP_DIGEST, FILE_NO_UNCOMPRESSED, FILE_FSYNC = 1, 2, 4
 VARIANT_KGZ, VARIANT_FASTKGZ = 1, 2
 STATUS_NONE = 0xFFFFFFFFFFFFFFFF
 

@@ -19,7 +19,7 @@
 static void usage(const char* argv0) {
   fprintf(stderr,
           "usage: %s [--dir D] [--log2-powers K] [--skip-digest | --expect-digest HEX] [--no-uncompressed]\n"
-          "          [--gpus N] [--checks strict|reference]\n",
+          "          [--gpus N] [--checks strict|reference] [--fsync]\n",
           argv0);
 }
 
@@ -35,6 +35,7 @@ int main(int argc, char** argv) {
     else if (a == "--skip-digest") flags |= PTAU_FILE_SKIP_DIGEST;
     else if (a == "--expect-digest" && i + 1 < argc) digest = argv[++i];
     else if (a == "--no-uncompressed") flags |= PTAU_FILE_NO_UNCOMPRESSED;
+    else if (a == "--fsync") flags |= PTAU_FILE_FSYNC;
     else if (a == "--gpus" && i + 1 < argc) gpus = atoi(argv[++i]);
     else if (a == "--checks" && i + 1 < argc) {
       std::string c = argv[++i];

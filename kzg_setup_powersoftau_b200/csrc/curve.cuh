@@ -201,18 +201,74 @@ PTAU_HD_NOINLINE bool g1_in_subgroup(const Fq& x, const Fq& y) {
   return jac_eq_affine(q2, fq_mul(x, k_beta_mont()), fq_neg(y));
 }
 
-// psi(P) == [z]P   <=>   [|z|]P == -psi(P) = (psi_x, -psi_y)
-PTAU_HD_NOINLINE bool g2_in_subgroup(const Fq2& x, const Fq2& y) {
-  Jac<Fq2> q = mul_zabs_affine(x, y, fq2_one());
+// Operand file of the G2 ladder: the base point (x, y) is needed only at the five additions and in the final
+// comparison, so it is parked outside the register file and the 63 doublings run with the accumulator and the
+// temporaries of the field operations only.  On the device the file is shared memory, transposed (word j of a
+// thread at byte address base + j * 4 * STRIDE, STRIDE = block size: conflict-free) and addressed in the shared
+// window directly (ld.shared / st.shared); on the host it is a plain array.
+// Layout: x.c0 | x.c1 | y.c0 | y.c1, 12 words each.
+template <int STRIDE>
+struct Park {
+#ifdef __CUDA_ARCH__
+  uint32_t base;  // shared-window byte address of this thread's word 0
+  __device__ __forceinline__ uint32_t ld(int j) const {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(base + (uint32_t)(j * 4 * STRIDE)) : "memory");
+    return v;
+  }
+  __device__ __forceinline__ void st(int j, uint32_t v) const {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(base + (uint32_t)(j * 4 * STRIDE)), "r"(v) : "memory");
+  }
+#else
+  uint32_t* p;
+  uint32_t ld(int j) const { return p[j * STRIDE]; }
+  void st(int j, uint32_t v) const { p[j * STRIDE] = v; }
+#endif
+  PTAU_HD void store_fq(int at, const Fq& a) const {
+#pragma unroll
+    for (int j = 0; j < 12; j++) st(at + j, a.l[j]);
+  }
+  PTAU_HD Fq load_fq(int at) const {
+    Fq r;
+#pragma unroll
+    for (int j = 0; j < 12; j++) r.l[j] = ld(at + j);
+    return r;
+  }
+  PTAU_HD Fq2 load_fq2(int at) const {
+    Fq2 r;
+    r.c0 = load_fq(at);
+    r.c1 = load_fq(at + 12);
+    return r;
+  }
+  PTAU_HD void store_g2(const Fq2& x, const Fq2& y) const {
+    store_fq(0, x.c0);
+    store_fq(12, x.c1);
+    store_fq(24, y.c0);
+    store_fq(36, y.c1);
+  }
+};
+
+// psi(P) == [z]P   <=>   [|z|]P == -psi(P) = (psi_x, -psi_y); P = (x, y) parked in `pk`
+template <int STRIDE>
+PTAU_HD_NOINLINE bool g2_in_subgroup(Park<STRIDE> pk) {
+  Jac<Fq2> q;
+  q.X = pk.load_fq2(0);
+  q.Y = pk.load_fq2(24);
+  q.Z = fq2_one();
+#pragma unroll 1
+  for (int i = 62; i >= 0; --i) {
+    jac_dbl_ladder(q);
+    if ((PTAU_Z_ABS >> i) & 1ull) jac_madd(q, pk.load_fq2(0), pk.load_fq2(24));
+  }
   // psi_x = conj(x) * (0, cx1) = (x1*cx1, x0*cx1)
   Fq cx1 = k_psi_cx1_mont();
   Fq2 px;
-  px.c0 = fq_mul(x.c1, cx1);
-  px.c1 = fq_mul(x.c0, cx1);
+  px.c0 = fq_mul(pk.load_fq(12), cx1);
+  px.c1 = fq_mul(pk.load_fq(0), cx1);
   Fq2 cy;
   cy.c0 = k_psi_cy0_mont();
   cy.c1 = k_psi_cy1_mont();
-  Fq2 py = fq2_mul(fq2_conj(y), cy);
+  Fq2 py = fq2_mul(fq2_conj(pk.load_fq2(24)), cy);
   return jac_eq_affine(q, px, fq2_neg(py));
 }
 

@@ -10,10 +10,12 @@
 #include <errno.h>
 #include <fcntl.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <chrono>
 #include <future>
 #include <string>
 #include <vector>
@@ -56,6 +58,21 @@ bool pwrite_all(int fd, const void* buf, size_t len, uint64_t off) {
   return true;
 }
 
+// PTAU_TRACE=1: wall-clock marks of the file pipelines on stderr
+struct Trace {
+  bool on;
+  std::chrono::steady_clock::time_point t0, last;
+  Trace() : on(getenv("PTAU_TRACE") != nullptr), t0(std::chrono::steady_clock::now()), last(t0) {}
+  void mark(const char* what) {
+    if (!on) return;
+    auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[ptau trace] %-24s +%.1f ms (total %.1f ms)\n", what,
+            std::chrono::duration<double, std::milli>(now - last).count(),
+            std::chrono::duration<double, std::milli>(now - t0).count());
+    last = now;
+  }
+};
+
 struct Pinned {
   void* p = nullptr;
   explicit Pinned(size_t n) { p = ptau_host_alloc(n); }
@@ -88,6 +105,17 @@ int ptau_blake2b_file(const char* path, char out_hex[129]) {
   return PTAU_OK;
 }
 
+// Outputs are written under temporary names next to their final paths and published only when the whole job
+// succeeded (`kzg_setup`: rename(), replacing an older file atomically; `powersoftau_uncompressed`: link(), which
+// keeps the reference's create_new semantics); on any error they are unlinked.  The reference validates everything
+// in RAM before it creates `kzg_setup` (preprocess-kgz.rs:128-160 then :186), so a bad input never leaves a partial
+// or truncated file behind there either.
+//
+// Error precedence = the reference's order of events: BLAKE2b digest (preprocess-kgz.rs:33-47), then any decode error
+// of the decompression pass over ALL sections (:105-110), then create_new of the intermediate file (:113-118), then
+// the first bad point of the read_g1 / read_g2 loops (:140-153).  The slabs still make one pass: a stage-2 error is
+// remembered while the remaining slabs are only decompressed, and the digest is computed by a thread of its own
+// while the GPUs work.
 int ptau_preprocess_files(ptau_ctx* ctx, int variant, const char* response_path, const char* setup_path,
                           const char* uncompressed_path, unsigned log2_powers, const char* expected_digest_hex,
                           unsigned flags, unsigned checks, uint64_t* bad_index, int* bad_kind, int* bad_section) {
@@ -96,6 +124,7 @@ int ptau_preprocess_files(ptau_ctx* ctx, int variant, const char* response_path,
   const uint64_t n = 1ull << log2_powers;
   const bool fast = variant == PTAU_VARIANT_FASTKGZ;
   const bool emit_unc = uncompressed_path && !(flags & PTAU_FILE_NO_UNCOMPRESSED);
+  Trace trace;
 
   int fd_in = open(response_path, O_RDONLY);
   if (fd_in < 0) return PTAU_ERR_IO;
@@ -109,35 +138,38 @@ int ptau_preprocess_files(ptau_ctx* ctx, int variant, const char* response_path,
     close(fd_in);
     return PTAU_ERR_SIZE;
   }
-  // download_parameters (preprocess-kgz.rs:38-47): digest of the existing file.  A
-  // mismatch sends the reference to the network; offline that is an error.
-  if (!(flags & PTAU_FILE_SKIP_DIGEST)) {
-    char hex[129];
-    int rc = ptau_blake2b_file(response_path, hex);
-    if (rc) {
-      close(fd_in);
-      return rc;
-    }
-    if (strcmp(hex, expected_digest_hex ? expected_digest_hex : kPowersoftauDigest) != 0) {
-      close(fd_in);
-      return PTAU_ERR_DIGEST;
-    }
-  }
-  int fd_unc = -1;
-  if (emit_unc) {
-    // create_new(true): an existing file is an error (preprocess-kgz.rs:113-118)
-    fd_unc = open(uncompressed_path, O_WRONLY | O_CREAT | O_EXCL, 0644);
-    if (fd_unc < 0) {
-      close(fd_in);
-      return errno == EEXIST ? PTAU_ERR_EXISTS : PTAU_ERR_IO;
-    }
-  }
-  int fd_out = open(setup_path, O_WRONLY | O_CREAT | O_TRUNC, 0644);
-  if (fd_out < 0) {
+  // download_parameters (preprocess-kgz.rs:38-47): digest of the existing file.  A mismatch sends the reference to
+  // the network; offline that is an error.  Hashing 604 MB takes as long as the GPUs need for the points, so it
+  // runs beside them and is checked before anything is published.
+  std::future<int> digest;
+  char digest_hex[129] = {0};
+  if (!(flags & PTAU_FILE_SKIP_DIGEST))
+    digest = std::async(std::launch::async, ptau_blake2b_file, response_path, digest_hex);
+
+  const std::string tmp_tag = ".tmp." + std::to_string((long)getpid());
+  const std::string setup_tmp = std::string(setup_path) + tmp_tag;
+  const std::string unc_tmp = emit_unc ? std::string(uncompressed_path) + tmp_tag : std::string();
+  bool unc_exists = false;
+  int fd_unc = -1, fd_out = -1;
+  auto fail = [&](int code) {
+    if (digest.valid()) digest.wait();
     close(fd_in);
     if (fd_unc >= 0) close(fd_unc);
-    return PTAU_ERR_IO;
+    if (fd_out >= 0) close(fd_out);
+    if (fd_out >= 0) unlink(setup_tmp.c_str());
+    if (fd_unc >= 0) unlink(unc_tmp.c_str());
+    return code;
+  };
+  if (emit_unc) {
+    struct stat su;
+    unc_exists = lstat(uncompressed_path, &su) == 0;  // create_new(true) will fail (preprocess-kgz.rs:113-118)
+    if (!unc_exists) {
+      fd_unc = open(unc_tmp.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
+      if (fd_unc < 0) return fail(PTAU_ERR_IO);
+    }
   }
+  fd_out = open(setup_tmp.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
+  if (fd_out < 0) return fail(PTAU_ERR_IO);
 
   struct Sec {
     int group;
@@ -153,14 +185,14 @@ int ptau_preprocess_files(ptau_ctx* ctx, int variant, const char* response_path,
       {PTAU_G1, n, -1, fast || emit_unc},  // beta_g1: fastkgz reads+checks+drops it (:156-159); kgz never reads it
       {PTAU_G2, 1, -1, emit_unc},          // beta_g2: only ever decompressed into `powersoftau_uncompressed`
   };
-  const size_t slab = (size_t)((2 * n) < (1u << 20) ? (2 * n) : (1u << 20));  // points per slab
-  Pinned in0(slab * 96), in1(slab * 96), unc0(slab * 192), unc1(slab * 192), out0(slab * 192), out1(slab * 192);
-  if (!in0.p || !in1.p || !unc0.p || !unc1.p || !out0.p || !out1.p) {
-    close(fd_in);
-    close(fd_out);
-    if (fd_unc >= 0) close(fd_unc);
-    return PTAU_ERR_NOMEM;
-  }
+  // points per slab: pinned memory is paid for by the page (allocation time), so no more than the pipeline needs
+  unsigned slab_log2 = 19;
+  if (const char* e = getenv("PTAU_SLAB_LOG2")) slab_log2 = (unsigned)atoi(e) < 10 ? 10 : (unsigned)atoi(e) > 22 ? 22 : (unsigned)atoi(e);
+  const size_t slab = (size_t)((2 * n) < (1ull << slab_log2) ? (2 * n) : (1ull << slab_log2));
+  Pinned in0(slab * 96), in1(slab * 96), out0(slab * 192), out1(slab * 192);
+  Pinned unc0(emit_unc ? slab * 192 : 16), unc1(emit_unc ? slab * 192 : 16);
+  if (!in0.p || !in1.p || !unc0.p || !unc1.p || !out0.p || !out1.p) return fail(PTAU_ERR_NOMEM);
+  trace.mark("open + pinned slabs");
   uint8_t* inb[2] = {in0.u8(), in1.u8()};
   uint8_t* uncb[2] = {unc0.u8(), unc1.u8()};
   uint8_t* outb[2] = {out0.u8(), out1.u8()};
@@ -168,6 +200,9 @@ int ptau_preprocess_files(ptau_ctx* ctx, int variant, const char* response_path,
   memset(first_g2, 0, sizeof(first_g2));
 
   int rc = PTAU_OK;
+  // first stage-2 (read_g1 / read_g2) error, reported only if the decompression of everything after it is clean
+  int s2_rc = PTAU_OK, s2_kind = 0, s2_sec = -1;
+  uint64_t s2_index = 0;
   uint64_t in_off = 64;  // skip the 64-byte challenge hash (:96-101)
   uint64_t unc_off = 0;
   std::future<bool> wr[2], wu[2];
@@ -196,23 +231,48 @@ int ptau_preprocess_files(ptau_ctx* ctx, int variant, const char* response_path,
         if (rc != PTAU_OK) break;
         uint64_t bi = 0;
         int bk = 0;
+        const bool stage2 = !only_decompress && s2_rc == PTAU_OK;
         // sections that are checked but not written (kgz: tau_g2 beyond its first slab;
         // fastkgz: beta_g1) are validated on the GPU without copying results back
         uint8_t* dst = (sec.out_off >= 0 || k == 0) ? outb[b] : nullptr;
+        int rc2 = PTAU_OK;
         if (emit_unc) {
           // stage 1: decompress (CheckForCorrectness::No) -> `powersoftau_uncompressed`
           rc = ptau_convert(ctx, sec.group, PTAU_FMT_ZCASH_COMPRESSED, inb[b], PTAU_FMT_ZCASH_UNCOMPRESSED, uncb[b], cnt,
                             PTAU_CHECKS_DECOMPRESS, &bi, &bk);
-          if (rc == PTAU_OK)
+          if (rc == PTAU_OK && fd_unc >= 0)
             wu[b] = std::async(std::launch::async, pwrite_all, fd_unc, (const void*)uncb[b], cnt * r_unc,
                                unc_off + lo * r_unc);
           // stage 2: read_g1 / read_g2 on the uncompressed bytes
-          if (rc == PTAU_OK && !only_decompress)
-            rc = ptau_convert(ctx, sec.group, PTAU_FMT_ZCASH_UNCOMPRESSED, uncb[b], PTAU_FMT_ARK_UNCOMPRESSED, dst, cnt,
-                              checks, &bi, &bk);
-        } else if (!only_decompress) {
-          rc = ptau_convert(ctx, sec.group, PTAU_FMT_ZCASH_COMPRESSED, inb[b], PTAU_FMT_ARK_UNCOMPRESSED, dst, cnt, checks,
-                            &bi, &bk);
+          if (rc == PTAU_OK && stage2)
+            rc2 = ptau_convert(ctx, sec.group, PTAU_FMT_ZCASH_UNCOMPRESSED, uncb[b], PTAU_FMT_ARK_UNCOMPRESSED, dst, cnt,
+                               checks, &bi, &bk);
+        } else if (stage2) {
+          // fused: a decode error of the decompression and a failed check are told apart by the kind, and the kernel
+          // reports the lowest bad index of the slab -- same precedence within a slab only if nothing later fails to
+          // decode, so a check failure is re-examined below
+          rc2 = ptau_convert(ctx, sec.group, PTAU_FMT_ZCASH_COMPRESSED, inb[b], PTAU_FMT_ARK_UNCOMPRESSED, dst, cnt, checks,
+                             &bi, &bk);
+          if (rc2 == PTAU_BAD_NOT_IN_SUBGROUP || rc2 == PTAU_BAD_INFINITY) {
+            // stage-2 kinds; is there a stage-1 (decode) error anywhere in this slab?
+            uint64_t bi1 = 0;
+            int bk1 = 0;
+            int rc1 = ptau_convert(ctx, sec.group, PTAU_FMT_ZCASH_COMPRESSED, inb[b], PTAU_FMT_ZCASH_UNCOMPRESSED, nullptr, cnt,
+                                   PTAU_CHECKS_DECOMPRESS, &bi1, &bk1);
+            if (rc1 != PTAU_OK) {
+              rc = rc1;
+              bi = bi1;
+              bk = bk1;
+              rc2 = PTAU_OK;
+            }
+          } else if (rc2 != PTAU_OK) {  // decode error (or a runtime error): stage 1
+            rc = rc2;
+            rc2 = PTAU_OK;
+          }
+        } else if (!only_decompress || emit_unc) {
+          // a stage-2 error is pending: only look for decode errors from here on
+          rc = ptau_convert(ctx, sec.group, PTAU_FMT_ZCASH_COMPRESSED, inb[b], PTAU_FMT_ZCASH_UNCOMPRESSED, nullptr, cnt,
+                            PTAU_CHECKS_DECOMPRESS, &bi, &bk);
         }
         if (rc > 0) {
           if (bad_index) *bad_index = lo + bi;
@@ -221,7 +281,18 @@ int ptau_preprocess_files(ptau_ctx* ctx, int variant, const char* response_path,
           break;
         }
         if (rc != PTAU_OK) break;
-        if (!only_decompress) {
+        if (rc2 < 0) {
+          rc = rc2;
+          break;
+        }
+        if (rc2 > 0) {
+          s2_rc = rc2;
+          s2_kind = bk;
+          s2_sec = s;
+          s2_index = lo + bi;
+          continue;
+        }
+        if (stage2) {
           if (k == 0) {
             if (s == 0) memcpy(first_g1, outb[b], 96);
             if (s == 2) memcpy(first_alpha, outb[b], 96);
@@ -241,21 +312,59 @@ int ptau_preprocess_files(ptau_ctx* ctx, int variant, const char* response_path,
     if (wr[b].valid() && !wr[b].get() && rc == PTAU_OK) rc = PTAU_ERR_IO;
     if (wu[b].valid() && !wu[b].get() && rc == PTAU_OK) rc = PTAU_ERR_IO;
   }
-  if (rc == PTAU_OK) {
-    if (!fast) {  // VerifierKey tail: g, gamma_g, h, beta_h (preprocess-kgz.rs:177-194)
-      uint8_t tail[576];
-      memcpy(tail, first_g1, 96);
-      memcpy(tail + 96, first_alpha, 96);
-      memcpy(tail + 192, first_g2, 384);
-      if (!pwrite_all(fd_out, tail, sizeof(tail), g1_all)) rc = PTAU_ERR_IO;
-    } else {  // h, beta_h in front of powers_of_h (preprocess-fastkgz.rs:199-208)
-      if (!pwrite_all(fd_out, first_g2, 384, g1_all)) rc = PTAU_ERR_IO;
+  trace.mark("sections");
+  // precedence: digest, decode errors (rc), create_new, first read_g1/read_g2 error
+  if (digest.valid()) {
+    int drc = digest.get();
+    if (drc != PTAU_OK) return fail(drc);
+    if (strcmp(digest_hex, expected_digest_hex ? expected_digest_hex : kPowersoftauDigest) != 0) return fail(PTAU_ERR_DIGEST);
+  }
+  trace.mark("digest join");
+  if (rc != PTAU_OK) return fail(rc);
+  if (unc_exists) return fail(PTAU_ERR_EXISTS);
+  if (s2_rc != PTAU_OK) {
+    if (bad_index) *bad_index = s2_index;
+    if (bad_kind) *bad_kind = s2_kind;
+    if (bad_section) *bad_section = s2_sec;
+    return fail(s2_rc);
+  }
+  if (!fast) {  // VerifierKey tail: g, gamma_g, h, beta_h (preprocess-kgz.rs:177-194)
+    uint8_t tail[576];
+    memcpy(tail, first_g1, 96);
+    memcpy(tail + 96, first_alpha, 96);
+    memcpy(tail + 192, first_g2, 384);
+    if (!pwrite_all(fd_out, tail, sizeof(tail), g1_all)) return fail(PTAU_ERR_IO);
+  } else {  // h, beta_h in front of powers_of_h (preprocess-fastkgz.rs:199-208)
+    if (!pwrite_all(fd_out, first_g2, 384, g1_all)) return fail(PTAU_ERR_IO);
+  }
+  if (flags & PTAU_FILE_FSYNC) {
+    if (fsync(fd_out) != 0 || (fd_unc >= 0 && fsync(fd_unc) != 0)) return fail(PTAU_ERR_IO);
+  }
+  // publish
+  if (fd_unc >= 0) {
+    if (close(fd_unc) != 0) {
+      fd_unc = -1;
+      unlink(unc_tmp.c_str());
+      return fail(PTAU_ERR_IO);
     }
+    fd_unc = -1;
+    if (link(unc_tmp.c_str(), uncompressed_path) != 0) {  // create_new: never replaces an existing file
+      const int code = errno == EEXIST ? PTAU_ERR_EXISTS : PTAU_ERR_IO;
+      unlink(unc_tmp.c_str());
+      return fail(code);
+    }
+    unlink(unc_tmp.c_str());
+  }
+  const int crc = close(fd_out);
+  fd_out = -1;
+  if (crc != 0 || rename(setup_tmp.c_str(), setup_path) != 0) {
+    unlink(setup_tmp.c_str());
+    if (emit_unc) unlink(uncompressed_path);
+    return fail(PTAU_ERR_IO);
   }
   close(fd_in);
-  if (fd_unc >= 0) close(fd_unc);
-  if (close(fd_out) != 0 && rc == PTAU_OK) rc = PTAU_ERR_IO;
-  return rc;
+  trace.mark("publish");
+  return PTAU_OK;
 }
 
 // load_kzg_setup / load_fastkzg_setup (/root/reference/src/lib.rs:174-228) from the file:

@@ -99,6 +99,20 @@ PTAU_HD Fq2 fq2_mul_inl(const Fq2& a, const Fq2& b) {
   r.c0 = fq_redc(V0);
   return r;
 }
+#else
+// Karatsuba: 3 Fq multiplications
+PTAU_HD Fq2 fq2_mul_inl(const Fq2& a, const Fq2& b) {
+  Fq v0 = PTAU_FQ2_M(a.c0, b.c0);
+  Fq v1 = PTAU_FQ2_M(a.c1, b.c1);
+  Fq s = PTAU_FQ2_M(fq_add(a.c0, a.c1), fq_add(b.c0, b.c1));
+  Fq2 r;
+  r.c0 = fq_sub(v0, v1);
+  r.c1 = fq_sub(fq_sub(s, v0), v1);
+  return r;
+}
+#endif
+
+#ifdef PTAU_FQ2_SQR3
 // c0 = a0^2 - a1^2, c1 = (a0+a1)^2 - a0^2 - a1^2: three dedicated wide squarings (78 MADs each) + 2 reductions
 // = 546 MADs instead of the 600 of the complex-squaring formula with two full multiplications.
 PTAU_HD Fq2 fq2_sqr_inl(const Fq2& a) {
@@ -118,17 +132,8 @@ PTAU_HD Fq2 fq2_sqr_inl(const Fq2& a) {
   return r;
 }
 #else
-// Karatsuba: 3 Fq multiplications
-PTAU_HD Fq2 fq2_mul_inl(const Fq2& a, const Fq2& b) {
-  Fq v0 = PTAU_FQ2_M(a.c0, b.c0);
-  Fq v1 = PTAU_FQ2_M(a.c1, b.c1);
-  Fq s = PTAU_FQ2_M(fq_add(a.c0, a.c1), fq_add(b.c0, b.c1));
-  Fq2 r;
-  r.c0 = fq_sub(v0, v1);
-  r.c1 = fq_sub(fq_sub(s, v0), v1);
-  return r;
-}
-// complex squaring: 2 Fq multiplications
+// complex squaring: 2 Fq multiplications.  (The three-squarings form above has fewer MADs, 546 against 600, but ~400 more
+// ALU instructions; the squaring then becomes issue-bound instead of FMA-pipe-bound -- A/B in profiles/.)
 PTAU_HD Fq2 fq2_sqr_inl(const Fq2& a) {
   Fq t = PTAU_FQ2_M(a.c0, a.c1);
   Fq2 r;

@@ -170,8 +170,8 @@ PTAU_HD void fqw_sub_fix(uint32_t* a, const uint32_t* b) {
 
 // One reduction row with the window shift fused in.  On entry X is the previous even-aligned accumulator whose limb 0
 // has just been zeroed (limb 1 is the left-over at the new position 0); E0 is limb 0 of the new even-aligned
-// accumulator.  E0 += left-over; m = E0 * (-p^-1); X = (X >> 64) + m * (odd limbs of p), carry chained from E0.
-PTAU_HD void row_red_odd_shift(uint32_t* X, uint32_t& E0, uint32_t& m) {
+// accumulator.  E0 += left-over; m = E0 * (-p^-1); X = (X >> 64) + m * (odd limbs of p) + tin W^10, carry chained from E0.
+PTAU_HD void row_red_odd_shift(uint32_t* X, uint32_t& E0, uint32_t& m, uint32_t tin) {
 #ifdef __CUDA_ARCH__
   asm("add.cc.u32 %12, %12, %1;\n\t"
       "mul.lo.u32 %13, %12, 0xfffcfffd;\n\t"
@@ -185,10 +185,11 @@ PTAU_HD void row_red_odd_shift(uint32_t* X, uint32_t& E0, uint32_t& m) {
       "madc.hi.cc.u32 %7, %13, " P7S ", %9;\n\t"
       "madc.lo.cc.u32 %8, %13, " P9S ", %10;\n\t"
       "madc.hi.cc.u32 %9, %13, " P9S ", %11;\n\t"
-      "madc.lo.cc.u32 %10, %13, " P11S ", 0;\n\t"
+      "madc.lo.cc.u32 %10, %13, " P11S ", %14;\n\t"
       "madc.hi.cc.u32 %11, %13, " P11S ", 0;"
       : "+r"(X[0]), "+r"(X[1]), "+r"(X[2]), "+r"(X[3]), "+r"(X[4]), "+r"(X[5]), "+r"(X[6]), "+r"(X[7]),
-        "+r"(X[8]), "+r"(X[9]), "+r"(X[10]), "+r"(X[11]), "+r"(E0), "=&r"(m));
+        "+r"(X[8]), "+r"(X[9]), "+r"(X[10]), "+r"(X[11]), "+r"(E0), "=&r"(m)
+      : "r"(tin));
 #else
   uint32_t cf = 0;
   E0 = emu::addc(E0, X[1], cf);
@@ -197,7 +198,7 @@ PTAU_HD void row_red_odd_shift(uint32_t* X, uint32_t& E0, uint32_t& m) {
     X[j] = emu::madlo(m, emu::PL[j + 1], X[j + 2], cf);
     X[j + 1] = emu::madhi(m, emu::PL[j + 1], X[j + 3], cf);
   }
-  X[10] = emu::madlo(m, emu::PL[11], 0, cf);
+  X[10] = emu::madlo(m, emu::PL[11], tin, cf);
   X[11] = emu::madhi(m, emu::PL[11], 0, cf);
 #endif
 }
@@ -221,12 +222,9 @@ PTAU_HD Fq fq_redc(const uint32_t* t) {
     uint32_t* E = (i & 1) ? od : ev;
     uint32_t* X = (i & 1) ? ev : od;
     uint32_t m;
-    row_red_odd_shift(X, E[0], m);
-    {  // limb 11+i of T enters at window position 11 (= X[10]); by the bound T + sum m p W^i < 2 p W^12 nothing leaves X[11]
-      PX_DECL;
-      PX_ADD_CC(X[10], X[10], t[11 + i]);
-      PX_ADDC(X[11], X[11], 0u);
-    }
+    // limb 11+i of T enters at window position 11 (= X[10]) as the addend of the top product; by the bound
+    // T + sum m p W^i < 2 p W^12 nothing leaves X[11]
+    row_red_odd_shift(X, E[0], m, t[11 + i]);
     row_red_even(E, X[11], m);
   }
   // last row had E = od, X = ev: result = ev + (od >> 32) + t[23] * W^11

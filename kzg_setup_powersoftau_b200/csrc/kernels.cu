@@ -64,6 +64,16 @@ __device__ __forceinline__ void stage_out(uint32_t* __restrict__ g, const uint32
   for (int i = (nvec << 2) + threadIdx.x; i < nwords; i += BLK) g[i] = sm[i];
 }
 
+// shared memory of one block: the record staging buffer (BLK x max(record_in, record_out)) and, for the G2 kernels
+// with curve checks, the operand file of the subgroup ladder (48 words per thread, transposed: conflict-free)
+template <int G, int INFMT, int OUTFMT, bool HEAVY>
+constexpr int convert_smem_words() {
+  constexpr int BLK = G == PTAU_G1 ? PTAU_BLOCK_G1 : PTAU_BLOCK_G2;
+  constexpr int WIN = record_bytes(G, INFMT) / 4;
+  constexpr int WOUT = record_bytes(G, OUTFMT) / 4;
+  return BLK * (WIN > WOUT ? WIN : WOUT) + ((G == PTAU_G2 && HEAVY) ? BLK * 48 : 0);
+}
+
 template <int G, int INFMT, int OUTFMT, bool HEAVY>
 __global__ void __launch_bounds__((G == PTAU_G1 ? PTAU_BLOCK_G1 : PTAU_BLOCK_G2), (G == PTAU_G1 ? PTAU_MINBLOCKS_G1 : PTAU_MINBLOCKS_G2))
     convert_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint64_t n, uint32_t checks,
@@ -72,7 +82,8 @@ __global__ void __launch_bounds__((G == PTAU_G1 ? PTAU_BLOCK_G1 : PTAU_BLOCK_G2)
   constexpr int WIN = record_bytes(G, INFMT) / 4;
   constexpr int WOUT = record_bytes(G, OUTFMT) / 4;
   constexpr int WMAX = WIN > WOUT ? WIN : WOUT;
-  __shared__ __align__(16) uint32_t sm[BLK * WMAX];
+  constexpr bool PARK = G == PTAU_G2 && HEAVY;
+  extern __shared__ __align__(16) uint32_t sm[];
 
   const uint64_t rec0 = (uint64_t)blockIdx.x * BLK;
   const int nrec = (int)((n - rec0) < (uint64_t)BLK ? (n - rec0) : (uint64_t)BLK);
@@ -106,36 +117,52 @@ __global__ void __launch_bounds__((G == PTAU_G1 ? PTAU_BLOCK_G1 : PTAU_BLOCK_G2)
   __syncthreads();
 
   if (tid < nrec) {
-    uint32_t wout[WOUT];
-    uint32_t st = (G == PTAU_G1) ? g1_process<INFMT, HEAVY>(win, OUTFMT, wout, checks)
-                                 : g2_process<INFMT, HEAVY>(win, OUTFMT, wout, checks);
-    uint2* s2 = reinterpret_cast<uint2*>(sm + tid * WOUT);
+    uint32_t st;
+    if (G == PTAU_G2) {
+      // every input record is in registers now: the thread's slot of the staging buffer takes the output record
+      // directly (written before the subgroup ladder starts), and the ladder's base point lives in the operand file
+      Park<BLK> pk;
+      pk.base = (uint32_t)__cvta_generic_to_shared(sm + (PARK ? BLK * WMAX : 0) + tid);  // !PARK: never touched
+      st = g2_process<INFMT, HEAVY, BLK>(win, OUTFMT, sm + tid * WOUT, checks, pk);
+    } else {
+      uint32_t wout[WOUT];
+      st = g1_process<INFMT, HEAVY>(win, OUTFMT, wout, checks);
+      uint2* s2 = reinterpret_cast<uint2*>(sm + tid * WOUT);
 #pragma unroll
-    for (int j = 0; j < WOUT / 2; j++) s2[j] = make_uint2(wout[2 * j], wout[2 * j + 1]);
+      for (int j = 0; j < WOUT / 2; j++) s2[j] = make_uint2(wout[2 * j], wout[2 * j + 1]);
+    }
     if (st != PTAU_OK) atomicMin(status, (unsigned long long)(((base_index + rec0 + tid) << 8) | st));
   }
   __syncthreads();
   stage_out<BLK>(out + rec0 * WOUT, sm, nrec * WOUT);
 }
 
+template <int G, int INFMT, int OUTFMT, bool HEAVY>
+static cudaError_t launch_inst(const void* d_in, void* d_out, uint64_t n, uint32_t checks, uint64_t base_index,
+                               unsigned long long* d_status, cudaStream_t stream) {
+  constexpr int BLK = G == PTAU_G1 ? PTAU_BLOCK_G1 : PTAU_BLOCK_G2;
+  constexpr int SMEM = convert_smem_words<G, INFMT, OUTFMT, HEAVY>() * 4;
+  auto kern = convert_kernel<G, INFMT, OUTFMT, HEAVY>;
+  if (SMEM > 48 * 1024) {  // per device: cheap, and a context may own several GPUs
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    if (e != cudaSuccess) return e;
+  }
+  unsigned grid = (unsigned)((n + BLK - 1) / BLK);
+  kern<<<grid, BLK, SMEM, stream>>>((const uint32_t*)d_in, (uint32_t*)d_out, n, checks, base_index, d_status);
+  return cudaGetLastError();
+}
+
 template <int G, int INFMT, int OUTFMT>
 static cudaError_t launch_one(const void* d_in, void* d_out, uint64_t n, uint32_t checks, uint64_t base_index,
                               unsigned long long* d_status, cudaStream_t stream) {
   if (n == 0) return cudaSuccess;
-  constexpr int BLK = G == PTAU_G1 ? PTAU_BLOCK_G1 : PTAU_BLOCK_G2;
-  unsigned grid = (unsigned)((n + BLK - 1) / BLK);
   // no curve checks requested on an uncompressed input: the lightweight instance
   // (compressed input is on the curve by construction, so only the subgroup bit matters there)
   const bool light = INFMT == PTAU_FMT_ZCASH_COMPRESSED
                          ? !(checks & PTAU_CHECK_SUBGROUP)
                          : !(checks & (PTAU_CHECK_ON_CURVE | PTAU_CHECK_SUBGROUP));
-  if (light)
-    convert_kernel<G, INFMT, OUTFMT, false><<<grid, BLK, 0, stream>>>(
-        (const uint32_t*)d_in, (uint32_t*)d_out, n, checks, base_index, d_status);
-  else
-    convert_kernel<G, INFMT, OUTFMT, true><<<grid, BLK, 0, stream>>>(
-        (const uint32_t*)d_in, (uint32_t*)d_out, n, checks, base_index, d_status);
-  return cudaGetLastError();
+  if (light) return launch_inst<G, INFMT, OUTFMT, false>(d_in, d_out, n, checks, base_index, d_status, stream);
+  return launch_inst<G, INFMT, OUTFMT, true>(d_in, d_out, n, checks, base_index, d_status, stream);
 }
 
 template <int G, int INFMT>

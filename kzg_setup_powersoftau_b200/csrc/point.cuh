@@ -265,8 +265,10 @@ PTAU_HD uint32_t g1_process(const uint32_t* in, int out_fmt, uint32_t* out, uint
 // =============================================================================
 // G2
 // =============================================================================
-template <int INFMT, bool HEAVY = true>
-PTAU_HD uint32_t g2_process(const uint32_t* in, int out_fmt, uint32_t* out, uint32_t checks) {
+// `out` may point to shared memory: the record is encoded BEFORE the subgroup ladder so that nothing but the
+// ladder's own state is live across it.  `pk` is the ladder's operand file (curve.cuh: Park).
+template <int INFMT, bool HEAVY, int PSTRIDE>
+PTAU_HD uint32_t g2_process(const uint32_t* in, int out_fmt, uint32_t* out, uint32_t checks, Park<PSTRIDE> pk) {
   if (!HEAVY) checks &= PTAU_CHECK_REJECT_INFINITY;
   Fq2 xp, yp, xm, ym;
   uint32_t st = PTAU_OK;
@@ -378,10 +380,10 @@ PTAU_HD uint32_t g2_process(const uint32_t* in, int out_fmt, uint32_t* out, uint
     }
   }
   if (st == PTAU_OK && inf && (checks & PTAU_CHECK_REJECT_INFINITY)) st = PTAU_BAD_INFINITY;
-  if (HEAVY && st == PTAU_OK && !inf && !off_curve && (checks & PTAU_CHECK_SUBGROUP)) {
-    if (!g2_in_subgroup(xm, ym)) st = PTAU_BAD_NOT_IN_SUBGROUP;
-  }
+  const bool ladder = HEAVY && st == PTAU_OK && !inf && !off_curve && (checks & PTAU_CHECK_SUBGROUP);
+  if (ladder) pk.store_g2(xm, ym);
 
+  // ---- encode (the subgroup result below only changes the status) ----
   if (out_fmt == PTAU_FMT_ARK_UNCOMPRESSED) {
     fq_to_le_words(xp.c0, out);
     fq_to_le_words(xp.c1, out + 12);
@@ -418,7 +420,19 @@ PTAU_HD uint32_t g2_process(const uint32_t* in, int out_fmt, uint32_t* out, uint
     out[48] = inf ? 1u : 0u;
     out[49] = 0;
   }
+  if (ladder && !g2_in_subgroup(pk)) st = PTAU_BAD_NOT_IN_SUBGROUP;
   return st;
 }
+
+#ifndef __CUDA_ARCH__
+// host build (tests/host_emul): the operand file is a local array
+template <int INFMT, bool HEAVY = true>
+inline uint32_t g2_process(const uint32_t* in, int out_fmt, uint32_t* out, uint32_t checks) {
+  uint32_t file[48];
+  Park<1> pk;
+  pk.p = file;
+  return g2_process<INFMT, HEAVY, 1>(in, out_fmt, out, checks, pk);
+}
+#endif
 
 }  // namespace ptau

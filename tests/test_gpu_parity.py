@@ -225,6 +225,75 @@ def test_file_pipeline_2pow14_multi_slab(ctx, tmp_path):
     assert params.powers_of_g.shape == (2 * n - 1, 104) and ph.shape == (n, 200)
 
 
+def test_file_pipeline_failure_is_atomic_and_ordered(ctx, tmp_path, monkeypatch):
+    """A failed run publishes nothing: an older good `kzg_setup` stays byte-identical, no partial
+    `powersoftau_uncompressed`, no temporary files (the reference validates in RAM before it creates `kzg_setup`,
+    preprocess-kgz.rs:128-160 then :186).  Errors come in the reference's order of events: decode errors of the
+    decompression pass over ALL sections (:105-110), then create_new of the intermediate file (:113-118), then the
+    first bad point of the read_g1/read_g2 loops (:140-153) -- with several slabs per section."""
+    monkeypatch.setenv("PTAU_SLAB_LOG2", "10")  # floor of the knob: slabs of 1024 points, 2^11-power file below
+    meta = json.load(open(os.path.join(GOLDEN, "edge_cases.json")))
+    off_subgroup = next(bytes.fromhex(c["rec"]) for c in meta["cases"] if c["group"] == 1 and c["in_fmt"] == 2 and c["strict"] == 5)
+    undecodable = next(bytes.fromhex(c["rec"]) for c in meta["cases"] if c["group"] == 1 and c["in_fmt"] == 2 and c["strict"] == 4)
+    k = 11
+    n = 1 << k
+    tau, alpha, beta = o.derive_scalars(0xB202)
+    ZCf = kz.FMT_ZCASH_COMPRESSED
+    body = np.concatenate([ctx.generate(1, ZCf, 1, tau, 0, 2 * n - 1), ctx.generate(2, ZCf, 1, tau, 0, n),
+                           ctx.generate(1, ZCf, alpha, tau, 0, n), ctx.generate(1, ZCf, beta, tau, 0, n),
+                           ctx.generate(2, ZCf, beta, tau, 0, 1)])
+    good = o.filler_bytes(3, 64, b"hash") + body.tobytes() + o.filler_bytes(3, o.PUBKEY_SIZE, b"pubkey")
+    src = tmp_path / "powersoftau"
+    src.write_bytes(good)
+    kz.preprocess_kgz(str(tmp_path), log2_powers=k, expected_digest=None, emit_uncompressed=False, ctx=ctx)
+    want = (tmp_path / "kzg_setup").read_bytes()
+    assert want == ctx.preprocess(kz.VARIANT_KGZ, good, n).tobytes()
+
+    def clean_dir():
+        assert sorted(p.name for p in tmp_path.iterdir()) == ["kzg_setup", "powersoftau"]
+        assert (tmp_path / "kzg_setup").read_bytes() == want
+
+    off_tau = 64 + 3000 * 48                                   # tau_powers_g1[3000]: third slab of section 0
+    off_alpha = 64 + (2 * n - 1) * 48 + n * 96 + 1500 * 48     # alpha_tau_powers_g1[1500]: second slab of section 2
+    bad = bytearray(good)
+    bad[off_tau:off_tau + 48] = off_subgroup
+    src.write_bytes(bytes(bad))
+    for emit in (False, True):
+        with pytest.raises(kz.PtauError) as ei:
+            kz.preprocess_kgz(str(tmp_path), log2_powers=k, expected_digest=None, emit_uncompressed=emit, ctx=ctx)
+        assert (ei.value.code, ei.value.section, ei.value.index) == (kz.BAD_NOT_IN_SUBGROUP, 0, 3000)
+        clean_dir()
+    # a later undecodable point wins over the earlier subgroup failure (the decompression pass runs first)
+    bad[off_alpha:off_alpha + 48] = undecodable
+    src.write_bytes(bytes(bad))
+    for emit in (False, True):
+        with pytest.raises(kz.PtauError) as ei:
+            kz.preprocess_kgz(str(tmp_path), log2_powers=k, expected_digest=None, emit_uncompressed=emit, ctx=ctx)
+        assert (ei.value.code, ei.value.section, ei.value.index) == (kz.BAD_NOT_ON_CURVE, 2, 1500)
+        clean_dir()
+    # ... and over create_new; create_new in turn wins over the read_g1 failure
+    (tmp_path / "powersoftau_uncompressed").write_bytes(b"older")
+    with pytest.raises(kz.PtauError) as ei:
+        kz.preprocess_kgz(str(tmp_path), log2_powers=k, expected_digest=None, ctx=ctx)
+    assert ei.value.code == kz.BAD_NOT_ON_CURVE
+    bad[off_alpha:off_alpha + 48] = good[off_alpha:off_alpha + 48]
+    src.write_bytes(bytes(bad))
+    with pytest.raises(FileExistsError):
+        kz.preprocess_kgz(str(tmp_path), log2_powers=k, expected_digest=None, ctx=ctx)
+    assert (tmp_path / "powersoftau_uncompressed").read_bytes() == b"older"
+    os.remove(tmp_path / "powersoftau_uncompressed")
+    # a wrong digest wins over everything
+    with pytest.raises(IOError):
+        kz.preprocess_kgz(str(tmp_path), log2_powers=k, expected_digest="00" * 64, ctx=ctx)
+    clean_dir()
+    # the good file again, through many slabs, with the intermediate file
+    src.write_bytes(good)
+    kz.preprocess_kgz(str(tmp_path), log2_powers=k, expected_digest=o.blake2b_hex(good), ctx=ctx)
+    assert (tmp_path / "kzg_setup").read_bytes() == want
+    assert (tmp_path / "powersoftau_uncompressed").read_bytes() == ctx.preprocess(kz.VARIANT_KGZ, good, n, emit_uncompressed=True)[1].tobytes()
+    assert sorted(p.name for p in tmp_path.iterdir()) == ["kzg_setup", "powersoftau", "powersoftau_uncompressed"]
+
+
 def test_phase1_and_read_g(ctx, tmp_path):
     m = 4
     data = golden("n8_phase1radix2m2.bin")
