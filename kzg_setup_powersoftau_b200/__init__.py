@@ -639,7 +639,7 @@ def _n_from_setup_size(variant: int, size: int) -> int:
 
 def _load_setup_file(variant: int, path: str, log2_powers: Optional[int], ctx: Optional["Context"], checks: int):
     """ptau_load_setup_file: the file is streamed through pinned slabs in C++; the records
-    land in pinned buffers owned by the returned arrays."""
+    land in the returned arrays."""
     L = _ffi.lib()
     ctx = ctx or default_context()
     if not os.path.exists(path):
@@ -653,12 +653,13 @@ def _load_setup_file(variant: int, path: str, log2_powers: Optional[int], ctx: O
     n = n_out.value
     fast = variant == VARIANT_FASTKGZ
     n_g1, n_g2 = 3 * n - 1 + (0 if fast else 2), (n + 2 if fast else 2)
-    b1, b2 = PinnedBuffer(n_g1 * 104), PinnedBuffer(n_g2 * 200)
-    rc = L.ptau_load_setup_file(ctx._h, variant, path.encode(), n, checks, b1.ptr, b1.nbytes, b2.ptr, b2.nbytes,
+    # plain (pageable) arrays: pinning 650 MB of output costs more (~0.5 ms per MB) than the staged copy it would save
+    b1, b2 = np.empty(n_g1 * 104, dtype=np.uint8), np.empty(n_g2 * 200, dtype=np.uint8)
+    rc = L.ptau_load_setup_file(ctx._h, variant, path.encode(), n, checks, _ptr(b1), b1.size, _ptr(b2), b2.size,
                                 C.byref(n_out), C.byref(bad_i), C.byref(bad_k))
     if rc != 0:
         ctx._raise(rc, bad_i.value if rc > 0 else None)
-    return n, b1.array.reshape(n_g1, 104), b2.array.reshape(n_g2, 200)  # views keep the pinned memory alive
+    return n, b1.reshape(n_g1, 104), b2.reshape(n_g2, 200)
 
 
 def load_kzg_setup(path: str = KZG_SETUP_FILE, log2_powers: Optional[int] = None, ctx: Optional[Context] = None,

@@ -7,6 +7,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
+#include <unistd.h>
 
 #include <string>
 
@@ -45,7 +47,12 @@ int main(int argc, char** argv) {
     } else { usage(argv[0]); return 2; }
   }
   ptau_ctx* ctx = nullptr;
+  struct timespec t0, t1;
+  clock_gettime(CLOCK_MONOTONIC, &t0);
   int rc = ptau_create(&ctx, gpus, nullptr, 0);
+  clock_gettime(CLOCK_MONOTONIC, &t1);
+  if (getenv("PTAU_TRACE"))
+    fprintf(stderr, "[ptau trace] ptau_create (CUDA context)   %.1f ms\n", (t1.tv_sec - t0.tv_sec) * 1e3 + (t1.tv_nsec - t0.tv_nsec) / 1e6);
   if (rc != PTAU_OK) {
     fprintf(stderr, "ptau_create(%d GPUs): %s\n", gpus, ptau_strerror(rc));
     return 1;
@@ -73,6 +80,9 @@ int main(int argc, char** argv) {
   } else {
     printf("Done serializing. KZG parameters are stored in kzg_setup\n");
   }
-  ptau_destroy(ctx);
-  return rc == PTAU_OK ? 0 : 1;
+  // every output is closed and published (or unlinked) by now: leave without tearing the CUDA context and the
+  // pinned slabs down page by page
+  fflush(stdout);
+  fflush(stderr);
+  _exit(rc == PTAU_OK ? 0 : 1);
 }

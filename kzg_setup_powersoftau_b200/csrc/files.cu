@@ -58,6 +58,23 @@ bool pwrite_all(int fd, const void* buf, size_t len, uint64_t off) {
   return true;
 }
 
+// A slab goes to the page cache in parallel parts: one thread copies ~2 GB/s into fresh pages, which is slower than
+// the GPUs produce records.
+bool pwrite_parts(int fd, const void* buf, size_t len, uint64_t off) {
+  const size_t kPart = 8u << 20;
+  if (len <= 2 * kPart) return pwrite_all(fd, buf, len, off);
+  const int parts = len / kPart > 4 ? 4 : (int)(len / kPart);
+  const size_t each = ((len / parts) + 4095) & ~(size_t)4095;
+  std::future<bool> f[4];
+  for (int i = 1; i < parts; i++) {
+    const size_t lo = each * i, n = i == parts - 1 ? len - lo : each;
+    f[i] = std::async(std::launch::async, pwrite_all, fd, (const void*)((const uint8_t*)buf + lo), n, off + lo);
+  }
+  bool ok = pwrite_all(fd, buf, each, off);
+  for (int i = 1; i < parts; i++) ok = f[i].get() && ok;
+  return ok;
+}
+
 // PTAU_TRACE=1: wall-clock marks of the file pipelines on stderr
 struct Trace {
   bool on;
@@ -186,7 +203,7 @@ int ptau_preprocess_files(ptau_ctx* ctx, int variant, const char* response_path,
       {PTAU_G2, 1, -1, emit_unc},          // beta_g2: only ever decompressed into `powersoftau_uncompressed`
   };
   // points per slab: pinned memory is paid for by the page (allocation time), so no more than the pipeline needs
-  unsigned slab_log2 = 19;
+  unsigned slab_log2 = 18;
   if (const char* e = getenv("PTAU_SLAB_LOG2")) slab_log2 = (unsigned)atoi(e) < 10 ? 10 : (unsigned)atoi(e) > 22 ? 22 : (unsigned)atoi(e);
   const size_t slab = (size_t)((2 * n) < (1ull << slab_log2) ? (2 * n) : (1ull << slab_log2));
   Pinned in0(slab * 96), in1(slab * 96), out0(slab * 192), out1(slab * 192);
@@ -241,7 +258,7 @@ int ptau_preprocess_files(ptau_ctx* ctx, int variant, const char* response_path,
           rc = ptau_convert(ctx, sec.group, PTAU_FMT_ZCASH_COMPRESSED, inb[b], PTAU_FMT_ZCASH_UNCOMPRESSED, uncb[b], cnt,
                             PTAU_CHECKS_DECOMPRESS, &bi, &bk);
           if (rc == PTAU_OK && fd_unc >= 0)
-            wu[b] = std::async(std::launch::async, pwrite_all, fd_unc, (const void*)uncb[b], cnt * r_unc,
+            wu[b] = std::async(std::launch::async, pwrite_parts, fd_unc, (const void*)uncb[b], cnt * r_unc,
                                unc_off + lo * r_unc);
           // stage 2: read_g1 / read_g2 on the uncompressed bytes
           if (rc == PTAU_OK && stage2)
@@ -299,7 +316,7 @@ int ptau_preprocess_files(ptau_ctx* ctx, int variant, const char* response_path,
             if (s == 1) memcpy(first_g2, outb[b], 384);  // n >= 2
           }
           if (sec.out_off >= 0)
-            wr[b] = std::async(std::launch::async, pwrite_all, fd_out, (const void*)outb[b], cnt * r_out,
+            wr[b] = std::async(std::launch::async, pwrite_parts, fd_out, (const void*)outb[b], cnt * r_out,
                                (uint64_t)sec.out_off + lo * r_out);
         }
       }
@@ -408,12 +425,16 @@ int ptau_load_setup_file(ptau_ctx* ctx, int variant, const char* setup_path, uin
     close(fd);
     return PTAU_ERR_SIZE;
   }
-  const size_t slab = (size_t)((2 * n) < (1u << 20) ? (2 * n) : (1u << 20));
-  Pinned b0(slab * 192), b1(slab * 192);
+  // pinned memory costs ~0.5 ms per MB to allocate: two slabs of 2^18 records (the G1 sections are 96-byte records;
+  // the few G2 slabs of a fastkgz file go through the same buffers at half the count)
+  Trace trace;
+  const size_t slab_bytes = (size_t)96 << 18;
+  Pinned b0(slab_bytes), b1(slab_bytes);
   if (!b0.p || !b1.p) {
     close(fd);
     return PTAU_ERR_NOMEM;
   }
+  trace.mark("load: pinned slabs");
   uint8_t* buf[2] = {b0.u8(), b1.u8()};
   const struct {
     int group;
@@ -425,6 +446,7 @@ int ptau_load_setup_file(ptau_ctx* ctx, int variant, const char* setup_path, uin
   for (int s = 0; s < 2 && rc == PTAU_OK; s++) {
     const size_t ri = ptau_record_size(secs[s].group, PTAU_FMT_ARK_UNCOMPRESSED);
     const size_t ro = ptau_record_size(secs[s].group, PTAU_FMT_ARK_MONT_LIMBS);
+    const size_t slab = slab_bytes / ri;
     const uint64_t cnt = secs[s].count, nslab = (cnt + slab - 1) / slab;
     std::future<bool> rd = std::async(std::launch::async, pread_all, fd, buf[0], (size_t)((cnt < slab ? cnt : slab) * ri), off);
     for (uint64_t k = 0; k < nslab && rc == PTAU_OK; k++) {
@@ -452,6 +474,7 @@ int ptau_load_setup_file(ptau_ctx* ctx, int variant, const char* setup_path, uin
     base += cnt;
   }
   close(fd);
+  trace.mark("load: sections");
   return rc;
 }
 
