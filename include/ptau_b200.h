@@ -247,6 +247,13 @@ int ptau_kzg_check(ptau_ctx* ctx, const void* vk_g1, const void* vk_g2, const vo
  * (ptau_kzg_commit) followed by one such product against {beta_h, h}. */
 int ptau_pairing_product2(ptau_ctx* ctx, const void* g1, const void* g2, size_t n, void* gt_out, uint8_t* is_one);
 
+/* ark-ec 0.2 `G2Prepared` of n G2 points (ARK_MONT_LIMBS records): `prepared_h` / `prepared_beta_h` of the keys the
+ * reference builds with `h.into()` / `beta_h.into()` (src/lib.rs:223-224, src/bin/preprocess-kgz.rs:177-184).
+ * coeffs_out: n x PTAU_G2_PREPARED_COEFFS x 288 bytes -- per coefficient the triple (c0, c1, c2) of Fq2 in ark-ff's
+ * in-memory Montgomery limbs, in the order ark pushes them (doubling step, then the addition step on the set bits of
+ * |z|); infinity_out[i] = 1 for a point at infinity (ark keeps no coefficients then; the slot is zero-filled). */
+#define PTAU_G2_PREPARED_COEFFS 68
+int ptau_g2_prepare(ptau_ctx* ctx, const void* g2, size_t n, void* coeffs_out, uint8_t* infinity_out);
 /* ---- self-test hook --------------------------------------------------------------- */
 /* Raw Fq operations on n pairs of 48-byte Montgomery-limb values (host pointers), computed by
  * the kernels' own field code on the GPU: op 0 mul, 1 add, 2 sub, 3 neg, 4 sqr, 5 a^((p-3)/4),

@@ -443,6 +443,31 @@ class KZG10:
         return bool(KZG10.pairing_product2(g1, g2, ctx=ctx)[1][0])
 
 
+G2_PREPARED_COEFFS = 68  # PTAU_G2_PREPARED_COEFFS
+
+
+@dataclass
+class G2Prepared:
+    """ark-ec 0.2 `G2Prepared { ell_coeffs, infinity }` (prepared_h / prepared_beta_h, src/lib.rs:223-224):
+    ell_coeffs as a u8 array [68, 3, 96] -- per Miller-loop step the triple (c0, c1, c2) of Fq2 in ark-ff's in-memory
+    Montgomery limbs (c0-part | c1-part); empty for the point at infinity, as in ark."""
+    ell_coeffs: np.ndarray
+    infinity: bool
+
+
+def g2_prepare(points, ctx: Optional["Context"] = None) -> list:
+    """`G2Prepared::from(q)` for each 200-byte G2 record, computed on the GPU (ptau_g2_prepare)."""
+    ctx = ctx or default_context()
+    pts = np.ascontiguousarray(np.asarray(points, dtype=np.uint8).reshape(-1, 200))
+    n = pts.shape[0]
+    coeffs = np.zeros((n, G2_PREPARED_COEFFS, 3, 96), dtype=np.uint8)
+    inf = np.zeros(n, dtype=np.uint8)
+    rc = _ffi.lib().ptau_g2_prepare(ctx._h, _ptr(pts) if n else None, n, _ptr(coeffs) if n else None, _ptr(inf) if n else None)
+    if rc != 0:
+        ctx._raise(rc)
+    return [G2Prepared(ell_coeffs=coeffs[i] if not inf[i] else coeffs[i][:0], infinity=bool(inf[i])) for i in range(n)]
+
+
 class ResidentPoints:
     """G1 powers kept on the GPU(s) of a context (ptau_kzg_powers_upload): commitments then send only the scalars.
     Behaves like the array it was made from as far as KZG10.commit / open are concerned (len, prefix use)."""
@@ -527,6 +552,12 @@ class VerifierKey:
     h: np.ndarray
     beta_h: np.ndarray
 
+    def prepared_h(self, ctx: Optional["Context"] = None) -> "G2Prepared":
+        return g2_prepare(self.h, ctx)[0]
+
+    def prepared_beta_h(self, ctx: Optional["Context"] = None) -> "G2Prepared":
+        return g2_prepare(self.beta_h, ctx)[0]
+
 
 @dataclass
 class UniversalParams:
@@ -538,6 +569,13 @@ class UniversalParams:
     beta_h: np.ndarray            # = powers_of_h[1] (src/lib.rs:221)
     prepared_beta_h_src: np.ndarray  # the file's beta_h, source of prepared_beta_h (src/lib.rs:224)
     neg_powers_of_h: Dict[int, np.ndarray] = field(default_factory=dict)
+
+    def prepared_h(self, ctx: Optional["Context"] = None) -> "G2Prepared":
+        return g2_prepare(self.h, ctx)[0]
+
+    def prepared_beta_h(self, ctx: Optional["Context"] = None) -> "G2Prepared":
+        """`beta_h.into()` of the FILE's beta_h, not of the `beta_h` field (= powers_of_h[1]): src/lib.rs:221 vs :224."""
+        return g2_prepare(self.prepared_beta_h_src, ctx)[0]
 
 
 @dataclass

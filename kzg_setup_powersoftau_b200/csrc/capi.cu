@@ -17,6 +17,8 @@
 #include <vector>
 
 #include "../../include/ptau_b200.h"
+#include <future>
+
 #include "kernels.h"
 
 namespace {
@@ -38,6 +40,11 @@ struct GpuSlot {
   // KZG10::check: fixed-base tables of the verifier key's g, gamma_g, h, rebuilt when the key changes
   void* d_kzg_tbl = nullptr;
   std::string kzg_tbl_key;
+  // multi-scalar multiplication: device points / scalars / scratch / result and the pinned staging buffer of the
+  // scalars, kept between calls and grown on demand (no cudaMalloc / cudaFree inside a commitment)
+  void *d_msm_pts = nullptr, *d_msm_sc = nullptr, *d_msm_scratch = nullptr, *d_msm_out = nullptr, *h_msm_sc = nullptr;
+  size_t cap_msm_pts = 0, cap_msm_sc = 0, cap_msm_scratch = 0, cap_h_msm_sc = 0;
+  uint32_t* h_msm_out = nullptr;  // pinned: 26 words of the result record + 1 word "a scalar was >= r"
 };
 
 }  // namespace
@@ -270,6 +277,12 @@ void ptau_destroy(ptau_ctx* ctx) {
     if (s.ev_first) cudaEventDestroy(s.ev_first);
     if (s.ev_last) cudaEventDestroy(s.ev_last);
     if (s.d_kzg_tbl) cudaFree(s.d_kzg_tbl);
+    if (s.d_msm_pts) cudaFree(s.d_msm_pts);
+    if (s.d_msm_sc) cudaFree(s.d_msm_sc);
+    if (s.d_msm_scratch) cudaFree(s.d_msm_scratch);
+    if (s.d_msm_out) cudaFree(s.d_msm_out);
+    if (s.h_msm_sc) cudaFreeHost(s.h_msm_sc);
+    if (s.h_msm_out) cudaFreeHost(s.h_msm_out);
   }
   delete ctx;
 }
@@ -706,39 +719,61 @@ int ptau_load_phase1(ptau_ctx* ctx, const void* data, uint64_t len, uint64_t m, 
 }
 
 namespace {
-// one multi-scalar multiplication on one GPU, issued asynchronously on the slot's first stream
-struct MsmJob {
-  void *d_pts = nullptr, *d_sc = nullptr, *d_part = nullptr, *d_out = nullptr;
-  bool own_pts = true;  // false: d_pts points into a resident copy (ptau_kzg_powers)
-  int launches = 0;
-  uint8_t result[104];
-  ~MsmJob() {
-    if (own_pts) cudaFree(d_pts);
-    cudaFree(d_sc);
-    cudaFree(d_part);
-    cudaFree(d_out);
+cudaError_t grow(void** p, size_t* cap, size_t need, bool pinned = false) {
+  if (need <= *cap) return cudaSuccess;
+  if (*p) {
+    cudaError_t e = pinned ? cudaFreeHost(*p) : cudaFree(*p);
+    *p = nullptr;
+    *cap = 0;
+    if (e != cudaSuccess) return e;
   }
-};
-// pts: host records, or (resident = true) device records already on this GPU
-cudaError_t msm_issue(GpuSlot& s, MsmJob& j, const void* pts, const void* sc, size_t n, bool resident = false) {
+  need += need / 8;  // head room: the next slightly larger call does not reallocate
+  cudaError_t e = pinned ? cudaHostAlloc(p, need, cudaHostAllocPortable) : cudaMalloc(p, need);
+  if (e == cudaSuccess) *cap = need;
+  return e;
+}
+// pageable -> pinned in parallel parts (one thread copies ~10 GB/s; 32 MB of scalars would cost as much as a
+// quarter of the kernels)
+void copy_parts(void* dst, const void* src, size_t len) {
+  const size_t kPart = 4u << 20;
+  if (len <= 2 * kPart) {
+    memcpy(dst, src, len);
+    return;
+  }
+  const int parts = len / kPart > 4 ? 4 : (int)(len / kPart);
+  const size_t each = (len / parts + 63) & ~(size_t)63;
+  std::future<void> f[4];
+  for (int i = 1; i < parts; i++) {
+    const size_t lo = each * i, n = i == parts - 1 ? len - lo : each;
+    f[i] = std::async(std::launch::async, [=] { memcpy((uint8_t*)dst + lo, (const uint8_t*)src + lo, n); });
+  }
+  memcpy(dst, src, each);
+  for (int i = 1; i < parts; i++) f[i].get();
+}
+// One multi-scalar multiplication on one GPU, issued asynchronously on the slot's first stream; result and the
+// "scalar >= r" flag land in s.h_msm_out.  pts: host records, or (resident = true) device records on this GPU.
+cudaError_t msm_issue(GpuSlot& s, const void* pts, const void* sc, size_t n, int* launches, bool resident = false) {
   cudaError_t e = cudaSetDevice(s.device);
   ptau::MsmPlan plan;
   ptau::msm_g1_plan(n, &plan);
-  if (resident) {
-    j.own_pts = false;
-    j.d_pts = const_cast<void*>(pts);
-  } else if (e == cudaSuccess) {
-    e = cudaMalloc(&j.d_pts, n * 104 + 16);
+  const void* d_pts = pts;
+  if (e == cudaSuccess && !resident) {
+    e = grow(&s.d_msm_pts, &s.cap_msm_pts, n * 104 + 16);
+    d_pts = s.d_msm_pts;
   }
-  if (e == cudaSuccess) e = cudaMalloc(&j.d_sc, n * 32 + 16);
-  if (e == cudaSuccess) e = cudaMalloc(&j.d_part, plan.scratch_bytes);
-  if (e == cudaSuccess) e = cudaMalloc(&j.d_out, 104);
-  if (e == cudaSuccess && !resident) e = cudaMemcpyAsync(j.d_pts, pts, n * 104, cudaMemcpyHostToDevice, s.stream[0]);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(j.d_sc, sc, n * 32, cudaMemcpyHostToDevice, s.stream[0]);
+  if (e == cudaSuccess) e = grow(&s.d_msm_sc, &s.cap_msm_sc, n * 32 + 16);
+  if (e == cudaSuccess) e = grow(&s.d_msm_scratch, &s.cap_msm_scratch, plan.scratch_bytes);
+  if (e == cudaSuccess) e = grow(&s.h_msm_sc, &s.cap_h_msm_sc, n * 32 + 16, true);
+  if (e == cudaSuccess && !s.d_msm_out) e = cudaMalloc(&s.d_msm_out, 128);
+  if (e == cudaSuccess && !s.h_msm_out) e = cudaHostAlloc((void**)&s.h_msm_out, 128, cudaHostAllocPortable);
+  if (e != cudaSuccess) return e;
+  copy_parts(s.h_msm_sc, sc, n * 32);
+  if (!resident) e = cudaMemcpyAsync(s.d_msm_pts, pts, n * 104, cudaMemcpyHostToDevice, s.stream[0]);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(s.d_msm_sc, s.h_msm_sc, n * 32, cudaMemcpyHostToDevice, s.stream[0]);
   if (e == cudaSuccess) e = cudaEventRecord(s.ev_k0[0], s.stream[0]);
-  if (e == cudaSuccess) e = ptau::launch_msm_g1(j.d_pts, j.d_sc, n, j.d_part, j.d_out, &j.launches, s.stream[0]);
+  if (e == cudaSuccess) e = ptau::launch_msm_g1(d_pts, s.d_msm_sc, n, s.d_msm_scratch, s.d_msm_out, launches, s.stream[0]);
   if (e == cudaSuccess) e = cudaEventRecord(s.ev_k1[0], s.stream[0]);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(j.result, j.d_out, 104, cudaMemcpyDeviceToHost, s.stream[0]);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(s.h_msm_out, s.d_msm_out, 108, cudaMemcpyDeviceToHost, s.stream[0]);
   return e;
 }
 cudaError_t msm_wait(GpuSlot& s, float* ms) {
@@ -800,11 +835,7 @@ int ptau_kzg_commit_resident(ptau_ctx* ctx, const ptau_kzg_powers* powers, const
 
 static int kzg_commit_impl(ptau_ctx* ctx, const void* powers, const ptau_kzg_powers* res, const void* coeffs, size_t n,
                            void* commitment) {
-  // scalars must be canonical (< r), like ark's Fr
-  for (size_t i = 0; i < n; i++) {
-    Fr c = fr_from_le32((const uint8_t*)coeffs + i * 32);
-    if (fr_ge_mod(c.l)) return PTAU_ERR_ARG;
-  }
+  // scalars must be canonical (< r), like ark's Fr: checked on the device by the kernel that reads them anyway
   ptau::MsmPlan plan;
   ptau::msm_g1_plan(n, &plan);
   // point indices travel in 31 bits and the bucket lists (n x W entries) are addressed with 32-bit offsets
@@ -812,41 +843,45 @@ static int kzg_commit_impl(ptau_ctx* ctx, const void* powers, const ptau_kzg_pow
   const int G = (ctx->n_gpus > 1 && n >= (size_t)ctx->n_gpus * (1u << 12)) ? ctx->n_gpus : 1;
   memset(&ctx->timing, 0, sizeof(ctx->timing));
   ctx->timing.n_gpus = ctx->n_gpus;
-  MsmJob jobs[kMaxGpus];
   cudaError_t e = cudaSuccess;
+  int launches[kMaxGpus] = {0};
   for (int g = 0; g < G && e == cudaSuccess; g++) {
     const size_t lo = n * g / G, hi = n * (g + 1) / G;
     if (res)
-      e = msm_issue(ctx->gpu[g], jobs[g], (const uint8_t*)res->d_pts[g] + lo * 104, (const uint8_t*)coeffs + lo * 32, hi - lo, true);
+      e = msm_issue(ctx->gpu[g], (const uint8_t*)res->d_pts[g] + lo * 104, (const uint8_t*)coeffs + lo * 32, hi - lo, &launches[g], true);
     else
-      e = msm_issue(ctx->gpu[g], jobs[g], (const uint8_t*)powers + lo * 104, (const uint8_t*)coeffs + lo * 32, hi - lo);
+      e = msm_issue(ctx->gpu[g], (const uint8_t*)powers + lo * 104, (const uint8_t*)coeffs + lo * 32, hi - lo, &launches[g]);
     ctx->timing.h2d_bytes[g] = (hi - lo) * (res ? 32 : 136);
     ctx->timing.d2h_bytes[g] = 104;
   }
+  bool bad_scalar = false;
+  uint8_t parts[kMaxGpus * 104];
   for (int g = 0; g < G && e == cudaSuccess; g++) {
     float ms = 0;
     e = msm_wait(ctx->gpu[g], &ms);
     ctx->timing.kernel_ms[g] = ms;
     ctx->timing.gpu_ms[g] = ms;
-    ctx->timing.kernel_launches += jobs[g].launches;
-  }
-  if (e == cudaSuccess && G > 1) {
-    uint8_t parts[kMaxGpus * 104], ones[kMaxGpus * 32];
-    memset(ones, 0, sizeof(ones));
-    for (int g = 0; g < G; g++) {
-      memcpy(parts + g * 104, jobs[g].result, 104);
-      ones[g * 32] = 1;
+    ctx->timing.kernel_launches += launches[g];
+    if (e == cudaSuccess) {
+      memcpy(parts + g * 104, ctx->gpu[g].h_msm_out, 104);
+      bad_scalar = bad_scalar || ctx->gpu[g].h_msm_out[26] != 0;
     }
-    MsmJob fin;
+  }
+  if (e == cudaSuccess && bad_scalar) return PTAU_ERR_ARG;
+  if (e == cudaSuccess && G > 1) {
+    uint8_t ones[kMaxGpus * 32];
+    memset(ones, 0, sizeof(ones));
+    for (int g = 0; g < G; g++) ones[g * 32] = 1;
     float ms = 0;
-    e = msm_issue(ctx->gpu[0], fin, parts, ones, (size_t)G);
+    int nl = 0;
+    e = msm_issue(ctx->gpu[0], parts, ones, (size_t)G, &nl);
     if (e == cudaSuccess) e = msm_wait(ctx->gpu[0], &ms);
     ctx->timing.kernel_ms[0] += ms;
     ctx->timing.gpu_ms[0] += ms;
-    ctx->timing.kernel_launches += fin.launches;
-    memcpy(commitment, fin.result, 104);
+    ctx->timing.kernel_launches += nl;
+    if (e == cudaSuccess) memcpy(commitment, ctx->gpu[0].h_msm_out, 104);
   } else if (e == cudaSuccess) {
-    memcpy(commitment, jobs[0].result, 104);
+    memcpy(commitment, parts, 104);
   }
   if (e != cudaSuccess) {
     ctx->last_error = std::string("kzg_commit: ") + cudaGetErrorString(e);
@@ -914,6 +949,39 @@ int ptau_pairing_product2(ptau_ctx* ctx, const void* g1, const void* g2, size_t 
   return PTAU_OK;
 }
 
+int ptau_g2_prepare(ptau_ctx* ctx, const void* g2, size_t n, void* coeffs_out, uint8_t* infinity_out) {
+  if (!ctx || (n && (!g2 || !coeffs_out || !infinity_out))) return PTAU_ERR_ARG;
+  if (n == 0) return PTAU_OK;
+  GpuSlot& s = ctx->gpu[0];
+  CUDA_TRY(ctx, cudaSetDevice(s.device));
+  DevArgs a;
+  void *d2 = nullptr, *dc = nullptr, *di = nullptr;
+  const size_t cb = (size_t)PTAU_G2_PREPARED_COEFFS * 288;
+  cudaError_t e = a.push(g2, n * 200, s.stream[0], &d2);
+  if (e == cudaSuccess) e = a.push(nullptr, n * cb, s.stream[0], &dc);
+  if (e == cudaSuccess) e = a.push(nullptr, n, s.stream[0], &di);
+  if (e == cudaSuccess) e = cudaEventRecord(s.ev_k0[0], s.stream[0]);
+  if (e == cudaSuccess) e = ptau::launch_g2_prepare(d2, n, dc, di, s.stream[0]);
+  if (e == cudaSuccess) e = cudaEventRecord(s.ev_k1[0], s.stream[0]);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(coeffs_out, dc, n * cb, cudaMemcpyDeviceToHost, s.stream[0]);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(infinity_out, di, n, cudaMemcpyDeviceToHost, s.stream[0]);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s.stream[0]);
+  float ms = 0;
+  if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, s.ev_k0[0], s.ev_k1[0]);
+  if (e != cudaSuccess) {
+    ctx->last_error = std::string("g2_prepare: ") + cudaGetErrorString(e);
+    return PTAU_ERR_CUDA;
+  }
+  memset(&ctx->timing, 0, sizeof(ctx->timing));
+  ctx->timing.n_gpus = ctx->n_gpus;
+  ctx->timing.kernel_ms[0] = ms;
+  ctx->timing.gpu_ms[0] = ms;
+  ctx->timing.kernel_launches = 1;
+  ctx->timing.h2d_bytes[0] = n * 200;
+  ctx->timing.d2h_bytes[0] = n * (cb + 1);
+  return PTAU_OK;
+}
+
 int ptau_kzg_check(ptau_ctx* ctx, const void* vk_g1, const void* vk_g2, const void* comms, const void* points,
                    const void* values, const void* proofs_w, const void* random_v, size_t n, uint8_t* ok) {
   if (!ctx || !vk_g1 || !vk_g2 || (n && (!comms || !points || !values || !proofs_w || !ok))) return PTAU_ERR_ARG;
@@ -928,6 +996,7 @@ int ptau_kzg_check(ptau_ctx* ctx, const void* vk_g1, const void* vk_g2, const vo
   memset(&ctx->timing, 0, sizeof(ctx->timing));
   ctx->timing.n_gpus = ctx->n_gpus;
   DevArgs args[kMaxGpus];
+  bool rebuilt[kMaxGpus] = {false};
   cudaError_t e = cudaSuccess;
   for (int g = 0; g < G && e == cudaSuccess; g++) {
     GpuSlot& s = ctx->gpu[g];
@@ -948,8 +1017,10 @@ int ptau_kzg_check(ptau_ctx* ctx, const void* vk_g1, const void* vk_g2, const vo
     if (e == cudaSuccess) {  // fixed-base tables of g, gamma_g, h: kept while the key stays the same
       if (!s.d_kzg_tbl) e = cudaMalloc(&s.d_kzg_tbl, ptau::kzg_tables_bytes());
       if (e == cudaSuccess && key != s.kzg_tbl_key) {
+        // the key is recorded only once the build is known to have completed (below); until then the slot has none
+        s.kzg_tbl_key.clear();
         e = ptau::launch_kzg_tables(dv1, dv2, s.d_kzg_tbl, st);
-        if (e == cudaSuccess) s.kzg_tbl_key = key;
+        rebuilt[g] = true;
         launches++;
       }
     }
@@ -967,6 +1038,7 @@ int ptau_kzg_check(ptau_ctx* ctx, const void* vk_g1, const void* vk_g2, const vo
     e = cudaSetDevice(s.device);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s.stream[0]);
     if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, s.ev_k0[0], s.ev_k1[0]);
+    if (e == cudaSuccess && rebuilt[g]) s.kzg_tbl_key = key;  // the table kernel ran to completion on this GPU
     ctx->timing.kernel_ms[g] = ms;
     ctx->timing.gpu_ms[g] = ms;
   }

@@ -606,14 +606,24 @@ cudaError_t launch_generate_win(int group, int fmt, const uint32_t* s0_mont, con
 
 // pts: ARK_MONT_LIMBS records (26 words); scalars: 8 x u32 LE each, < r.  SCATTER = false: histogram
 // into cnt[]; SCATTER = true: cnt[] holds the running cursor of every bucket, entries[] receives the indices.
+// `bad` (SCATTER = false only): set when a scalar is not canonical (>= r; ark's Fr cannot hold such a value).
 template <bool SCATTER>
 __global__ void __launch_bounds__(256) msm_digits(const uint32_t* __restrict__ pts, const uint32_t* __restrict__ scalars,
                                                   uint64_t n, MsmGeom g, uint32_t* __restrict__ cnt,
-                                                  uint32_t* __restrict__ entries) {
+                                                  uint32_t* __restrict__ entries, uint32_t* __restrict__ bad) {
   const uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x;
   if (i >= n) return;
-  if (pts[i * 26 + 24] & 0xffu) return;  // a point flagged infinity contributes nothing
   const uint32_t* k = scalars + i * 8;
+  if (!SCATTER) {
+    uint32_t bf = 0;  // k - r borrows  <=>  k < r
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      uint64_t t = (uint64_t)k[j] - K_R_ORDER_D[j] - bf;
+      bf = (uint32_t)(t >> 63);
+    }
+    if (!bf) *bad = 1u;
+  }
+  if (pts[i * 26 + 24] & 0xffu) return;  // a point flagged infinity contributes nothing
   uint32_t carry = 0, base = 0;
   int bit = 0;
   for (int w = 0; w < g.W; w++) {
@@ -775,15 +785,18 @@ cudaError_t launch_msm_g1(const void* d_pts, const void* d_scalars, uint64_t n, 
   const uint32_t* sc = (const uint32_t*)d_scalars;
   cudaError_t e = cudaMemsetAsync(counts, 0, (size_t)(m + 1) * 4, stream);
   if (e != cudaSuccess) return e;
+  uint32_t* bad = (uint32_t*)d_out + 26;  // d_out: 26 words of the result record + the "scalar >= r" flag
+  e = cudaMemsetAsync(bad, 0, 4, stream);
+  if (e != cudaSuccess) return e;
   const unsigned gn = (unsigned)((n + 255) / 256);
   int nl = 0;
   if (gn) {
-    msm_digits<false><<<gn, 256, 0, stream>>>(pts, sc, n, g, counts, nullptr);
+    msm_digits<false><<<gn, 256, 0, stream>>>(pts, sc, n, g, counts, nullptr, bad);
     nl++;
   }
   msm_scan<<<1, 1024, 0, stream>>>(counts, m, offsets, cursor);
   if (gn) {
-    msm_digits<true><<<gn, 256, 0, stream>>>(pts, sc, n, g, cursor, entries);
+    msm_digits<true><<<gn, 256, 0, stream>>>(pts, sc, n, g, cursor, entries, nullptr);
     nl++;
   }
   msm_bucket_sum<<<(m + PTAU_BLOCK - 1) / PTAU_BLOCK, PTAU_BLOCK, 0, stream>>>(pts, entries, offsets, m, buckets);

@@ -19,7 +19,8 @@ cudaError_t launch_generate_win(int group, int fmt, const uint32_t* s0_mont, con
                                 const uint32_t* d_tbl, void* d_out, uint64_t first, uint64_t n, cudaStream_t stream);
 
 // sum_i [s_i] P_i over ARK_MONT_LIMBS G1 records and 32-byte LE scalars (< r) by the bucket method;
-// msm_g1_plan sizes the device scratch buffer (window width by n); result: one ARK_MONT_LIMBS record
+// msm_g1_plan sizes the device scratch buffer (window width by n); d_out (27 words): one ARK_MONT_LIMBS record and a
+// word that is non-zero when some scalar was >= r
 struct MsmPlan {
   int c, W, a, lgL;
   uint32_t NB;
@@ -40,6 +41,9 @@ cudaError_t launch_kzg_tables(const void* d_vk_g1, const void* d_vk_g2, void* d_
 cudaError_t launch_kzg_check(const void* d_vk_g1, const void* d_vk_g2, const void* d_comms, const void* d_points,
                              const void* d_values, const void* d_proofs, const void* d_random_v, const void* d_tbl,
                              uint64_t n, void* d_ok, cudaStream_t stream);
+
+// G2Prepared (ark-ec 0.2): n x 68 x 288 bytes of line coefficients + n infinity bytes
+cudaError_t launch_g2_prepare(const void* d_g2, uint64_t n, void* d_coeffs, void* d_infinity, cudaStream_t stream);
 
 cudaError_t launch_fq_op(int op, const void* d_a, const void* d_b, void* d_out, uint64_t n, cudaStream_t stream);
 

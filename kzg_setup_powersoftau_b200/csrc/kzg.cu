@@ -43,6 +43,21 @@ __global__ void __launch_bounds__(PTAU_PAIR_BLOCK) kzg_check_kernel(const uint32
               : 0;
 }
 
+// G2Prepared line coefficients, one point per thread
+__global__ void __launch_bounds__(PTAU_PAIR_BLOCK) g2_prepare_kernel(const uint32_t* __restrict__ g2, uint64_t n, uint32_t* __restrict__ coeffs,
+                                                                     uint8_t* __restrict__ infinity) {
+  const uint64_t i = (uint64_t)blockIdx.x * PTAU_PAIR_BLOCK + threadIdx.x;
+  if (i >= n) return;
+  infinity[i] = g2_prepare_item(g2 + i * 50, coeffs + i * (uint64_t)(PTAU_G2PREP_COEFFS * 72)) ? 1 : 0;
+}
+
+cudaError_t launch_g2_prepare(const void* d_g2, uint64_t n, void* d_coeffs, void* d_infinity, cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  g2_prepare_kernel<<<(unsigned)((n + PTAU_PAIR_BLOCK - 1) / PTAU_PAIR_BLOCK), PTAU_PAIR_BLOCK, 0, stream>>>(
+      (const uint32_t*)d_g2, n, (uint32_t*)d_coeffs, (uint8_t*)d_infinity);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_pairing_product2(const void* d_g1, const void* d_g2, uint64_t n, void* d_gt, void* d_is_one,
                                     cudaStream_t stream) {
   if (n == 0) return cudaSuccess;

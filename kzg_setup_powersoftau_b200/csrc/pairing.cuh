@@ -292,6 +292,52 @@ PTAU_HD_NOINLINE void addition_step(G2Hom& r, const Fq2& qx, const Fq2& qy, EllC
   co.c1 = fq2_neg(theta);
   co.c2 = lambda;
 }
+// G2Prepared of ark-ec 0.2 (`prepared_h`, `prepared_beta_h`: /root/reference/src/lib.rs:223-224,
+// src/bin/preprocess-kgz.rs:177-184): the 68 line-coefficient triples of the loop above, as ark keeps them in memory
+// (Montgomery limbs; triple t at out + 72 t words: c0 | c1 | c2, each c0-part then c1-part).  rec: one ARK_MONT_LIMBS G2
+// record.  A point at infinity has no coefficients (ark: empty vector, infinity = true): the slot is zero-filled.
+#define PTAU_G2PREP_COEFFS 68
+PTAU_HD_NOINLINE bool g2_prepare_item(const uint32_t* rec, uint32_t* out) {
+  G2Hom r;
+  Fq2 qx, qy;
+#pragma unroll
+  for (int i = 0; i < 12; i++) {
+    qx.c0.l[i] = rec[i];
+    qx.c1.l[i] = rec[12 + i];
+    qy.c0.l[i] = rec[24 + i];
+    qy.c1.l[i] = rec[36 + i];
+  }
+  if ((rec[48] & 0xffu) != 0) {
+#pragma unroll 1
+    for (int i = 0; i < PTAU_G2PREP_COEFFS * 72; i++) out[i] = 0;
+    return true;
+  }
+  r.x = qx;
+  r.y = qy;
+  r.z = fq2_one();
+  EllCoeff co;
+  int t = 0;
+#pragma unroll 1
+  for (int i = 62; i >= 0; --i) {
+#pragma unroll 1
+    for (int step = 0; step < 2; step++) {
+      if (step == 0)
+        doubling_step(r, co);
+      else if ((PTAU_Z_ABS >> i) & 1ull)
+        addition_step(r, qx, qy, co);
+      else
+        break;
+      const Fq* f[6] = {&co.c0.c0, &co.c0.c1, &co.c1.c0, &co.c1.c1, &co.c2.c0, &co.c2.c1};
+#pragma unroll 1
+      for (int k = 0; k < 6; k++)
+#pragma unroll
+        for (int j = 0; j < 12; j++) out[t * 72 + k * 12 + j] = f[k]->l[j];
+      t++;
+    }
+  }
+  return false;
+}
+
 // Fq6 times the sparse b0 + b1 v (5 Fq2 multiplications); r may alias a
 PTAU_HD_NOINLINE void fq6_mul_by_01(Fq6& r, const Fq6& a, const Fq2& b0, const Fq2& b1) {
   Fq2 v0 = fq2_mul(a.c0, b0), v1 = fq2_mul(a.c1, b1);

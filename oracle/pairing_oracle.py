@@ -242,3 +242,61 @@ def kzg_batch_check(vk, comms, points, values, proofs, randomizers) -> bool:
     total_c = _g1_sub(total_c, o.g1_mul(gamma_g, ggm))
     neg_w = None if total_w is None else (total_w[0], (-total_w[1]) % P)
     return product_of_pairings([(neg_w, beta_h), (total_c, h)]) == F12_ONE
+
+
+# ---- G2Prepared (ark-ec 0.2 models/bls12/g2.rs) ----------------------------------------------------------
+# [dagger recalled] `G2Prepared { ell_coeffs: Vec<(Fp2, Fp2, Fp2)>, infinity }` as the reference builds it with
+# `h.into()` / `beta_h.into()` (/root/reference/src/lib.rs:223-224, src/bin/preprocess-kgz.rs:177-184): homogeneous
+# projective doubling / addition steps over BitIteratorBE(|z|).skip(1), M-type twist coefficient order.  The exact
+# bytes can only be pinned against arkworks (rust/tests/golden.rs::shim_g2_prepare_equals_ark); what IS checked here
+# is that a Miller loop evaluated from these coefficients gives the pairing of the independent construction above.
+def g2_prepared_coeffs(q):
+    """-> (list of 68 (c0, c1, c2) Fq2 triples, infinity)"""
+    if q is None:
+        return [], True
+    two_inv = pow(2, -1, P)
+    A, S, M, Q = o.fq2_add, o.fq2_sub, o.fq2_mul, o.fq2_sqr
+    sc = lambda a, k: (a[0] * k % P, a[1] * k % P)
+    bt = (4, 4)
+    rx, ry, rz = q[0], q[1], (1, 0)
+    out = []
+    for i in range(62, -1, -1):
+        a = sc(M(rx, ry), two_inv)
+        b, c = Q(ry), Q(rz)
+        e = M(bt, sc(c, 3))
+        f = sc(e, 3)
+        g = sc(A(b, f), two_inv)
+        h = S(Q(A(ry, rz)), A(b, c))
+        ii = S(e, b)
+        j = Q(rx)
+        e2 = Q(e)
+        rx, ry, rz = M(a, S(b, f)), S(Q(g), sc(e2, 3)), M(b, h)
+        out.append((ii, sc(j, 3), o.fq2_neg(h)))
+        if (o.Z_ABS >> i) & 1:
+            theta = S(ry, M(q[1], rz))
+            lam = S(rx, M(q[0], rz))
+            c, d = Q(theta), Q(lam)
+            e = M(lam, d)
+            f = M(rz, c)
+            g = M(rx, d)
+            h = S(A(e, f), sc(g, 2))
+            rx, ry, rz = M(lam, h), S(M(theta, S(g, h)), M(e, ry)), M(rz, e)
+            out.append((S(M(theta, q[0]), M(lam, q[1])), o.fq2_neg(theta), lam))
+    return out, False
+
+
+def miller_from_prepared(coeffs, p) -> F12:
+    """Miller value of (p, Q) from Q's prepared coefficients: f <- f^2 * ell(c, p) ... with
+    ell = (c0 + c1 px v) + (c2 py v) w in the tower, i.e. c0 + c1 px w^2 + c2 py w^3 in the flat ring."""
+    def embed(c0, c1, c2):
+        a = f12_from_fq2(c0)
+        b = f12_mul(f12_from_fq2((c1[0] * p[0] % P, c1[1] * p[0] % P)), [0, 0, 1] + [0] * 9)
+        c = f12_mul(f12_from_fq2((c2[0] * p[1] % P, c2[1] * p[1] % P)), [0, 0, 0, 1] + [0] * 8)
+        return f12_add(f12_add(a, b), c)
+    f = F12_ONE
+    it = iter(coeffs)
+    for i in range(62, -1, -1):
+        f = f12_mul(f12_mul(f, f), embed(*next(it)))
+        if (o.Z_ABS >> i) & 1:
+            f = f12_mul(f, embed(*next(it)))
+    return f

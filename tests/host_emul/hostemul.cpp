@@ -118,6 +118,16 @@ extern "C" void hostemul_pairing_product2(const uint8_t* g1, const uint8_t* g2, 
     std::memcpy(gt_out + i * 576, gt, 576);
   }
 }
+// G2Prepared line coefficients (csrc/pairing.cuh: g2_prepare_item) on the host
+extern "C" void hostemul_g2_prepare(const uint8_t* g2, size_t n, uint8_t* coeffs_out, uint8_t* infinity) {
+  for (size_t i = 0; i < n; i++) {
+    uint32_t rec[50];
+    static uint32_t out[PTAU_G2PREP_COEFFS * 72];
+    std::memcpy(rec, g2 + i * 200, 200);
+    infinity[i] = g2_prepare_item(rec, out) ? 1 : 0;
+    std::memcpy(coeffs_out + i * sizeof(out), out, sizeof(out));
+  }
+}
 // use_tables != 0: fixed-base window tables for g, gamma_g, h (the path the library takes), else double-and-add
 extern "C" void hostemul_kzg_check(const uint8_t* vk_g1, const uint8_t* vk_g2, const uint8_t* comms, const uint8_t* points,
                                    const uint8_t* values, const uint8_t* proofs, const uint8_t* random_v, size_t n, uint8_t* ok,

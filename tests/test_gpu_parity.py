@@ -430,6 +430,56 @@ def test_random_batches_vs_c_oracle(ctx, cref):
         assert ctx.convert(g, AU, au_want, ZU, 0).tobytes() == zu_want
 
 
+def test_configs_1_and_2_input_from_the_c_oracle_2pow16(ctx, cref):
+    """BASELINE configs[1] / configs[2] at 2^16 points per group with input that does NOT come from the repository's
+    GPU generator: sections built by oracle/cpu_ref.c (6 x 64-bit Montgomery, its own scalar multiplication), expected
+    bytes by the same C code running the reference's algorithms (Algorithm-9 Fq2 sqrt, multiplication by r).  A field
+    bug shared by the GPU generator and the GPU decompressor cannot cancel here."""
+    n = 1 << 16
+    th = os.cpu_count() or 1
+    rnd = random.Random(0xC0FFEE)
+    tau, s0 = rnd.randrange(1, o.R_ORDER), rnd.randrange(1, o.R_ORDER)
+    for g in (1, 2):
+        zc = cref.generate(g, ZC, s0, tau, 5, n, th)
+        zu_want, st = cref.convert(g, ZC, zc, ZU, 0, th)
+        assert not any(st)
+        au_want, st = cref.convert(g, ZU, zu_want, AU, 4, th)
+        assert not any(st)
+        assert ctx.convert(g, ZC, zc, AU, STRICT).tobytes() == au_want            # configs[2]: fused compressed path
+        assert ctx.convert(g, ZC, zc, ZU, kz.CHECKS_DECOMPRESS).tobytes() == zu_want
+        assert ctx.convert(g, ZU, zu_want, AU, STRICT).tobytes() == au_want        # configs[1]: uncompressed path
+        # and the GPU generator against the independent one, at this size
+        assert ctx.generate(g, ZC, s0, tau, 5, n).tobytes() == zc
+
+
+def test_config5_known_tau_spot_check_2pow24(ctx):
+    """BASELINE configs[4] at 2^24 points per section, slab by slab on the device (generate -> fused compressed ->
+    strict -> ark), with 64 random indices per group compared with [s tau^i]G computed by the Python big-int oracle
+    (affine formulas, nothing shared with the CUDA field code), plus the boundary indices of every slab."""
+    import torch
+
+    n = 1 << 24
+    slab = 1 << 22
+    tau, alpha, _ = o.derive_scalars(0xB226)
+    dev = torch.device("cuda", 0)
+    d_in = torch.empty(slab * 96, dtype=torch.uint8, device=dev)
+    d_out = torch.empty(slab * 192, dtype=torch.uint8, device=dev)
+    status = torch.full((1,), -1, dtype=torch.int64, device=dev)
+    rnd = random.Random(24)
+    for g, s0, ro, enc, mul, gen in ((kz.G1, alpha, 96, o.ark_g1_serialize_uncompressed, o.g1_mul, o.G1_GEN),
+                                     (kz.G2, 1, 192, o.ark_g2_serialize_uncompressed, o.g2_mul, o.G2_GEN)):
+        picks = sorted(rnd.randrange(n) for _ in range(64))
+        for a in range(0, n, slab):
+            ctx.generate_device(g, ZC, s0, tau, a, slab, d_in.data_ptr())
+            ctx.convert_device(g, ZC, d_in.data_ptr(), AU, d_out.data_ptr(), slab, STRICT, status.data_ptr(), base_index=a)
+            torch.cuda.synchronize()
+            for i in [a, a + slab - 1] + [p for p in picks if a <= p < a + slab]:
+                got = bytes(d_out[(i - a) * ro:(i - a + 1) * ro].cpu().numpy())
+                want = enc(mul(gen, s0 * pow(tau, i, o.R_ORDER) % o.R_ORDER))
+                assert got == want, (g, i)
+    assert int(status.item()) == -1
+
+
 def test_generator_vs_oracles(ctx, cref):
     rnd = random.Random(5)
     tau, beta = rnd.randrange(1, o.R_ORDER), rnd.randrange(1, o.R_ORDER)
@@ -850,6 +900,29 @@ def test_kzg10_check_mirrors_reference_test(ctx, tmp_path):
     c0 = np.ascontiguousarray(comms[0])
     assert kz._ffi.lib().ptau_kzg_check(ctx._h, g1v.ctypes.data, g2v.ctypes.data, c0.ctypes.data, bad.ctypes.data, bad.ctypes.data,
                                         c0.ctypes.data, None, 1, ok.ctypes.data) == kz._ffi.ERR_ARG
+
+
+def test_g2_prepared_on_gpu(ctx):
+    """ptau_g2_prepare = ark-ec 0.2 G2Prepared::from (prepared_h / prepared_beta_h, src/lib.rs:223-224): the 68 line
+    coefficient triples per point against oracle/pairing_oracle.py, infinity, and the VerifierKey helpers."""
+    import pairing_oracle as po
+
+    pts = [o.g2_mul(o.G2_GEN, k) for k in (1, 3, 0xDEADBEEF)] + [None]
+    recs = np.frombuffer(b"".join(o.g2_mont_record((0, 0), (1, 0), True) if q is None else o.g2_mont_record(q[0], q[1], False)
+                                  for q in pts), dtype=np.uint8).reshape(-1, 200)
+    prep = kz.g2_prepare(recs, ctx=ctx)
+    rinv = pow(1 << 384, -1, o.P)
+    for q, pr in zip(pts, prep):
+        want, is_inf = po.g2_prepared_coeffs(q)
+        assert pr.infinity == is_inf and pr.ell_coeffs.shape[0] == len(want)
+        for t, w in enumerate(want):
+            blob = pr.ell_coeffs[t].tobytes()
+            vals = [int.from_bytes(blob[48 * k:48 * k + 48], "little") * rinv % o.P for k in range(6)]
+            assert ((vals[0], vals[1]), (vals[2], vals[3]), (vals[4], vals[5])) == w
+    g1 = np.frombuffer(o.g1_mont_record(o.G1_GEN[0], o.G1_GEN[1], False), dtype=np.uint8)
+    vk = kz.VerifierKey(g=g1, gamma_g=g1, h=recs[0], beta_h=recs[1])
+    assert vk.prepared_h(ctx).ell_coeffs.tobytes() == prep[0].ell_coeffs.tobytes()
+    assert vk.prepared_beta_h(ctx).ell_coeffs.tobytes() == prep[1].ell_coeffs.tobytes()
 
 
 def test_multi_gpu_sharding_is_invisible(cref):

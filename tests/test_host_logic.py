@@ -565,6 +565,37 @@ def _g2r(q):
     return o.g2_mont_record((0, 0), (1, 0), True) if q is None else o.g2_mont_record(q[0], q[1], False)
 
 
+def test_limb_g2_prepared_coefficients(hostemul):
+    """csrc/pairing.cuh g2_prepare_item (the G2Prepared of ark-ec 0.2: prepared_h / prepared_beta_h of src/lib.rs:223-224)
+    on the host against oracle/pairing_oracle.py g2_prepared_coeffs, and the oracle's coefficients against the pairing
+    itself: a Miller loop evaluated from them must give the same GT element as the independent construction."""
+    import pairing_oracle as po
+
+    pts = [o.g2_mul(o.G2_GEN, k) for k in (1, 7, 0xB200B200)] + [None]
+    recs = b"".join(_g2r(q) for q in pts)
+    out = ctypes.create_string_buffer(len(pts) * 68 * 288)
+    inf = ctypes.create_string_buffer(len(pts))
+    hostemul.hostemul_g2_prepare(recs, ctypes.c_size_t(len(pts)), out, inf)
+    assert inf.raw == b"\0\0\0\1"
+    rinv = pow(1 << 384, -1, o.P)
+    for i, q in enumerate(pts):
+        want, is_inf = po.g2_prepared_coeffs(q)
+        blob = out.raw[i * 68 * 288:(i + 1) * 68 * 288]
+        if is_inf:
+            assert blob == bytes(68 * 288) and want == []
+            continue
+        assert len(want) == 68
+        got = []
+        for t in range(68):
+            vals = [int.from_bytes(blob[t * 288 + 48 * k:t * 288 + 48 * k + 48], "little") * rinv % o.P for k in range(6)]
+            got.append(((vals[0], vals[1]), (vals[2], vals[3]), (vals[4], vals[5])))
+        assert got == want
+    # the coefficients define the pairing: e(P, Q) from prepared(Q) equals the oracle's own e(P, Q) (z < 0: inverse)
+    p1, q2 = o.g1_mul(o.G1_GEN, 5), pts[1]
+    f = po.miller_from_prepared(po.g2_prepared_coeffs(q2)[0], p1)
+    assert po.f12_pow(po.f12_inv(f), po.FINAL_EXP) == po.pairing(p1, q2)
+
+
 def test_limb_pairing_code_on_golden_vectors(hostemul):
     """tests/golden/pairing_vectors.json (made by tools/make_golden_pairing.py from the independent CPU pairing)
     against csrc/pairing.cuh compiled for the host: GT values of pairing products and KZG10::check booleans."""
