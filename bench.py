@@ -288,6 +288,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--log2-points", type=int, default=LOG2_POINTS, help="points per section of the headline workload")
     ap.add_argument("--no-extra", action="store_true", help="skip the non-headline legs (extra, config5, cpu_baseline)")
+    ap.add_argument("--no-legs", action="store_true", help="skip only the N=1 `extra` legs and the CPU baseline (keeps config5)")
     ap.add_argument("--workload", default="config3", choices=["config3", "config5"],
                     help="config3 = headline (BASELINE configs[2], config5 reported inside the same line); config5 = only "
                          "the 2^K-power setup, printed as its own line")
@@ -468,7 +469,7 @@ def main():
         extra = {}
         # the other kernels of the path, the whole-job legs and the CPU baseline are reported at N=1 only: under
         # torchrun the other ranks would sit in the closing barrier while rank 0 runs them
-        if not args.no_extra and world == 1:
+        if not args.no_extra and not args.no_legs and world == 1:
             def timed_leg(group, in_fmt, out_fmt, checks, din, dout, n, steps, warmup):
                 for _ in range(warmup):
                     launch(group, in_fmt, din, out_fmt, dout, n, checks, 0)
@@ -648,8 +649,8 @@ def main():
         try:
             if world > 1:
                 raise RuntimeError("cpu_baseline is measured at N=1 only")
-            if args.no_extra:
-                raise RuntimeError("--no-extra")
+            if args.no_extra or args.no_legs:
+                raise RuntimeError("--no-extra / --no-legs")
             rate1, _, _ = cpu_config3(1 << 8, 1)
             n_s = 1 << 10  # probe, then size the sample to ~15 s of host work
             rate, dt, _ = cpu_config3(n_s, threads)

@@ -90,28 +90,79 @@ PTAU_HD void jac_add(Jac<F>& p, const Jac<F>& q) {
 // |z| = 0xd201000000010000 = 2^63 + 2^62 + 2^60 + 2^57 + 2^48 + 2^16
 #define PTAU_Z_ABS 0xd201000000010000ull
 
-// The doubling of the ladders.  PTAU_G1_DBL_INLINE (device, Fq only) expands the seven
-// field multiplications in place instead of calling fq_mul / fq_sqr: no argument shuffles,
-// at the price of a ~40 KB loop body.
+// The doubling of the G1 ladders.  PTAU_G1_DBL_INLINE (device) expands the seven field multiplications in place
+// instead of calling fq_mul / fq_sqr: no argument shuffles, at the price of a ~45 KB loop body.
+//
+// Sums that only feed multiplications stay unreduced (fq_add_nored): the Montgomery product accepts operands up to
+// 3p (9 p^2 < p 2^384) and the dedicated squaring operands below 2^383, so X + B < 2p, 3A < 3p and Z3 = 2YZ < 2p need
+// no conditional subtraction.  Z stays in [0, 2p) across the ladder; it is only ever multiplied, squared or tested for
+// zero (2YZ = p is impossible for YZ < p, p odd).  Saves 100 of ~2900 instructions per doubling: the ladders are
+// bound by instruction issue as much as by the multiplier.  The host build runs the same formula (tests/host_emul).
 #if defined(__CUDA_ARCH__) && defined(PTAU_G1_DBL_INLINE)
+#define PTAU_LAD_MUL(a, b) fq_mul_inl(a, b)
+#define PTAU_LAD_SQR(a) fq_sqr_inl(a)
+#else
+#define PTAU_LAD_MUL(a, b) fq_mul(a, b)
+#define PTAU_LAD_SQR(a) fq_sqr(a)
+#endif
 PTAU_HD void jac_dbl_ladder(Jac<Fq>& p) {
-  Fq B = fq_sqr_inl(p.Y);
-  p.Z = fq_dbl(fq_mul_inl(p.Z, p.Y));
-  Fq C = fq_sqr_inl(B);
+#if !defined(PTAU_DBL_EAGER_ADDS) && !defined(PTAU_DBL_NO_SHARED_RED)
+  // dbl-2009-l with two of its seven Montgomery reductions shared (fqw.cuh): C = Y^4 is only ever used inside the
+  // sums D = 2((X+B)^2 - A - C) and Y3 = E (D - X3) - 8C, so it stays an unreduced 768-bit square and each sum is
+  // reduced once:  7 products + 6 reductions instead of 7 + 7 (1614 MADs instead of 1770).
+  //   (X+B)^2 - X^2 - B^2 = 2 X B exactly (the sum X + B is left unreduced), so that difference needs no sign fix;
+  //   E (D - X3) - 8C may be negative: fqw_sub_fix adds p 2^384, keeping the value below p 2^384 (E < 3p, 8C < 8p^2).
+  Fq B = PTAU_LAD_SQR(p.Y);
+  Fq zy = PTAU_LAD_MUL(p.Z, p.Y);
+  p.Z = fq_add_nored(zy, zy);
+  uint32_t wC[24], wA[24], wS[24];
+  fq_sqr_wide(wC, B);
+  Fq t = fq_add_nored(p.X, B);
+  fq_sqr_wide(wA, p.X);
+  fq_sqr_wide(wS, t);
+  fqw_sub(wS, wA);
+  fqw_sub(wS, wC);
+  Fq A = fq_redc(wA);
+  Fq D = fq_redc(wS);  // S - A - C
+  D = fq_dbl(D);
+  Fq E = fq_add_nored(fq_add_nored(A, A), A);
+  Fq Fv = PTAU_LAD_SQR(E);
+  p.X = fq_sub(Fv, fq_dbl(D));
+  fq_mul_wide(wS, fq_sub(D, p.X), E);
+  fqw_shl3(wC);
+  fqw_sub_fix(wS, wC);
+  p.Y = fq_redc(wS);
+#elif !defined(PTAU_DBL_EAGER_ADDS)
+  Fq B = PTAU_LAD_SQR(p.Y);
+  Fq zy = PTAU_LAD_MUL(p.Z, p.Y);
+  p.Z = fq_add_nored(zy, zy);
+  Fq C = PTAU_LAD_SQR(B);
+  Fq t = fq_add_nored(p.X, B);
+  Fq A = PTAU_LAD_SQR(p.X);
+  Fq D = PTAU_LAD_SQR(t);
+  D = fq_sub(fq_sub(D, A), C);
+  D = fq_dbl(D);
+  Fq E = fq_add_nored(fq_add_nored(A, A), A);
+  Fq Fv = PTAU_LAD_SQR(E);
+  p.X = fq_sub(Fv, fq_dbl(D));
+  C = fq_dbl(fq_dbl(fq_dbl(C)));
+  p.Y = fq_sub(PTAU_LAD_MUL(fq_sub(D, p.X), E), C);
+#else
+  Fq B = PTAU_LAD_SQR(p.Y);
+  p.Z = fq_dbl(PTAU_LAD_MUL(p.Z, p.Y));
+  Fq C = PTAU_LAD_SQR(B);
   Fq t = fq_add(p.X, B);
-  Fq A = fq_sqr_inl(p.X);
-  Fq D = fq_sqr_inl(t);
+  Fq A = PTAU_LAD_SQR(p.X);
+  Fq D = PTAU_LAD_SQR(t);
   D = fq_sub(fq_sub(D, A), C);
   D = fq_dbl(D);
   Fq E = fq_add(fq_dbl(A), A);
-  Fq Fv = fq_sqr_inl(E);
+  Fq Fv = PTAU_LAD_SQR(E);
   p.X = fq_sub(Fv, fq_dbl(D));
   C = fq_dbl(fq_dbl(fq_dbl(C)));
-  p.Y = fq_sub(fq_mul_inl(fq_sub(D, p.X), E), C);
-}
-#else
-PTAU_HD void jac_dbl_ladder(Jac<Fq>& p) { jac_dbl(p); }
+  p.Y = fq_sub(PTAU_LAD_MUL(fq_sub(D, p.X), E), C);
 #endif
+}
 PTAU_HD void jac_dbl_ladder(Jac<Fq2>& p) { jac_dbl(p); }
 
 // acc = [|z|] (x, y), affine base, mixed additions

@@ -369,12 +369,51 @@ PTAU_HD Fq fq_mul_inl(const Fq& a, const Fq& b) {
 #define PX_MADC_HI(r, a, b, c) do { r = emu::madhi(a, b, c, px_cf); px_cf = 0; } while (0)
 #endif
 
-// Montgomery square a*a/R mod p.  Same row structure as fq_mul_inl, but row i only
-// forms the products with limbs j >= i of the multiplicand
+// One reduction row with the window shift fused in.  On entry X is the previous even-aligned accumulator whose limb 0
+// has just been zeroed (limb 1 is the left-over at the new position 0); E0 is limb 0 of the new even-aligned
+// accumulator.  E0 += left-over; m = E0 * (-p^-1); X = (X >> 64) + m * (odd limbs of p) + tin W^10, carry chained from E0.
+PTAU_HD void row_red_odd_shift(uint32_t* X, uint32_t& E0, uint32_t& m, uint32_t tin) {
+#ifdef __CUDA_ARCH__
+  asm("add.cc.u32 %12, %12, %1;\n\t"
+      "mul.lo.u32 %13, %12, 0xfffcfffd;\n\t"
+      "madc.lo.cc.u32 %0, %13, " P1S ", %2;\n\t"
+      "madc.hi.cc.u32 %1, %13, " P1S ", %3;\n\t"
+      "madc.lo.cc.u32 %2, %13, " P3S ", %4;\n\t"
+      "madc.hi.cc.u32 %3, %13, " P3S ", %5;\n\t"
+      "madc.lo.cc.u32 %4, %13, " P5S ", %6;\n\t"
+      "madc.hi.cc.u32 %5, %13, " P5S ", %7;\n\t"
+      "madc.lo.cc.u32 %6, %13, " P7S ", %8;\n\t"
+      "madc.hi.cc.u32 %7, %13, " P7S ", %9;\n\t"
+      "madc.lo.cc.u32 %8, %13, " P9S ", %10;\n\t"
+      "madc.hi.cc.u32 %9, %13, " P9S ", %11;\n\t"
+      "madc.lo.cc.u32 %10, %13, " P11S ", %14;\n\t"
+      "madc.hi.cc.u32 %11, %13, " P11S ", 0;"
+      : "+r"(X[0]), "+r"(X[1]), "+r"(X[2]), "+r"(X[3]), "+r"(X[4]), "+r"(X[5]), "+r"(X[6]), "+r"(X[7]),
+        "+r"(X[8]), "+r"(X[9]), "+r"(X[10]), "+r"(X[11]), "+r"(E0), "=&r"(m)
+      : "r"(tin));
+#else
+  uint32_t cf = 0;
+  E0 = emu::addc(E0, X[1], cf);
+  m = E0 * PTAU_M0;
+  for (int j = 0; j < 10; j += 2) {
+    X[j] = emu::madlo(m, emu::PL[j + 1], X[j + 2], cf);
+    X[j + 1] = emu::madhi(m, emu::PL[j + 1], X[j + 3], cf);
+  }
+  X[10] = emu::madlo(m, emu::PL[11], tin, cf);
+  X[11] = emu::madhi(m, emu::PL[11], 0, cf);
+#endif
+}
+
+// Montgomery square a*a/R mod p.  Row i only forms the products with limbs j >= i of the multiplicand
 //     c(i) = a_i W^i + 2 * sum_{j>i} a_j W^j        (a^2 = sum_i a_i W^i c(i)),
-// i.e. 78 wide MADs for the product instead of 144; the 12 reduction rows are
-// unchanged.  Limbs of c(i): j == i -> a_i ; j == i+1 -> a_j << 1 ; j > i+1 ->
-// (a_j << 1) | (a_{j-1} >> 31).  a < 2^381 so nothing is shifted out of limb 11.
+// i.e. 78 wide MADs for the product instead of 144; the 12 reduction rows are unchanged.  Limbs of c(i):
+// j == i -> a_i ; j == i+1 -> a_j << 1 ; j > i+1 -> (a_j << 1) | (a_{j-1} >> 31).  a < 2^383 so nothing is shifted out
+// of limb 11.
+// Row order: the products of row i >= 1 sit at window positions >= i, so they do not touch position 0 and the
+// reduction of the row can run FIRST, fused with the one-limb shift of the window (row_red_odd_shift): every
+// position gets its shift from a reduction MAD and the product chains simply start at their first position.
+// (With the products first, the skipped low positions needed 60 add-with-carry instructions per squaring just to
+// move the window; the ladders are issue-bound, not multiplier-bound, so those were pure cost.)
 PTAU_HD Fq fq_sqr_inl(const Fq& a) {
   uint32_t ev[12], od[12];
   uint32_t c2[12], d1[12];
@@ -404,38 +443,37 @@ PTAU_HD Fq fq_sqr_inl(const Fq& a) {
 #pragma unroll
   for (int i = 1; i < 12; i++) {
     uint32_t* E = (i & 1) ? od : ev;  // even-aligned accumulator of this row
-    uint32_t* X = (i & 1) ? ev : od;  // odd-aligned (holds the previous even accumulator, to be shifted)
+    uint32_t* X = (i & 1) ? ev : od;  // odd-aligned (the previous even accumulator: limb 0 is zero, limb 1 the left-over)
     const uint32_t bi = a.l[i];
+    {  // reduction of this row, with the window shift
+      uint32_t m;
+      row_red_odd_shift(X, E[0], m, 0u);
+      row_red_even(E, X[11], m);
+    }
     PX_DECL;
-    // shift X down two limbs, absorb the left-over limb into E[0], add the odd-j products (j >= i)
-    PX_ADD_CC(E[0], E[0], X[1]);
+    // odd-j products (j >= i) into X[j-1], X[j]; the chain starts at the first such j
+    const int jo = (i & 1) ? i : i + 1;
+    if (jo <= 11) {
+      PX_MAD_LO_CC(X[jo - 1], SQ_M(i, jo), bi, X[jo - 1]);
+      PX_MADC_HI_CC(X[jo], SQ_M(i, jo), bi, X[jo]);
 #pragma unroll
-    for (int k = 0; k < 10; k += 2) {
-      if (k + 1 >= i) {
-        PX_MADC_LO_CC(X[k], SQ_M(i, k + 1), bi, X[k + 2]);
-        PX_MADC_HI_CC(X[k + 1], SQ_M(i, k + 1), bi, X[k + 3]);
-      } else {
-        PX_ADDC_CC(X[k], X[k + 2], 0u);
-        PX_ADDC_CC(X[k + 1], X[k + 3], 0u);
+      for (int j = jo + 2; j < 12; j += 2) {
+        PX_MADC_LO_CC(X[j - 1], SQ_M(i, j), bi, X[j - 1]);
+        PX_MADC_HI_CC(X[j], SQ_M(i, j), bi, X[j]);  // no carry leaves X[11] (bound on the window)
       }
     }
-    PX_MADC_LO_CC(X[10], SQ_M(i, 11), bi, 0u);
-    PX_MADC_HI_CC(X[11], SQ_M(i, 11), bi, 0u);  // carry-out is 0 by the bound; .cc lets lo/hi fuse into one IMAD.WIDE
-    // even-j products (j >= i); the chain starts at the first such j
-    const int j0 = (i & 1) ? i + 1 : i;
-    if (j0 <= 10) {
-      PX_MAD_LO_CC(E[j0], SQ_M(i, j0), bi, E[j0]);
-      PX_MADC_HI_CC(E[j0 + 1], SQ_M(i, j0), bi, E[j0 + 1]);
+    // even-j products (j >= i) into E[j], E[j+1]; the carry of the chain goes to window position 12 = X[11]
+    const int je = (i & 1) ? i + 1 : i;
+    if (je <= 10) {
+      PX_MAD_LO_CC(E[je], SQ_M(i, je), bi, E[je]);
+      PX_MADC_HI_CC(E[je + 1], SQ_M(i, je), bi, E[je + 1]);
 #pragma unroll
-      for (int j = j0 + 2; j < 12; j += 2) {
+      for (int j = je + 2; j < 12; j += 2) {
         PX_MADC_LO_CC(E[j], SQ_M(i, j), bi, E[j]);
         PX_MADC_HI_CC(E[j + 1], SQ_M(i, j), bi, E[j + 1]);
       }
       PX_ADDC(X[11], X[11], 0u);
     }
-    uint32_t m = E[0] * PTAU_M0;
-    row_red_odd(X, m);
-    row_red_even(E, X[11], m);
   }
 #undef SQ_M
   // last row (i = 11) had E = od, X = ev: result = ev + (od >> 32)

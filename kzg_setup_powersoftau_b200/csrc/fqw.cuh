@@ -148,6 +148,12 @@ PTAU_HD void fqw_sub(uint32_t* a, const uint32_t* b) {
   for (int i = 1; i < 23; i++) PX_SUBC_CC(a[i], a[i], b[i]);
   PX_SUBC(a[23], a[23], b[23]);
 }
+// a <<= 3 over 24 limbs (the caller guarantees a < 2^765)
+PTAU_HD void fqw_shl3(uint32_t* a) {
+#pragma unroll
+  for (int i = 23; i > 0; i--) a[i] = (a[i] << 3) | (a[i - 1] >> 29);
+  a[0] <<= 3;
+}
 // a = a - b + (a < b ? p * 2^384 : 0): the difference of two products, made non-negative (< p * 2^384)
 PTAU_HD void fqw_sub_fix(uint32_t* a, const uint32_t* b) {
   const uint32_t pl[12] = PTAU_P_LIMBS;
@@ -166,41 +172,6 @@ PTAU_HD void fqw_sub_fix(uint32_t* a, const uint32_t* b) {
     for (int i = 1; i < 11; i++) PX_ADDC_CC(a[12 + i], a[12 + i], pl[i] & mask);
     PX_ADDC(a[23], a[23], pl[11] & mask);
   }
-}
-
-// One reduction row with the window shift fused in.  On entry X is the previous even-aligned accumulator whose limb 0
-// has just been zeroed (limb 1 is the left-over at the new position 0); E0 is limb 0 of the new even-aligned
-// accumulator.  E0 += left-over; m = E0 * (-p^-1); X = (X >> 64) + m * (odd limbs of p) + tin W^10, carry chained from E0.
-PTAU_HD void row_red_odd_shift(uint32_t* X, uint32_t& E0, uint32_t& m, uint32_t tin) {
-#ifdef __CUDA_ARCH__
-  asm("add.cc.u32 %12, %12, %1;\n\t"
-      "mul.lo.u32 %13, %12, 0xfffcfffd;\n\t"
-      "madc.lo.cc.u32 %0, %13, " P1S ", %2;\n\t"
-      "madc.hi.cc.u32 %1, %13, " P1S ", %3;\n\t"
-      "madc.lo.cc.u32 %2, %13, " P3S ", %4;\n\t"
-      "madc.hi.cc.u32 %3, %13, " P3S ", %5;\n\t"
-      "madc.lo.cc.u32 %4, %13, " P5S ", %6;\n\t"
-      "madc.hi.cc.u32 %5, %13, " P5S ", %7;\n\t"
-      "madc.lo.cc.u32 %6, %13, " P7S ", %8;\n\t"
-      "madc.hi.cc.u32 %7, %13, " P7S ", %9;\n\t"
-      "madc.lo.cc.u32 %8, %13, " P9S ", %10;\n\t"
-      "madc.hi.cc.u32 %9, %13, " P9S ", %11;\n\t"
-      "madc.lo.cc.u32 %10, %13, " P11S ", %14;\n\t"
-      "madc.hi.cc.u32 %11, %13, " P11S ", 0;"
-      : "+r"(X[0]), "+r"(X[1]), "+r"(X[2]), "+r"(X[3]), "+r"(X[4]), "+r"(X[5]), "+r"(X[6]), "+r"(X[7]),
-        "+r"(X[8]), "+r"(X[9]), "+r"(X[10]), "+r"(X[11]), "+r"(E0), "=&r"(m)
-      : "r"(tin));
-#else
-  uint32_t cf = 0;
-  E0 = emu::addc(E0, X[1], cf);
-  m = E0 * PTAU_M0;
-  for (int j = 0; j < 10; j += 2) {
-    X[j] = emu::madlo(m, emu::PL[j + 1], X[j + 2], cf);
-    X[j + 1] = emu::madhi(m, emu::PL[j + 1], X[j + 3], cf);
-  }
-  X[10] = emu::madlo(m, emu::PL[11], tin, cf);
-  X[11] = emu::madhi(m, emu::PL[11], 0, cf);
-#endif
 }
 
 // Montgomery reduction: T / 2^384 mod p for T = t[0..23] < p * 2^384; result < p.
