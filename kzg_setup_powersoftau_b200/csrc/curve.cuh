@@ -99,7 +99,7 @@ PTAU_HD void jac_add(Jac<F>& p, const Jac<F>& q) {
 // zero (2YZ = p is impossible for YZ < p, p odd).  Saves 100 of ~2900 instructions per doubling: the ladders are
 // bound by instruction issue as much as by the multiplier.  The host build runs the same formula (tests/host_emul).
 #if defined(__CUDA_ARCH__) && defined(PTAU_G1_DBL_INLINE)
-#define PTAU_LAD_MUL(a, b) fq_mul_inl(a, b)
+#define PTAU_LAD_MUL(a, b) PTAU_FQ_MUL_IMPL(a, b)
 #define PTAU_LAD_SQR(a) fq_sqr_inl(a)
 #else
 #define PTAU_LAD_MUL(a, b) fq_mul(a, b)
@@ -163,7 +163,26 @@ PTAU_HD void jac_dbl_ladder(Jac<Fq>& p) {
   p.Y = fq_sub(PTAU_LAD_MUL(fq_sub(D, p.X), E), C);
 #endif
 }
+#if defined(__CUDA_ARCH__) && defined(PTAU_G2_DBL_INLINE)
+// experiment: the G2 doubling with its seven Fq2 multiplications expanded in place (A/B knob)
+PTAU_HD void jac_dbl_ladder(Jac<Fq2>& p) {
+  Fq2 B = fq2_sqr_inl(p.Y);
+  p.Z = fq2_dbl(fq2_mul_inl(p.Z, p.Y));
+  Fq2 C = fq2_sqr_inl(B);
+  Fq2 t = fq2_add(p.X, B);
+  Fq2 A = fq2_sqr_inl(p.X);
+  Fq2 D = fq2_sqr_inl(t);
+  D = fq2_sub(fq2_sub(D, A), C);
+  D = fq2_dbl(D);
+  Fq2 E = fq2_add(fq2_dbl(A), A);
+  Fq2 Fv = fq2_sqr_inl(E);
+  p.X = fq2_sub(Fv, fq2_dbl(D));
+  C = fq2_dbl(fq2_dbl(fq2_dbl(C)));
+  p.Y = fq2_sub(fq2_mul_inl(fq2_sub(D, p.X), E), C);
+}
+#else
 PTAU_HD void jac_dbl_ladder(Jac<Fq2>& p) { jac_dbl(p); }
+#endif
 
 // acc = [|z|] (x, y), affine base, mixed additions
 template <class F>

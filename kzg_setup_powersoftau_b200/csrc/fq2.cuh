@@ -12,11 +12,16 @@
 
 namespace ptau {
 
+#ifdef PTAU_MUL_K_EAGER
+#define PTAU_FQ_MUL_IMPL(a, b) fq_mul_kr(a, b)
+#else
+#define PTAU_FQ_MUL_IMPL(a, b) fq_mul_inl(a, b)
+#endif
 #ifdef __CUDA_ARCH__
-__device__ __noinline__ Fq fq_mul(Fq a, Fq b) { return fq_mul_inl(a, b); }
+__device__ __noinline__ Fq fq_mul(Fq a, Fq b) { return PTAU_FQ_MUL_IMPL(a, b); }
 __device__ __noinline__ Fq fq_sqr(Fq a) { return fq_sqr_inl(a); }
 #else
-inline Fq fq_mul(const Fq& a, const Fq& b) { return fq_mul_inl(a, b); }
+inline Fq fq_mul(const Fq& a, const Fq& b) { return PTAU_FQ_MUL_IMPL(a, b); }
 inline Fq fq_sqr(const Fq& a) { return fq_sqr_inl(a); }
 #endif
 
@@ -72,7 +77,7 @@ PTAU_HD bool fq2_eq(const Fq2& a, const Fq2& b) { return fq_eq(a.c0, b.c0) && fq
 // PTAU_FQ2_LEAF (device): expand the Fq multiplications inside fq2_mul / fq2_sqr so that
 // they are leaf functions (one call level, no nested argument shuffles).
 #if defined(__CUDA_ARCH__) && defined(PTAU_FQ2_LEAF)
-#define PTAU_FQ2_M(a, b) fq_mul_inl(a, b)
+#define PTAU_FQ2_M(a, b) PTAU_FQ_MUL_IMPL(a, b)
 #else
 #define PTAU_FQ2_M(a, b) fq_mul(a, b)
 #endif

@@ -38,7 +38,7 @@ PTAU_HD Fq fq_add_nored(const Fq& a, const Fq& b) {
 
 // t[0..23] = a * b.  Same rows as fq_mul_inl without the reduction rows: after row i the lowest limb of the
 // even-aligned accumulator is limb i of the product.
-PTAU_HD void fq_mul_wide(uint32_t* t, const Fq& a, const Fq& b) {
+PTAU_HD void fq_mul_wide_plain(uint32_t* t, const Fq& a, const Fq& b) {
   uint32_t ev[12], od[12];
 #pragma unroll
   for (int j = 0; j < 12; j += 2) {
@@ -65,6 +65,121 @@ PTAU_HD void fq_mul_wide(uint32_t* t, const Fq& a, const Fq& b) {
 #pragma unroll
     for (int k = 1; k < 11; k++) PX_ADDC_CC(t[12 + k], ev[k], od[k + 1]);
     PX_ADDC(t[23], ev[11], 0u);
+  }
+}
+
+// ---- one level of Karatsuba on the 12 x 12 limb product -------------------------------------------------------------
+// a = aL + aH W^6, b = bL + bH W^6:  a b = PL + (PM - PL - PH) W^6 + PH W^12 with PL = aL bL, PH = aH bH and
+// PM = (aL + aH)(bL + bH): three 6 x 6 products = 108 wide MADs instead of 144.  The kernels are bound by the
+// multiplier pipe (a wide MAD occupies it for 4 cycles per warp, an add issues in 1), so ~100 extra additions for 36
+// fewer MADs is a gain.  The half sums are 6 limbs + a carry bit; the carry bits are folded in as masked additions.
+//
+// t[0..11] = x * y for 6-limb x, y: the even/odd rows of fq_mul_wide at half width.
+PTAU_HD void mul6_wide(uint32_t* t, const uint32_t* x, const uint32_t* y) {
+  uint32_t ev[6], od[6];
+#pragma unroll
+  for (int j = 0; j < 6; j += 2) {
+    uint64_t t0 = (uint64_t)x[j] * y[0];
+    uint64_t t1 = (uint64_t)x[j + 1] * y[0];
+    ev[j] = (uint32_t)t0;
+    ev[j + 1] = (uint32_t)(t0 >> 32);
+    od[j] = (uint32_t)t1;
+    od[j + 1] = (uint32_t)(t1 >> 32);
+  }
+  t[0] = ev[0];
+#pragma unroll
+  for (int i = 1; i < 6; i++) {
+    uint32_t* E = (i & 1) ? od : ev;
+    uint32_t* X = (i & 1) ? ev : od;
+    const uint32_t bi = y[i];
+    PX_DECL;
+    PX_ADD_CC(E[0], E[0], X[1]);
+    PX_MADC_LO_CC(X[0], x[1], bi, X[2]);
+    PX_MADC_HI_CC(X[1], x[1], bi, X[3]);
+    PX_MADC_LO_CC(X[2], x[3], bi, X[4]);
+    PX_MADC_HI_CC(X[3], x[3], bi, X[5]);
+    PX_MADC_LO_CC(X[4], x[5], bi, 0u);
+    PX_MADC_HI_CC(X[5], x[5], bi, 0u);  // the window value stays below W^7: nothing leaves X[5]
+    PX_MAD_LO_CC(E[0], x[0], bi, E[0]);
+    PX_MADC_HI_CC(E[1], x[0], bi, E[1]);
+    PX_MADC_LO_CC(E[2], x[2], bi, E[2]);
+    PX_MADC_HI_CC(E[3], x[2], bi, E[3]);
+    PX_MADC_LO_CC(E[4], x[4], bi, E[4]);
+    PX_MADC_HI_CC(E[5], x[4], bi, E[5]);
+    PX_ADDC(X[5], X[5], 0u);
+    t[i] = E[0];
+  }
+  {  // last row had E = od, X = ev: high half = ev + (od >> 32)
+    PX_DECL;
+    PX_ADD_CC(t[6], ev[0], od[1]);
+#pragma unroll
+    for (int k = 1; k < 5; k++) PX_ADDC_CC(t[6 + k], ev[k], od[k + 1]);
+    PX_ADDC(t[11], ev[5], 0u);
+  }
+}
+
+// t[0..23] = a * b by one level of Karatsuba (a, b any 384-bit values)
+PTAU_HD void fq_mul_wide_k(uint32_t* t, const Fq& a, const Fq& b) {
+  uint32_t sa[6], sb[6], ca, cb;
+  {
+    PX_DECL;
+    PX_ADD_CC(sa[0], a.l[0], a.l[6]);
+#pragma unroll
+    for (int i = 1; i < 6; i++) PX_ADDC_CC(sa[i], a.l[i], a.l[6 + i]);
+    PX_ADDC(ca, 0u, 0u);
+  }
+  {
+    PX_DECL;
+    PX_ADD_CC(sb[0], b.l[0], b.l[6]);
+#pragma unroll
+    for (int i = 1; i < 6; i++) PX_ADDC_CC(sb[i], b.l[i], b.l[6 + i]);
+    PX_ADDC(cb, 0u, 0u);
+  }
+  uint32_t m[13];
+  mul6_wide(t, a.l, b.l);            // PL -> t[0..11]
+  mul6_wide(t + 12, a.l + 6, b.l + 6);  // PH -> t[12..23]
+  mul6_wide(m, sa, sb);              // low 12 limbs of PM
+  {  // + (ca ? sb : 0) W^6 + (cb ? sa : 0) W^6 + (ca & cb) W^12
+    const uint32_t ma = 0u - ca, mb = 0u - cb;
+    uint32_t c1, c2;
+    {
+      PX_DECL;
+      PX_ADD_CC(m[6], m[6], sb[0] & ma);
+#pragma unroll
+      for (int i = 1; i < 6; i++) PX_ADDC_CC(m[6 + i], m[6 + i], sb[i] & ma);
+      PX_ADDC(c1, 0u, 0u);
+    }
+    {
+      PX_DECL;
+      PX_ADD_CC(m[6], m[6], sa[0] & mb);
+#pragma unroll
+      for (int i = 1; i < 6; i++) PX_ADDC_CC(m[6 + i], m[6 + i], sa[i] & mb);
+      PX_ADDC(c2, 0u, 0u);
+    }
+    m[12] = c1 + c2 + (ca & cb);
+  }
+  {  // PM - PL - PH >= 0 (13 limbs)
+    PX_DECL;
+    PX_SUB_CC(m[0], m[0], t[0]);
+#pragma unroll
+    for (int i = 1; i < 12; i++) PX_SUBC_CC(m[i], m[i], t[i]);
+    PX_SUBC(m[12], m[12], 0u);
+  }
+  {
+    PX_DECL;
+    PX_SUB_CC(m[0], m[0], t[12]);
+#pragma unroll
+    for (int i = 1; i < 12; i++) PX_SUBC_CC(m[i], m[i], t[12 + i]);
+    PX_SUBC(m[12], m[12], 0u);
+  }
+  {  // t += middle * W^6 (no carry leaves limb 23: the total is a * b < 2^768)
+    PX_DECL;
+    PX_ADD_CC(t[6], t[6], m[0]);
+#pragma unroll
+    for (int i = 1; i < 13; i++) PX_ADDC_CC(t[6 + i], t[6 + i], m[i]);
+#pragma unroll
+    for (int i = 19; i < 23; i++) PX_ADDC_CC(t[i], t[i], 0u);
+    PX_ADDC(t[23], t[23], 0u);
   }
 }
 
@@ -131,6 +246,19 @@ PTAU_HD void fq_sqr_wide(uint32_t* t, const Fq& a) {
     for (int k = 1; k < 11; k++) PX_ADDC_CC(t[12 + k], ev[k], od[k + 1]);
     PX_ADDC(t[23], ev[11], 0u);
   }
+}
+
+// the wide product the rest of the code uses
+PTAU_HD void fq_mul_wide(uint32_t* t, const Fq& a, const Fq& b) {
+  // Measured on B200 (profiles/r02_ab_karatsuba.log): the Karatsuba product saves 25 % of the MADs of a wide product
+  // and makes every kernel slower or no faster (G2 compressed 77.6 -> 79.8 ms per 2^20 points) -- at two warps per
+  // scheduler the extra dependent carry chains cost more latency than the multiplier pipe gains.  Kept (and
+  // tested on the host) as an opt-in.
+#ifdef PTAU_KARATSUBA
+  fq_mul_wide_k(t, a, b);
+#else
+  fq_mul_wide_plain(t, a, b);
+#endif
 }
 
 // a += b, a -= b over 24 limbs (callers guarantee no carry / borrow out, except fqw_sub_fix)
@@ -211,6 +339,14 @@ PTAU_HD Fq fq_redc(const uint32_t* t) {
 #pragma unroll
   for (int i = 0; i < 12; i++) r.l[i] = ev[i];
   return r;
+}
+
+// Montgomery product as Karatsuba wide product + separate reduction (264 MADs instead of the 300 of the interleaved
+// fq_mul_inl, ~90 more additions): PTAU_MUL_K_EAGER routes the reduced multiplications through it.
+PTAU_HD Fq fq_mul_kr(const Fq& a, const Fq& b) {
+  uint32_t t[24];
+  fq_mul_wide_k(t, a, b);
+  return fq_redc(t);
 }
 
 }  // namespace ptau

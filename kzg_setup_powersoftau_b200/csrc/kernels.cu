@@ -46,17 +46,54 @@ __device__ __forceinline__ uint4 ld_stream(const uint4* p) {
   return v;
 }
 
-// global -> shared, nwords u32 words (block-cooperative, 128-bit where possible)
-template <int BLK>
-__device__ __forceinline__ void stage_in(const uint32_t* __restrict__ g, uint32_t* sm, int nwords) {
-  int nvec = nwords >> 2;
-  const uint4* g4 = reinterpret_cast<const uint4*>(g);
-  uint4* s4 = reinterpret_cast<uint4*>(sm);
-  for (int i = threadIdx.x; i < nvec; i += BLK) s4[i] = ld_stream(g4 + i);
-  for (int i = (nvec << 2) + threadIdx.x; i < nwords; i += BLK) sm[i] = g[i];
+// Shared-memory stride of a record of W words.  Each thread reads / writes its own record with 128-bit accesses, which a
+// warp performs in quarter-warps: conflict-free iff (stride / 4) is odd.  24- and 48-word records get one vector of
+// padding (28, 52); 12-word records are fine; the 26- / 50-word Montgomery records (8-byte granular) are left alone.
+__host__ __device__ constexpr int smem_stride(int w) { return (w % 4 == 0 && ((w / 4) % 2) == 0) ? w + 4 : w; }
+
+// global -> shared: record r of W words lands at sm + r * S (block-cooperative, coalesced 128-bit global accesses)
+template <int BLK, int W, int S>
+__device__ __forceinline__ void stage_in(const uint32_t* __restrict__ g, uint32_t* sm, int nrec) {
+  if (W % 4 == 0) {
+    constexpr int VPR = W / 4;
+    const uint4* g4 = reinterpret_cast<const uint4*>(g);
+    uint4* s4 = reinterpret_cast<uint4*>(sm);
+    const int nvec = nrec * VPR;
+    for (int i = threadIdx.x; i < nvec; i += BLK) {
+      const int r = i / VPR, c = i - r * VPR;
+      s4[r * (S / 4) + c] = ld_stream(g4 + i);
+    }
+  } else {  // S == W: flat copy
+    const int nwords = nrec * W, nvec = nwords >> 2;
+    const uint4* g4 = reinterpret_cast<const uint4*>(g);
+    uint4* s4 = reinterpret_cast<uint4*>(sm);
+    for (int i = threadIdx.x; i < nvec; i += BLK) s4[i] = ld_stream(g4 + i);
+    for (int i = (nvec << 2) + threadIdx.x; i < nwords; i += BLK) sm[i] = g[i];
+  }
 }
+template <int BLK, int W, int S>
+__device__ __forceinline__ void stage_out(uint32_t* __restrict__ g, const uint32_t* sm, int nrec) {
+  if (W % 4 == 0) {
+    constexpr int VPR = W / 4;
+    uint4* g4 = reinterpret_cast<uint4*>(g);
+    const uint4* s4 = reinterpret_cast<const uint4*>(sm);
+    const int nvec = nrec * VPR;
+    for (int i = threadIdx.x; i < nvec; i += BLK) {
+      const int r = i / VPR, c = i - r * VPR;
+      g4[i] = s4[r * (S / 4) + c];
+    }
+  } else {
+    const int nwords = nrec * W, nvec = nwords >> 2;
+    uint4* g4 = reinterpret_cast<uint4*>(g);
+    const uint4* s4 = reinterpret_cast<const uint4*>(sm);
+    for (int i = threadIdx.x; i < nvec; i += BLK) g4[i] = s4[i];
+    for (int i = (nvec << 2) + threadIdx.x; i < nwords; i += BLK) g[i] = sm[i];
+  }
+}
+
+// shared -> global, flat (the generators: records written at their natural stride)
 template <int BLK>
-__device__ __forceinline__ void stage_out(uint32_t* __restrict__ g, const uint32_t* sm, int nwords) {
+__device__ __forceinline__ void stage_out_flat(uint32_t* __restrict__ g, const uint32_t* sm, int nwords) {
   int nvec = nwords >> 2;
   uint4* g4 = reinterpret_cast<uint4*>(g);
   const uint4* s4 = reinterpret_cast<const uint4*>(sm);
@@ -64,38 +101,43 @@ __device__ __forceinline__ void stage_out(uint32_t* __restrict__ g, const uint32
   for (int i = (nvec << 2) + threadIdx.x; i < nwords; i += BLK) g[i] = sm[i];
 }
 
-// shared memory of one block: the record staging buffer (BLK x max(record_in, record_out)) and, for the G2 kernels
+// shared memory of one block: the record staging buffer (BLK x max(stride_in, stride_out)) and, for the G2 kernels
 // with curve checks, the operand file of the subgroup ladder (48 words per thread, transposed: conflict-free)
 template <int G, int INFMT, int OUTFMT, bool HEAVY>
 constexpr int convert_smem_words() {
   constexpr int BLK = G == PTAU_G1 ? PTAU_BLOCK_G1 : PTAU_BLOCK_G2;
-  constexpr int WIN = record_bytes(G, INFMT) / 4;
-  constexpr int WOUT = record_bytes(G, OUTFMT) / 4;
-  return BLK * (WIN > WOUT ? WIN : WOUT) + ((G == PTAU_G2 && HEAVY) ? BLK * 48 : 0);
+  constexpr int SIN = smem_stride(record_bytes(G, INFMT) / 4);
+  constexpr int SOUT = smem_stride(record_bytes(G, OUTFMT) / 4);
+  return BLK * (SIN > SOUT ? SIN : SOUT) + ((G == PTAU_G2 && HEAVY) ? BLK * 48 : 0);
 }
 
+// blocks per SM of the kernels without curve checks (memory-bound; A/B on B200: 2, 6 and 8 give the same 5.76-5.78 TB/s)
+#ifndef PTAU_MINBLOCKS_LIGHT
+#define PTAU_MINBLOCKS_LIGHT 2
+#endif
 template <int G, int INFMT, int OUTFMT, bool HEAVY>
-__global__ void __launch_bounds__((G == PTAU_G1 ? PTAU_BLOCK_G1 : PTAU_BLOCK_G2), (G == PTAU_G1 ? PTAU_MINBLOCKS_G1 : PTAU_MINBLOCKS_G2))
+__global__ void __launch_bounds__((G == PTAU_G1 ? PTAU_BLOCK_G1 : PTAU_BLOCK_G2),
+                                  (!HEAVY ? PTAU_MINBLOCKS_LIGHT : G == PTAU_G1 ? PTAU_MINBLOCKS_G1 : PTAU_MINBLOCKS_G2))
     convert_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint64_t n, uint32_t checks,
                    uint64_t base_index, unsigned long long* __restrict__ status) {
   constexpr int BLK = G == PTAU_G1 ? PTAU_BLOCK_G1 : PTAU_BLOCK_G2;
   constexpr int WIN = record_bytes(G, INFMT) / 4;
   constexpr int WOUT = record_bytes(G, OUTFMT) / 4;
-  constexpr int WMAX = WIN > WOUT ? WIN : WOUT;
-  constexpr bool PARK = G == PTAU_G2 && HEAVY;
+  constexpr int SIN = smem_stride(WIN), SOUT = smem_stride(WOUT);
+  constexpr int SMAX = SIN > SOUT ? SIN : SOUT;
   extern __shared__ __align__(16) uint32_t sm[];
 
   const uint64_t rec0 = (uint64_t)blockIdx.x * BLK;
   const int nrec = (int)((n - rec0) < (uint64_t)BLK ? (n - rec0) : (uint64_t)BLK);
   const int tid = threadIdx.x;
 
-  stage_in<BLK>(in + rec0 * WIN, sm, nrec * WIN);
+  stage_in<BLK, WIN, SIN>(in + rec0 * WIN, sm, nrec);
   __syncthreads();
 
   uint32_t win[WIN];
   if (tid < nrec) {
     if (WIN % 4 == 0) {
-      const uint4* s4 = reinterpret_cast<const uint4*>(sm + tid * WIN);
+      const uint4* s4 = reinterpret_cast<const uint4*>(sm + tid * SIN);
 #pragma unroll
       for (int j = 0; j < WIN / 4; j++) {
         uint4 v = s4[j];
@@ -105,7 +147,7 @@ __global__ void __launch_bounds__((G == PTAU_G1 ? PTAU_BLOCK_G1 : PTAU_BLOCK_G2)
         win[4 * j + 3] = v.w;
       }
     } else {  // Montgomery-limb records: 104 / 200 bytes, 8-byte granular
-      const uint2* s2 = reinterpret_cast<const uint2*>(sm + tid * WIN);
+      const uint2* s2 = reinterpret_cast<const uint2*>(sm + tid * SIN);
 #pragma unroll
       for (int j = 0; j < WIN / 2; j++) {
         uint2 v = s2[j];
@@ -118,23 +160,35 @@ __global__ void __launch_bounds__((G == PTAU_G1 ? PTAU_BLOCK_G1 : PTAU_BLOCK_G2)
 
   if (tid < nrec) {
     uint32_t st;
-    if (G == PTAU_G2) {
+    if (G == PTAU_G2 && HEAVY) {
       // every input record is in registers now: the thread's slot of the staging buffer takes the output record
       // directly (written before the subgroup ladder starts), and the ladder's base point lives in the operand file
       Park<BLK> pk;
-      pk.base = (uint32_t)__cvta_generic_to_shared(sm + (PARK ? BLK * WMAX : 0) + tid);  // !PARK: never touched
-      st = g2_process<INFMT, HEAVY, BLK>(win, OUTFMT, sm + tid * WOUT, checks, pk);
+      pk.base = (uint32_t)__cvta_generic_to_shared(sm + BLK * SMAX + tid);
+      st = g2_process<INFMT, HEAVY, BLK>(win, OUTFMT, sm + tid * SOUT, checks, pk);
     } else {
       uint32_t wout[WOUT];
-      st = g1_process<INFMT, HEAVY>(win, OUTFMT, wout, checks);
-      uint2* s2 = reinterpret_cast<uint2*>(sm + tid * WOUT);
+      if (G == PTAU_G2) {
+        Park<BLK> pk;
+        pk.base = 0;  // no ladder in this instance: never touched
+        st = g2_process<INFMT, HEAVY, BLK>(win, OUTFMT, wout, checks, pk);
+      } else {
+        st = g1_process<INFMT, HEAVY>(win, OUTFMT, wout, checks);
+      }
+      if (WOUT % 4 == 0) {
+        uint4* s4 = reinterpret_cast<uint4*>(sm + tid * SOUT);
 #pragma unroll
-      for (int j = 0; j < WOUT / 2; j++) s2[j] = make_uint2(wout[2 * j], wout[2 * j + 1]);
+        for (int j = 0; j < WOUT / 4; j++) s4[j] = make_uint4(wout[4 * j], wout[4 * j + 1], wout[4 * j + 2], wout[4 * j + 3]);
+      } else {
+        uint2* s2 = reinterpret_cast<uint2*>(sm + tid * SOUT);
+#pragma unroll
+        for (int j = 0; j < WOUT / 2; j++) s2[j] = make_uint2(wout[2 * j], wout[2 * j + 1]);
+      }
     }
     if (st != PTAU_OK) atomicMin(status, (unsigned long long)(((base_index + rec0 + tid) << 8) | st));
   }
   __syncthreads();
-  stage_out<BLK>(out + rec0 * WOUT, sm, nrec * WOUT);
+  stage_out<BLK, WOUT, SOUT>(out + rec0 * WOUT, sm, nrec);
 }
 
 template <int G, int INFMT, int OUTFMT, bool HEAVY>
@@ -314,7 +368,7 @@ __global__ void __launch_bounds__(PTAU_BLOCK)
     }
   }
   __syncthreads();
-  stage_out<PTAU_BLOCK>(out + rec0 * WOUT, sm, nrec * WOUT);
+  stage_out_flat<PTAU_BLOCK>(out + rec0 * WOUT, sm, nrec * WOUT);
 }
 
 cudaError_t launch_generate(int group, int fmt, const uint32_t* d_scalars, void* d_out, uint64_t n,
@@ -556,7 +610,7 @@ __global__ void __launch_bounds__(PTAU_BLOCK)
     __syncthreads();
     if (rec0 < n) {
       const int nrec = (int)((n - rec0) < (uint64_t)PTAU_BLOCK ? (n - rec0) : (uint64_t)PTAU_BLOCK);
-      stage_out<PTAU_BLOCK>(out + rec0 * WOUT, sm, nrec * WOUT);
+      stage_out_flat<PTAU_BLOCK>(out + rec0 * WOUT, sm, nrec * WOUT);
     }
     __syncthreads();
   }

@@ -105,6 +105,16 @@ extern "C" void hostemul_fqw_op(int op, const uint32_t* a, const uint32_t* b, ui
       std::memcpy(out, t, 96);
       break;
     }
+    case 6:  // the row-by-row 12 x 12 product
+      std::memcpy(x.l, a, 48);
+      std::memcpy(y.l, b, 48);
+      fq_mul_wide_plain(out, x, y);
+      break;
+    case 7:  // one level of Karatsuba
+      std::memcpy(x.l, a, 48);
+      std::memcpy(y.l, b, 48);
+      fq_mul_wide_k(out, x, y);
+      break;
   }
 }
 

@@ -113,10 +113,16 @@ def test_limb_wide_products_and_lazy_fq2(hostemul):
 
     ops = [0, 1, 2, P - 1, P, P + 1, 2 * P - 2, 2 * P - 1, (1 << 381) - 1, (1 << 382) - 1]
     ops += [patterned(2 * P) for _ in range(150)] + [rnd.randrange(2 * P) for _ in range(300)]
+    # full-width operands too: the Karatsuba half sums carry out exactly when the halves are large
+    ops += [(1 << 384) - 1, (1 << 384) - (1 << 192), (1 << 192) - 1, ((1 << 192) - 1) << 192, (1 << 383) + (1 << 191)]
+    ops += [patterned(1 << 384) for _ in range(150)] + [rnd.randrange(1 << 384) for _ in range(300)]
     for i, a in enumerate(ops):
         b = ops[(5 * i + 1) % len(ops)]
         assert op(0, a, b, 12, 12, 24) == a * b
-        assert op(1, a, 0, 12, 12, 24) == a * a
+        assert op(6, a, b, 12, 12, 24) == a * b
+        assert op(7, a, b, 12, 12, 24) == a * b
+        if a < (1 << 383):
+            assert op(1, a, 0, 12, 12, 24) == a * a
     # reduction: extremes of the admissible range and random values
     ts = [0, 1, R - 1, R, P * R - 1, P * R - P, (P - 1) * (P - 1), 4 * P * P - 1 if 4 * P * P < P * R else P * R - 2]
     ts += [rnd.randrange(P * R) for _ in range(400)]
