@@ -42,7 +42,7 @@ HBM_PEAK_GBPS = 6552.0  # MEASURED_PEAKS.json (driver-written copy bandwidth of 
 METRIC = "G1+G2 points/sec parse+decompress+subgroup-check+ark re-encode (2^21 compressed G1 + 2^21 compressed G2 per step)"
 TAU = 0x1234567890ABCDEF1234567890ABCDEF
 # the ncu capture the `traffic` / pipe-busy figures of the roofline object are read from (tools/ncu_summary.py output)
-NCU_SUMMARY = os.path.join("profiles", "r02_ncu_full_headline_config3.csv")
+NCU_SUMMARY = os.path.join("profiles", "r02_ncu_full_all_kernels.csv")
 KERNEL_G1C, KERNEL_G2C = "convert_kernel<1, 2, 3, 1>", "convert_kernel<2, 2, 3, 1>"
 
 
@@ -93,14 +93,26 @@ def ncu_summary_metrics(kernel):
     cols = [i for i, name in enumerate(rows[0]) if name.startswith("void " + kernel[:20]) and kernel in name]
     if not cols:
         return None
-    c = cols[-1]
-    m = {r[0]: r[c] for r in rows[1:] if len(r) > c}
+    import math
 
-    def f(name):
+    def column(c):
+        return {r[0]: r[c] for r in rows[1:] if len(r) > c}
+
+    def num(m, name):
         try:
-            return float(m[name])
+            v = float(m[name])
+            return v if math.isfinite(v) else None
         except Exception:
             return None
+    # the last capture of the kernel whose counters are complete (ncu leaves "-nan" in a column when a replay pass failed)
+    usable = [c for c in cols if num(column(c), "dram__bytes_read.sum") is not None
+              and num(column(c), "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed") is not None]
+    if not usable:
+        return None
+    m = column(usable[-1])
+
+    def f(name):
+        return num(m, name)
     grid, block = f("launch__grid_size"), f("launch__block_size")
     rd, wr = f("dram__bytes_read.sum"), f("dram__bytes_write.sum")
     units = {r[0]: r[1] for r in rows[1:]}
@@ -110,7 +122,8 @@ def ncu_summary_metrics(kernel):
     if wr is not None:
         wr *= scale.get(units.get("dram__bytes_write.sum", "byte"), 1.0)
     return {"points": grid * block if grid and block else None, "dram_bytes": (rd + wr) if rd is not None and wr is not None else None,
-            "fmaheavy_pct": f("sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_active"),
+            "fmaheavy_pct": f("sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed"),
+            "kernel_ms_in_capture": f("gpu__time_duration.sum"),
             "registers": f("launch__registers_per_thread"),
             "local_ld_sectors": f("l1tex__t_sectors_pipe_lsu_mem_local_op_ld.sum"),
             "local_st_sectors": f("l1tex__t_sectors_pipe_lsu_mem_local_op_st.sum")}
@@ -652,9 +665,9 @@ def main():
             if args.no_extra or args.no_legs:
                 raise RuntimeError("--no-extra / --no-legs")
             rate1, _, _ = cpu_config3(1 << 8, 1)
-            n_s = 1 << 10  # probe, then size the sample to ~15 s of host work
+            n_s = 1 << 12  # probe (large enough to keep every thread busy), then size the sample to 10-20 s of host work
             rate, dt, _ = cpu_config3(n_s, threads)
-            while n_s < N and 2 * (2 * n_s) / rate <= 16.0:
+            while n_s < N and 2 * (2 * n_s) / rate <= 20.0:
                 n_s *= 2
             rate, dt, inputs = cpu_config3(n_s, threads)
             line["cpu_baseline"] = {

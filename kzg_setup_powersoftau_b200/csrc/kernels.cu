@@ -650,6 +650,10 @@ cudaError_t launch_generate_win(int group, int fmt, const uint32_t* s0_mont, con
 //   2. msm_scan     exclusive prefix sum of the histogram (one block; <= 2^19 + 1 counters)
 //   3. msm_digits<true>  the same digits again, each non-zero one claims a slot of its bucket: a list of
 //                   point indices (sign in bit 31) grouped by bucket -- a counting sort without a key array
+//   3b. msm_size_hist / msm_size_scan / msm_size_scatter  counting sort of the buckets by size, largest first: thread t
+//                   of the next kernel takes the t-th largest bucket, so the 32 lanes of a warp run the same number of
+//                   additions (bucket sizes are Poisson around 32: in bucket order a warp waits for its largest lane,
+//                   ~1.35 x the mean)
 //   4. msm_bucket_sum    one thread per bucket: sum of its points (mixed additions)
 //   5. msm_window_segments  per window, runs of L consecutive buckets: sum_j j B_j by running sums
 //   6. msm_window_sum    one block per window adds the runs up and applies the window's weight 2^(c w)
@@ -743,13 +747,69 @@ __global__ void __launch_bounds__(1024) msm_scan(const uint32_t* __restrict__ cn
   if (threadIdx.x == 0) off[m] = carry_s;
 }
 
-// one thread per bucket: sum of the bucket's points
+// Buckets ordered by size, largest first (a counting sort over min(size, PTAU_MSM_BINS - 1)).
+//   msm_size_hist: hist[s] = number of buckets of size s;  msm_size_scan: hist[s] <- number of buckets larger than s;
+//   msm_size_scatter: order[hist[s]++] = b.  The order inside a size class is not deterministic; the sums do not
+//   depend on it (every bucket is still summed by one thread, in list order).
+#define PTAU_MSM_BINS 1024
+__global__ void __launch_bounds__(PTAU_MSM_BINS) msm_size_hist(const uint32_t* __restrict__ cnt, uint32_t m, uint32_t* __restrict__ hist) {
+  __shared__ uint32_t h[PTAU_MSM_BINS];
+  h[threadIdx.x] = 0;
+  __syncthreads();
+  const uint32_t b = blockIdx.x * PTAU_MSM_BINS + threadIdx.x;
+  if (b < m) atomicAdd(&h[min(cnt[b], (uint32_t)PTAU_MSM_BINS - 1u)], 1u);
+  __syncthreads();
+  if (h[threadIdx.x]) atomicAdd(&hist[threadIdx.x], h[threadIdx.x]);
+}
+__global__ void __launch_bounds__(PTAU_MSM_BINS) msm_size_scan(uint32_t* __restrict__ hist) {
+  __shared__ uint32_t wsum[32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const uint32_t bin = PTAU_MSM_BINS - 1 - threadIdx.x;  // thread 0 owns the largest size
+  const uint32_t mine = hist[bin];
+  uint32_t incl = mine;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += t;
+  }
+  if (lane == 31) wsum[wid] = incl;
+  __syncthreads();
+  if (wid == 0) {
+    uint32_t w = wsum[lane], wi = w;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      uint32_t t = __shfl_up_sync(0xffffffffu, wi, d);
+      if (lane >= d) wi += t;
+    }
+    wsum[lane] = wi - w;
+  }
+  __syncthreads();
+  hist[bin] = wsum[wid] + incl - mine;
+}
+__global__ void __launch_bounds__(PTAU_MSM_BINS) msm_size_scatter(const uint32_t* __restrict__ cnt, uint32_t m, uint32_t* __restrict__ cursor,
+                                                                  uint32_t* __restrict__ order) {
+  __shared__ uint32_t h[PTAU_MSM_BINS], base[PTAU_MSM_BINS];
+  h[threadIdx.x] = 0;
+  __syncthreads();
+  const uint32_t b = blockIdx.x * PTAU_MSM_BINS + threadIdx.x;
+  uint32_t bin = 0, rank = 0;
+  if (b < m) {
+    bin = min(cnt[b], (uint32_t)PTAU_MSM_BINS - 1u);
+    rank = atomicAdd(&h[bin], 1u);
+  }
+  __syncthreads();
+  if (h[threadIdx.x]) base[threadIdx.x] = atomicAdd(&cursor[threadIdx.x], h[threadIdx.x]);
+  __syncthreads();
+  if (b < m) order[base[bin] + rank] = b;
+}
+
+// one thread per bucket (thread t: the t-th largest): sum of the bucket's points
 __global__ void __launch_bounds__(PTAU_BLOCK) msm_bucket_sum(const uint32_t* __restrict__ pts, const uint32_t* __restrict__ entries,
-                                                             const uint32_t* __restrict__ off, uint32_t m,
-                                                             uint32_t* __restrict__ buckets /* 36 words each */) {
-  const uint32_t b = blockIdx.x * PTAU_BLOCK + threadIdx.x;
-  if (b >= m) return;
-  msm_bucket_item(pts, entries, off, b, buckets);
+                                                             const uint32_t* __restrict__ off, const uint32_t* __restrict__ order,
+                                                             uint32_t m, uint32_t* __restrict__ buckets /* 36 words each */) {
+  const uint32_t t = blockIdx.x * PTAU_BLOCK + threadIdx.x;
+  if (t >= m) return;
+  msm_bucket_item(pts, entries, off, order[t], buckets);
 }
 
 // one thread per run of L = 2^lgL consecutive buckets of one window (msm.cuh: msm_segment_item)
@@ -806,14 +866,15 @@ void msm_g1_plan(uint64_t n, MsmPlan* p) {
   p->segments = p->buckets >> p->lgL;
   const uint64_t a256 = 256;
   auto up = [&](uint64_t v) { return (v + a256 - 1) / a256 * a256; };
-  p->off_counts = 0;
-  p->off_offsets = up((p->buckets + 1) * 4);
+  p->off_counts = 0;  // bucket sizes (buckets + 1 words), then the histogram of the sizes (1024 words): one memset
+  p->off_offsets = up((p->buckets + 1 + 1024) * 4);
   p->off_cursor = p->off_offsets + up((p->buckets + 1) * 4);
   p->off_entries = p->off_cursor + up((p->buckets + 1) * 4);
   p->off_buckets = p->off_entries + up((n ? n : 1) * (uint64_t)p->W * 4);
   p->off_segments = p->off_buckets + up(p->buckets * 144);
   p->off_wsum = p->off_segments + up(p->segments * 144);
-  p->scratch_bytes = p->off_wsum + up((uint64_t)p->W * 144);
+  p->off_order = p->off_wsum + up((uint64_t)p->W * 144);
+  p->scratch_bytes = p->off_order + up(p->buckets * 4);
 }
 
 cudaError_t launch_msm_g1(const void* d_pts, const void* d_scalars, uint64_t n, void* d_scratch, void* d_out,
@@ -834,10 +895,12 @@ cudaError_t launch_msm_g1(const void* d_pts, const void* d_scalars, uint64_t n, 
   uint32_t* buckets = (uint32_t*)(base + p.off_buckets);
   uint32_t* segs = (uint32_t*)(base + p.off_segments);
   uint32_t* wsum = (uint32_t*)(base + p.off_wsum);
+  uint32_t* order = (uint32_t*)(base + p.off_order);
   const uint32_t m = (uint32_t)p.buckets;
+  uint32_t* size_hist = counts + m + 1;
   const uint32_t* pts = (const uint32_t*)d_pts;
   const uint32_t* sc = (const uint32_t*)d_scalars;
-  cudaError_t e = cudaMemsetAsync(counts, 0, (size_t)(m + 1) * 4, stream);
+  cudaError_t e = cudaMemsetAsync(counts, 0, (size_t)(m + 1 + PTAU_MSM_BINS) * 4, stream);
   if (e != cudaSuccess) return e;
   uint32_t* bad = (uint32_t*)d_out + 26;  // d_out: 26 words of the result record + the "scalar >= r" flag
   e = cudaMemsetAsync(bad, 0, 4, stream);
@@ -853,7 +916,12 @@ cudaError_t launch_msm_g1(const void* d_pts, const void* d_scalars, uint64_t n, 
     msm_digits<true><<<gn, 256, 0, stream>>>(pts, sc, n, g, cursor, entries, nullptr);
     nl++;
   }
-  msm_bucket_sum<<<(m + PTAU_BLOCK - 1) / PTAU_BLOCK, PTAU_BLOCK, 0, stream>>>(pts, entries, offsets, m, buckets);
+  const unsigned gs = (m + PTAU_MSM_BINS - 1) / PTAU_MSM_BINS;
+  msm_size_hist<<<gs, PTAU_MSM_BINS, 0, stream>>>(counts, m, size_hist);
+  msm_size_scan<<<1, PTAU_MSM_BINS, 0, stream>>>(size_hist);
+  msm_size_scatter<<<gs, PTAU_MSM_BINS, 0, stream>>>(counts, m, size_hist, order);
+  nl += 3;
+  msm_bucket_sum<<<(m + PTAU_BLOCK - 1) / PTAU_BLOCK, PTAU_BLOCK, 0, stream>>>(pts, entries, offsets, order, m, buckets);
   const uint32_t nseg = (uint32_t)p.segments;
   msm_window_segments<<<(nseg + PTAU_BLOCK - 1) / PTAU_BLOCK, PTAU_BLOCK, 0, stream>>>(buckets, g, nseg, segs);
   msm_window_sum<<<p.W, PTAU_BLOCK, 0, stream>>>(segs, g, wsum);

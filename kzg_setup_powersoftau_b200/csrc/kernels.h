@@ -25,7 +25,7 @@ struct MsmPlan {
   int c, W, a, lgL;
   uint32_t NB;
   uint64_t buckets, segments;
-  uint64_t off_counts, off_offsets, off_cursor, off_entries, off_buckets, off_segments, off_wsum, scratch_bytes;
+  uint64_t off_counts, off_offsets, off_cursor, off_entries, off_buckets, off_segments, off_wsum, off_order, scratch_bytes;
 };
 void msm_g1_plan(uint64_t n, MsmPlan* plan);
 cudaError_t launch_msm_g1(const void* d_pts, const void* d_scalars, uint64_t n, void* d_scratch, void* d_out,

@@ -156,12 +156,29 @@ PTAU_HD void msm_segment_item(const uint32_t* buckets, const MsmGeom& g, uint32_
   jac_store(seg + (uint64_t)t_id * 36, sacc);
 }
 
+// dbl-2009-l with the multiplications expanded in place: the weight of a window is a chain of up to 240 dependent
+// doublings in ONE thread, so what counts is latency -- inlined, the three independent products of every level
+// (Y^2, ZY, X^2; then B^2, (X+B)^2, E^2) overlap in the pipe instead of running one call after the other
+PTAU_HD void jac_dbl_latency(Jac<Fq>& p) {
+  Fq B = fq_sqr_inl(p.Y);
+  Fq ZY = fq_mul_inl(p.Z, p.Y);
+  Fq A = fq_sqr_inl(p.X);
+  Fq C = fq_sqr_inl(B);
+  Fq D = fq_sqr_inl(fq_add(p.X, B));
+  Fq E = fq_add(fq_dbl(A), A);
+  Fq Fv = fq_sqr_inl(E);
+  D = fq_dbl(fq_sub(fq_sub(D, A), C));
+  p.Z = fq_dbl(ZY);
+  p.X = fq_sub(Fv, fq_dbl(D));
+  C = fq_dbl(fq_dbl(fq_dbl(C)));
+  p.Y = fq_sub(fq_mul_inl(fq_sub(D, p.X), E), C);
+}
 // the window's weight 2^bitoff(w)
 PTAU_HD void msm_window_weight(Jac<Fq>& acc, const MsmGeom& g, int w) {
   const int nd = msm_bitoff(g, w);
+  if (fq_is_zero(acc.Z)) return;  // later on Z3 = 2 Y Z keeps an infinity (Z = 0) an infinity, whatever X and Y become
 #pragma unroll 1
-  for (int k = 0; k < nd; k++)
-    if (!fq_is_zero(acc.Z)) jac_dbl(acc);
+  for (int k = 0; k < nd; k++) jac_dbl_latency(acc);
 }
 
 // sum of the weighted window sums, then one ARK_MONT_LIMBS record (affine, or ark zero() = (0, 1, infinity))

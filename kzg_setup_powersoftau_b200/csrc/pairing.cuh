@@ -18,6 +18,14 @@
 
 namespace ptau {
 
+// PTAU_PAIR_SYNC (A/B): a block-wide barrier at the top of every iteration of the long loops, so that the warps of an SM
+// walk the same part of the (~200 KB) instruction stream together.  The callers keep control flow uniform per block.
+#if defined(__CUDA_ARCH__) && defined(PTAU_PAIR_SYNC)
+#define PTAU_TOWER_SYNC() __syncthreads()
+#else
+#define PTAU_TOWER_SYNC() ((void)0)
+#endif
+
 struct Fq6 {
   Fq2 c0, c1, c2;
 };
@@ -214,6 +222,7 @@ PTAU_HD_NOINLINE void fq12_pow_cyclotomic(Fq12& r, const Fq12& a, const uint32_t
   Fq12 acc = a;
 #pragma unroll 1
   for (int i = nbits - 2; i >= 0; --i) {
+    PTAU_TOWER_SYNC();
     fq12_cyclotomic_sqr(acc, acc);
     if ((e[i >> 5] >> (i & 31)) & 1u) fq12_mul(acc, acc, a);
   }
@@ -227,15 +236,35 @@ PTAU_HD_NOINLINE void fq12_exp_z(Fq12& r, const Fq12& a) {
   fq12_conj(r, t);
 }
 
-// f^((p^12 - 1) / r)
-PTAU_HD_NOINLINE void final_exponentiation(Fq12& r, const Fq12& f) {
-  Fq12 m, t, a, b, c;
+// f^((p^6 - 1)(p^2 + 1)): the result is in the cyclotomic subgroup
+PTAU_HD_NOINLINE void final_exp_easy(Fq12& m, const Fq12& f) {
+  Fq12 t;
   fq12_conj(t, f);
   fq12_inv(m, f);
   fq12_mul(m, t, m);  // f^(p^6 - 1)
   fq12_frob(t, m);
   fq12_frob(t, t);
-  fq12_mul(m, t, m);  // ^(p^2 + 1): m is in the cyclotomic subgroup from here on
+  fq12_mul(m, t, m);  // ^(p^2 + 1)
+}
+// m^((z + p)(z^2 + p^2 - 1)) for a in the cyclotomic subgroup, times `last`
+PTAU_HD_NOINLINE void final_exp_tail(Fq12& r, const Fq12& a, const Fq12& last) {
+  Fq12 t, b, c;
+  fq12_exp_z(b, a);
+  fq12_frob(t, a);
+  fq12_mul(b, b, t);  // ^(z + p)
+  fq12_exp_z(c, b);
+  fq12_exp_z(c, c);
+  fq12_frob(t, b);
+  fq12_frob(t, t);
+  fq12_mul(c, c, t);
+  fq12_conj(t, b);
+  fq12_mul(c, c, t);  // ^(z^2 + p^2 - 1)
+  fq12_mul(r, c, last);
+}
+// f^((p^12 - 1) / r)
+PTAU_HD_NOINLINE void final_exponentiation(Fq12& r, const Fq12& f) {
+  Fq12 m, a;
+  final_exp_easy(m, f);
   {
     uint32_t h1[4];
 #ifdef __CUDA_ARCH__
@@ -247,17 +276,25 @@ PTAU_HD_NOINLINE void final_exponentiation(Fq12& r, const Fq12& f) {
     for (int i = 0; i < 4; i++) h1[i] = hc[i];
     fq12_pow_cyclotomic(a, m, h1, 126);  // ^((z-1)^2 / 3)
   }
-  fq12_exp_z(b, a);
-  fq12_frob(t, a);
-  fq12_mul(b, b, t);  // ^(z + p)
-  fq12_exp_z(c, b);
-  fq12_exp_z(c, c);
-  fq12_frob(t, b);
-  fq12_frob(t, t);
-  fq12_mul(c, c, t);
-  fq12_conj(t, b);
-  fq12_mul(c, c, t);  // ^(z^2 + p^2 - 1)
-  fq12_mul(r, c, m);  // + 1
+  final_exp_tail(r, a, m);  // ^((z + p)(z^2 + p^2 - 1)), + 1
+}
+// f^((p^12 - 1) / r) == 1, decided on the cube: 3 (p^4 - p^2 + 1) / r = (z-1)^2 (z + p)(z^2 + p^2 - 1) + 3, and
+// x -> x^3 is a bijection of the order-r group the value lies in (r is a prime != 3).  (z-1)^2 costs two
+// exponentiations by the sparse z instead of one by the dense 126-bit (z-1)^2 / 3: 37 fewer Fq12 multiplications.
+// Only the boolean is the same as final_exponentiation's; KZG10::check needs nothing else.
+PTAU_HD_NOINLINE bool final_exp_is_one(const Fq12& f) {
+  Fq12 m, a, t;
+  final_exp_easy(m, f);
+  fq12_exp_z(a, m);
+  fq12_conj(t, m);
+  fq12_mul(a, a, t);  // m^(z - 1)
+  fq12_exp_z(t, a);
+  fq12_conj(a, a);
+  fq12_mul(a, t, a);  // m^((z - 1)^2)
+  fq12_cyclotomic_sqr(t, m);
+  fq12_mul(t, t, m);  // m^3
+  final_exp_tail(a, a, t);
+  return fq12_is_one(a);
 }
 
 // ---- Miller loop (ark-ec 0.2 bls12, TwistType::M) -------------------------------------------------
@@ -268,17 +305,40 @@ struct EllCoeff {
   Fq2 c0, c1, c2;
 };
 
+// a / 2: (a + (a odd ? p : 0)) >> 1, the same in Montgomery form
+PTAU_HD Fq fq_half(const Fq& a) {
+  const uint32_t pl[12] = PTAU_P_LIMBS;
+  const uint32_t mask = 0u - (a.l[0] & 1u);
+  uint32_t t[13];
+  uint64_t c = 0;
+#pragma unroll
+  for (int i = 0; i < 12; i++) {
+    c += (uint64_t)a.l[i] + (pl[i] & mask);
+    t[i] = (uint32_t)c;
+    c >>= 32;
+  }
+  t[12] = (uint32_t)c;
+  Fq r;
+#pragma unroll
+  for (int i = 0; i < 12; i++) r.l[i] = (t[i] >> 1) | (t[i + 1] << 31);
+  return r;
+}
+PTAU_HD Fq2 fq2_half(const Fq2& a) {
+  Fq2 r;
+  r.c0 = fq_half(a.c0);
+  r.c1 = fq_half(a.c1);
+  return r;
+}
+// ark-ec 0.2 doubling_step.  Two of its multiplications are by constants and are done without the multiplier, with the
+// same field values: `* two_inv` is a halving, and `* b'` (the twist coefficient 4(1 + u) = 4 xi) is two doublings and
+// a multiplication by xi.
 PTAU_HD_NOINLINE void doubling_step(G2Hom& r, EllCoeff& co) {
-  const Fq two_inv = k_half_mont();
-  Fq2 a = fq2_mul_fq(fq2_mul(r.x, r.y), two_inv);
+  Fq2 a = fq2_half(fq2_mul(r.x, r.y));
   Fq2 b = fq2_sqr(r.y);
   Fq2 c = fq2_sqr(r.z);
-  Fq2 bt;
-  bt.c0 = k_b1_mont();
-  bt.c1 = bt.c0;
-  Fq2 e = fq2_mul(bt, fq2_add(fq2_dbl(c), c));
+  Fq2 e = fq2_mul_xi(fq2_dbl(fq2_dbl(fq2_add(fq2_dbl(c), c))));  // b' * 3c
   Fq2 f = fq2_add(fq2_dbl(e), e);
-  Fq2 g = fq2_mul_fq(fq2_add(b, f), two_inv);
+  Fq2 g = fq2_half(fq2_add(b, f));
   Fq2 h = fq2_sub(fq2_sqr(fq2_add(r.y, r.z)), fq2_add(b, c));
   Fq2 i = fq2_sub(e, b);
   Fq2 j = fq2_sqr(r.x);
@@ -398,6 +458,7 @@ PTAU_HD_NOINLINE void miller_loop2(Fq12& f, const Fq* px, const Fq* py, const Fq
   EllCoeff co;
 #pragma unroll 1
   for (int i = 62; i >= 0; --i) {
+    PTAU_TOWER_SYNC();
     fq12_sqr(f, f);
 #pragma unroll 1
     for (int k = 0; k < 2; k++) {
@@ -411,6 +472,52 @@ PTAU_HD_NOINLINE void miller_loop2(Fq12& f, const Fq* px, const Fq* py, const Fq
         if (!use[k]) continue;
         addition_step(r[k], qx[k], qy[k], co);
         ell(f, co, px[k], py[k]);
+      }
+    }
+  }
+  fq12_conj(f, f);  // z < 0
+}
+
+// The same value when the line coefficients of Q_0 are already known (g2_prepare_item's layout, 68 triples of 72 words):
+// KZG10::check pairs every opening with the verifier key's h, so its doubling / addition steps are done once per key.
+PTAU_HD void load_ell_coeff(EllCoeff& co, const uint32_t* p) {
+#pragma unroll
+  for (int j = 0; j < 12; j++) {
+    co.c0.c0.l[j] = p[j];
+    co.c0.c1.l[j] = p[12 + j];
+    co.c1.c0.l[j] = p[24 + j];
+    co.c1.c1.l[j] = p[36 + j];
+    co.c2.c0.l[j] = p[48 + j];
+    co.c2.c1.l[j] = p[60 + j];
+  }
+}
+PTAU_HD_NOINLINE void miller_loop2_prep0(Fq12& f, const Fq* px, const Fq* py, const uint32_t* prep0, const Fq2& qx1,
+                                         const Fq2& qy1, const bool* use) {
+  fq12_one(f);
+  G2Hom r;
+  r.x = qx1;
+  r.y = qy1;
+  r.z = fq2_one();
+  EllCoeff co;
+  int t = 0;
+#pragma unroll 1
+  for (int i = 62; i >= 0; --i) {
+    PTAU_TOWER_SYNC();
+    if (i != 62) fq12_sqr(f, f);  // 1^2
+#pragma unroll 1
+    for (int step = 0; step < 2; step++) {
+      if (step == 1 && !((PTAU_Z_ABS >> i) & 1ull)) break;
+      if (use[0]) {
+        load_ell_coeff(co, prep0 + t * 72);
+        ell(f, co, px[0], py[0]);
+      }
+      t++;
+      if (use[1]) {
+        if (step == 0)
+          doubling_step(r, co);
+        else
+          addition_step(r, qx1, qy1, co);
+        ell(f, co, px[1], py[1]);
       }
     }
   }
@@ -468,6 +575,33 @@ PTAU_HD_NOINLINE bool jac_to_affine_t(const Jac<F>& p, F& x, F& y) {
   x = fmul(p.X, zi2);
   y = fmul(p.Y, fmul(zi2, zi));
   return true;
+}
+// Both conversions of one KZG10 opening with ONE field inversion (Montgomery's trick across Fq and Fq2:
+// 1 / Z2 = conj(Z2) / N(Z2) with the norm N in Fq, and 1/Z1, 1/N come from 1 / (Z1 N)).  Same affine values as two
+// jac_to_affine_t calls; returns through pok / qok whether each point is finite.
+PTAU_HD_NOINLINE void jac_to_affine_pair(const Jac<Fq>& p, const Jac<Fq2>& q, Fq& px, Fq& py, Fq2& qx, Fq2& qy, bool& pok,
+                                         bool& qok) {
+  pok = !fq_is_zero(p.Z);
+  qok = !fq2_is_zero(q.Z);
+  const Fq z1 = pok ? p.Z : fq_one();
+  // N = c0^2 + c1^2 is zero only for Z2 = 0 (-1 is not a square mod p)
+  const Fq n = qok ? fq_add(fq_sqr(q.Z.c0), fq_sqr(q.Z.c1)) : fq_one();
+  const Fq ti = fq_inv_fermat(fq_mul(z1, n));
+  if (pok) {
+    Fq zi = fq_mul(ti, n);
+    Fq zi2 = fq_sqr(zi);
+    px = fq_mul(p.X, zi2);
+    py = fq_mul(p.Y, fq_mul(zi2, zi));
+  }
+  if (qok) {
+    Fq ni = fq_mul(ti, z1);
+    Fq2 zi;
+    zi.c0 = fq_mul(q.Z.c0, ni);
+    zi.c1 = fq_neg(fq_mul(q.Z.c1, ni));
+    Fq2 zi2 = fq2_sqr(zi);
+    qx = fq2_mul(q.X, zi2);
+    qy = fq2_mul(q.Y, fq2_mul(zi2, zi));
+  }
 }
 // p += q, both Jacobian, every special case
 template <class F>
@@ -613,20 +747,69 @@ PTAU_HD_NOINLINE void fixed_base_window(uint32_t* tbl, const uint32_t* base_rec,
     store_rec(out + j * REC, fmul(m[j].X, zi2), fmul(m[j].Y, fmul(zi2, zi)), false);
   }
 }
-// acc = [k] B from B's table; k = 8 little-endian words
+// Second level: T8[w][e-1] = [e 256^w] B, w < 32, e = 1..255, from the 4-bit table: entry e = 16 hi + lo is
+// T[2w+1][hi] + T[2w][lo].  One thread per (w, hi) builds its 16 entries with one inversion.  32 mixed additions per
+// scalar instead of 64 (KZG10::check does three such multiplications per opening; the tables are built once per key).
+#define PTAU_FB8_WINDOWS 32
+#define PTAU_FB8_ENTRIES (PTAU_FB8_WINDOWS * 255)
 template <class F>
-PTAU_HD_NOINLINE void fixed_base_mul(Jac<F>& acc, const uint32_t* tbl, const uint32_t* k, const F& one) {
+PTAU_HD_NOINLINE void fixed_base_window8(uint32_t* tbl8, const uint32_t* tbl4, int w, int hi, const F& one) {
+  constexpr int REC = RecWords<F>::value;
+  uint32_t* out = tbl8 + ((size_t)w * 255 + hi * 16) * REC;  // entry e = 16 hi + lo lives at out + (lo - 1) REC
+  const F zero = fsub(one, one);
+  F bx = zero, by = one;
+  bool binf = true;
+  if (hi) load_rec(tbl4 + ((size_t)(2 * w + 1) * 15 + hi - 1) * REC, bx, by, binf);
+  Jac<F> m[16];
+#pragma unroll 1
+  for (int lo = 0; lo < 16; lo++) {
+    m[lo].X = bx;
+    m[lo].Y = by;
+    m[lo].Z = binf ? zero : one;
+    if (lo) {
+      F x, y;
+      bool inf;
+      load_rec(tbl4 + ((size_t)(2 * w) * 15 + lo - 1) * REC, x, y, inf);
+      if (!inf) jac_madd_complete_t(m[lo], x, y, one);
+    }
+  }
+  F pre[16];
+  F acc = one;
+#pragma unroll 1
+  for (int j = 0; j < 16; j++) {
+    pre[j] = acc;
+    if (!fis_zero(m[j].Z)) acc = fmul(acc, m[j].Z);
+  }
+  F inv = finv(acc);
+#pragma unroll 1
+  for (int j = 15; j >= 0; --j) {
+    if (hi == 0 && j == 0) continue;  // e = 0 has no entry
+    if (fis_zero(m[j].Z)) {
+      store_rec(out + (j - 1) * REC, bx, by, true);
+      continue;
+    }
+    F zi = fmul(inv, pre[j]);
+    inv = fmul(inv, m[j].Z);
+    F zi2 = fsqr(zi);
+    store_rec(out + (j - 1) * REC, fmul(m[j].X, zi2), fmul(m[j].Y, fmul(zi2, zi)), false);
+  }
+}
+// acc = [k] B from B's table (w8: the 8-bit second-level table, else the 4-bit one); k = 8 little-endian words
+template <class F>
+PTAU_HD_NOINLINE void fixed_base_mul(Jac<F>& acc, const uint32_t* tbl, const uint32_t* k, const F& one, bool w8 = false) {
   constexpr int REC = RecWords<F>::value;
   acc.X = fsub(one, one);
   acc.Y = one;
   acc.Z = acc.X;
+  const int bits = w8 ? 8 : 4;
+  const uint32_t per = w8 ? 255u : 15u;
 #pragma unroll 1
-  for (int w = 0; w < PTAU_FB_WINDOWS; w++) {
-    const uint32_t d = (k[w >> 3] >> ((w & 7) * 4)) & 15u;
+  for (int w = 0; w < 256 / bits; w++) {
+    const uint32_t d = (k[(w * bits) >> 5] >> ((w * bits) & 31)) & per;
     if (!d) continue;
     F x, y;
     bool inf;
-    load_rec(tbl + ((size_t)w * 15 + d - 1) * REC, x, y, inf);
+    load_rec(tbl + ((size_t)w * per + d - 1) * REC, x, y, inf);
     if (!inf) jac_madd_complete_t(acc, x, y, one);
   }
 }
@@ -654,17 +837,20 @@ PTAU_HD_NOINLINE bool pairing_product2_item(const uint32_t* g1, const uint32_t* 
 
 // KZG10::check of one opening: e(C - [v]g - [rv]gamma_g, h) == e(w, beta_h - [z]h), evaluated as
 // e(inner, h) * e(-w, beta_h - [z]h) == 1.  Scalars: 8 little-endian words, < r; random_v may be null.
-// tbl_g / tbl_gg / tbl_h: fixed-base tables of g, gamma_g, h (fixed_base_window), or null for plain double-and-add.
+// tbl_g / tbl_gg / tbl_h: fixed-base tables of g, gamma_g, h (fixed_base_window, or with w8 the second-level tables of
+// fixed_base_window8), or null for plain double-and-add;
+// prep_h: h's line coefficients (g2_prepare_item), or null to run its doubling / addition steps per opening.
 PTAU_HD_NOINLINE bool kzg_check_item(const uint32_t* vk_g1, const uint32_t* vk_g2, const uint32_t* comm, const uint32_t* point,
                                      const uint32_t* value, const uint32_t* proof_w, const uint32_t* random_v,
                                      const uint32_t* tbl_g = nullptr, const uint32_t* tbl_gg = nullptr,
-                                     const uint32_t* tbl_h = nullptr) {
+                                     const uint32_t* tbl_h = nullptr, const uint32_t* prep_h = nullptr, bool w8 = false) {
   Fq px[2], py[2];
   Fq2 qx[2], qy[2];
   bool use[2];
   uint32_t k[8];
   bool hinf;
   load_g2_rec(vk_g2, qx[0], qy[0], hinf);
+  Jac<Fq> inner;
   {  // inner = C - [v] g - [rv] gamma_g
     Fq gx, gy;
     bool ginf;
@@ -673,7 +859,7 @@ PTAU_HD_NOINLINE bool kzg_check_item(const uint32_t* vk_g1, const uint32_t* vk_g
 #pragma unroll
     for (int w = 0; w < 8; w++) k[w] = ginf ? 0u : value[w];
     if (tbl_g)
-      fixed_base_mul(acc, tbl_g, k, fq_one());
+      fixed_base_mul(acc, tbl_g, k, fq_one(), w8);
     else
       jac_scalar_mul_t(acc, gx, gy, k, fq_one());
     if (random_v) {
@@ -682,7 +868,7 @@ PTAU_HD_NOINLINE bool kzg_check_item(const uint32_t* vk_g1, const uint32_t* vk_g
       for (int w = 0; w < 8; w++) k[w] = ginf ? 0u : random_v[w];
       Jac<Fq> t;
       if (tbl_gg)
-        fixed_base_mul(t, tbl_gg, k, fq_one());
+        fixed_base_mul(t, tbl_gg, k, fq_one(), w8);
       else
         jac_scalar_mul_t(t, gx, gy, k, fq_one());
       jac_add_complete_t(acc, t);
@@ -692,14 +878,14 @@ PTAU_HD_NOINLINE bool kzg_check_item(const uint32_t* vk_g1, const uint32_t* vk_g
     bool cinf;
     load_g1_rec(comm, cx, cy, cinf);
     if (!cinf) jac_madd_complete_t(acc, cx, cy, fq_one());
-    use[0] = jac_to_affine_t(acc, px[0], py[0]) && !hinf;
+    inner = acc;
   }
   {  // Q = beta_h - [z] h
     Jac<Fq2> acc;
 #pragma unroll
     for (int w = 0; w < 8; w++) k[w] = hinf ? 0u : point[w];
     if (tbl_h)
-      fixed_base_mul(acc, tbl_h, k, fq2_one());
+      fixed_base_mul(acc, tbl_h, k, fq2_one(), w8);
     else
       jac_scalar_mul_t(acc, qx[0], qy[0], k, fq2_one());
     acc.Y = fq2_neg(acc.Y);
@@ -710,12 +896,17 @@ PTAU_HD_NOINLINE bool kzg_check_item(const uint32_t* vk_g1, const uint32_t* vk_g
     bool winf;
     load_g1_rec(proof_w, px[1], py[1], winf);
     py[1] = fq_neg(py[1]);
-    use[1] = jac_to_affine_t(acc, qx[1], qy[1]) && !winf;
+    bool pok, qok;
+    jac_to_affine_pair(inner, acc, px[0], py[0], qx[1], qy[1], pok, qok);
+    use[0] = pok && !hinf;
+    use[1] = qok && !winf;
   }
   Fq12 f;
-  miller_loop2(f, px, py, qx, qy, use);
-  final_exponentiation(f, f);
-  return fq12_is_one(f);
+  if (prep_h)
+    miller_loop2_prep0(f, px, py, prep_h, qx[1], qy[1], use);
+  else
+    miller_loop2(f, px, py, qx, qy, use);
+  return final_exp_is_one(f);
 }
 
 }  // namespace ptau

@@ -145,13 +145,22 @@ extern "C" void hostemul_kzg_check(const uint8_t* vk_g1, const uint8_t* vk_g2, c
   uint32_t v1[52], v2[100];
   std::memcpy(v1, vk_g1, 208);
   std::memcpy(v2, vk_g2, 400);
-  static uint32_t tg[PTAU_FB_ENTRIES * 26], tgg[PTAU_FB_ENTRIES * 26], th[PTAU_FB_ENTRIES * 50];
-  if (use_tables) {
+  static uint32_t tg[PTAU_FB_ENTRIES * 26], tgg[PTAU_FB_ENTRIES * 26], th[PTAU_FB_ENTRIES * 50], ph[PTAU_G2PREP_COEFFS * 72];
+  static uint32_t tg8[PTAU_FB8_ENTRIES * 26], tgg8[PTAU_FB8_ENTRIES * 26], th8[PTAU_FB8_ENTRIES * 50];
+  if (use_tables) {  // 1: 4-bit tables; 2: the second-level 8-bit tables the library's check kernel uses
+    g2_prepare_item(v2, ph);
     for (int w = 0; w < PTAU_FB_WINDOWS; w++) {
       fixed_base_window<Fq>(tg, v1, w, fq_one());
       fixed_base_window<Fq>(tgg, v1 + 26, w, fq_one());
       fixed_base_window<Fq2>(th, v2, w, fq2_one());
     }
+    if (use_tables == 2)
+      for (int w = 0; w < PTAU_FB8_WINDOWS; w++)
+        for (int hi = 0; hi < 16; hi++) {
+          fixed_base_window8<Fq>(tg8, tg, w, hi, fq_one());
+          fixed_base_window8<Fq>(tgg8, tgg, w, hi, fq_one());
+          fixed_base_window8<Fq2>(th8, th, w, hi, fq2_one());
+        }
   }
   for (size_t i = 0; i < n; i++) {
     uint32_t c[26], w[26], z[8], v[8], rv[8];
@@ -160,8 +169,9 @@ extern "C" void hostemul_kzg_check(const uint8_t* vk_g1, const uint8_t* vk_g2, c
     std::memcpy(z, points + i * 32, 32);
     std::memcpy(v, values + i * 32, 32);
     if (random_v) std::memcpy(rv, random_v + i * 32, 32);
-    ok[i] = (use_tables ? kzg_check_item(v1, v2, c, z, v, w, random_v ? rv : nullptr, tg, tgg, th)
-                        : kzg_check_item(v1, v2, c, z, v, w, random_v ? rv : nullptr))
+    ok[i] = (use_tables == 2   ? kzg_check_item(v1, v2, c, z, v, w, random_v ? rv : nullptr, tg8, tgg8, th8, ph, true)
+             : use_tables == 1 ? kzg_check_item(v1, v2, c, z, v, w, random_v ? rv : nullptr, tg, tgg, th, ph)
+                               : kzg_check_item(v1, v2, c, z, v, w, random_v ? rv : nullptr))
                 ? 1
                 : 0;
   }

@@ -445,7 +445,7 @@ def test_limb_pairing_code_vs_oracle(hostemul):
     w0 = o.g1_mul(o.G1_GEN, ev(quot(coeffs, zpt), tau))
     big = R - 12345  # a full-width evaluation point: every window of the fixed-base tables is used
     wb = o.g1_mul(o.G1_GEN, ev(quot(coeffs, big), tau))
-    for use_tables in (0, 1):  # plain double-and-add, then the fixed-base window tables the library uses
+    for use_tables in (0, 1, 2):  # plain double-and-add, the 4-bit window tables, the 8-bit tables the library uses
         hostemul.hostemul_kzg_check(vk1, vk2, g1r(comm) * 2, le(zpt) * 2, le(ev(coeffs, zpt)) + le(ev(coeffs, zpt) + 1),
                                     g1r(w) * 2, le(ev(blind, zpt)) * 2, ctypes.c_size_t(2), ok, use_tables)
         assert ok.raw == b"\x01\x00"
@@ -455,6 +455,17 @@ def test_limb_pairing_code_vs_oracle(hostemul):
         assert ok.raw == b"\x01\x00"
         hostemul.hostemul_kzg_check(vk1, vk2, g1r(comm0) * 2, le(big) * 2, le(ev(coeffs, big)) + le(ev(coeffs, big) - 1),
                                     g1r(wb) * 2, None, ctypes.c_size_t(2), ok, use_tables)
+        assert ok.raw == b"\x01\x00"
+        # degenerate openings (the two affine conversions share one inversion): a constant polynomial has the witness at
+        # infinity and C - [v]g at infinity (accepted; a wrong value leaves C - [v]g finite and is rejected), and the
+        # evaluation point tau itself makes beta_h - [z]h infinity (accepted only when C - [v]g is infinity too)
+        cc = o.g1_mul(o.G1_GEN, 42)
+        hostemul.hostemul_kzg_check(vk1, vk2, g1r(cc) * 2, le(zpt) * 2, le(42) + le(43), g1r(None) * 2, None,
+                                    ctypes.c_size_t(2), ok, use_tables)
+        assert ok.raw == b"\x01\x00"
+        wt = o.g1_mul(o.G1_GEN, ev(quot(coeffs, tau), tau))
+        hostemul.hostemul_kzg_check(vk1, vk2, g1r(comm0) * 2, le(tau) * 2, le(ev(coeffs, tau)) + le(ev(coeffs, tau) + 1),
+                                    g1r(wt) * 2, None, ctypes.c_size_t(2), ok, use_tables)
         assert ok.raw == b"\x01\x00"
 
 
