@@ -7,7 +7,7 @@
 namespace ptau {
 
 #ifndef PTAU_PAIR_BLOCK
-#define PTAU_PAIR_BLOCK 64
+#define PTAU_PAIR_BLOCK 128  // 255 registers: two blocks per SM, two warps per scheduler
 #endif
 
 // prod_{k<2} e(P_ik, Q_ik) for n items.  g1: n x 2 ARK_MONT_LIMBS G1 records, g2: n x 2 G2 records.
