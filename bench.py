@@ -471,6 +471,9 @@ def main():
             if prof and prof.get("dram_bytes") and prof.get("points"):
                 # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, scaled from the captured launch to this one
                 r["traffic"] = prof["dram_bytes"] * n_points / prof["points"]
+                # honest utilisation of the multiplier pipe (a squaring issues fewer slots than the multiplication it is
+                # counted as in `frac`): ncu's pipe-busy figure of the committed capture of this kernel
+                r["frac_pipe_busy_ncu"] = prof["fmaheavy_pct"] / 100.0 if prof.get("fmaheavy_pct") else None
                 r["ncu"] = {"source": NCU_SUMMARY, "points_in_capture": prof["points"],
                             "fma_heavy_pipe_busy_pct": prof["fmaheavy_pct"], "registers": prof["registers"],
                             "local_ld_sectors": prof["local_ld_sectors"], "local_st_sectors": prof["local_st_sectors"]}

@@ -142,7 +142,8 @@ PTAU_HD Fq2 fq2_sqr_inl(const Fq2& a) {
 PTAU_HD Fq2 fq2_sqr_inl(const Fq2& a) {
   Fq t = PTAU_FQ2_M(a.c0, a.c1);
   Fq2 r;
-  r.c0 = PTAU_FQ2_M(fq_add(a.c0, a.c1), fq_sub(a.c0, a.c1));
+  // the sum only feeds the multiplication: < 2p unreduced, and 2p * p < p 2^384 keeps the product's range
+  r.c0 = PTAU_FQ2_M(fq_add_nored(a.c0, a.c1), fq_sub(a.c0, a.c1));
   r.c1 = fq_dbl(t);
   return r;
 }
