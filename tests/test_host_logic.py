@@ -1,6 +1,7 @@
 """CPU-only checks of the product's host side: the limb-level arithmetic the CUDA
 kernels execute (compiled for the host with an emulated carry flag), the C ABI
 surface, and the N>1 sharding logic (gloo, world_size 2)."""
+import csv
 import ctypes
 import json
 import os
@@ -567,6 +568,38 @@ def test_bench_reference_arm_contract():
         assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
         assert d["e2e"] == {"value": d["value"], "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
         assert "workload" in d["config"] and d["metric"].startswith("G1+G2 points/sec") and d["scaling"] == "strong" and "configs[2]" in d["config"]["workload"]
+
+
+def test_bench_reads_roofline_figures_from_the_committed_ncu_summary(tmp_path, monkeypatch):
+    """bench.py takes `roofline.traffic` / pipe-busy from a named profiles/*.csv instead of literals: the last capture of
+    the kernel whose counters are complete is used (ncu leaves "-nan" where a replay pass failed), bytes are scaled by
+    the unit row, and a missing file or kernel gives None (the line then says traffic: null)."""
+    sys.path.insert(0, ROOT)
+    import bench
+
+    named = bench.NCU_SUMMARY
+    k = "void convert_kernel<2, 2, 3, 1>(const unsigned i"
+    rows = [["metric", "unit", "void convert_kernel<1, 2, 3, 1>(const unsigned i", k, k],
+            ["gpu__time_duration.sum", "ms", "47.0", "77.5", "77.2"],
+            ["launch__registers_per_thread", "register/thread", "220", "255", "255"],
+            ["launch__grid_size", "", "8192", "8192", "8192"], ["launch__block_size", "", "128", "128", "128"],
+            ["sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed", "%", "86.1", "81.5", "-nan"],
+            ["dram__bytes_read.sum", "Mbyte", "53.5", "109.0", "-nan"], ["dram__bytes_write.sum", "Mbyte", "73.3", "252.0", "-nan"],
+            ["l1tex__t_sectors_pipe_lsu_mem_local_op_ld.sum", "sector", "1", "2", "-nan"],
+            ["l1tex__t_sectors_pipe_lsu_mem_local_op_st.sum", "sector", "3", "4", "-nan"]]
+    (tmp_path / "profiles").mkdir()
+    with open(tmp_path / "profiles" / "x.csv", "w", newline="") as f:
+        csv.writer(f).writerows(rows)
+    monkeypatch.setattr(bench, "ROOT", str(tmp_path))
+    monkeypatch.setattr(bench, "NCU_SUMMARY", os.path.join("profiles", "x.csv"))
+    m = bench.ncu_summary_metrics(bench.KERNEL_G2C)
+    assert m["points"] == 8192 * 128 and m["dram_bytes"] == 361.0e6 and m["fmaheavy_pct"] == 81.5 and m["registers"] == 255
+    assert bench.ncu_summary_metrics(bench.KERNEL_G1C)["dram_bytes"] == pytest.approx(126.8e6)
+    assert bench.ncu_summary_metrics("convert_kernel<9, 9, 9, 9>") is None
+    monkeypatch.setattr(bench, "NCU_SUMMARY", os.path.join("profiles", "absent.csv"))
+    assert bench.ncu_summary_metrics(bench.KERNEL_G2C) is None
+    # and the file the line names is committed
+    assert os.path.exists(os.path.join(ROOT, named))
 
 
 def _pairing_vectors():
