@@ -1,4 +1,4 @@
-"""One bucket-MSM at 2^20 and one KZG10 check batch at 2^13 (for ncu): python tools/prof_consumer.py"""
+"""One bucket-MSM at 2^20 and one KZG10 check batch of one full wave, 37,888 openings (for ncu): python tools/prof_consumer.py"""
 import os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -16,7 +16,7 @@ sc.reshape(n, 32)[:, 31] &= 0x3F
 out = np.zeros(104, dtype=np.uint8)
 assert L.ptau_kzg_commit(ctx._h, pw.ctypes.data, sc.ctypes.data, n, out.ctypes.data) == 0
 print("msm ms", ctx.timing()["kernel_ms"][0])
-nk = 1 << 13
+nk = int(os.environ.get("NK", 148 * 256))  # 296 blocks of 128 = two per SM
 pwk = pw.reshape(-1, 104)[:32]
 g2p = ctx.convert(kz.G2, ZU, ctx.generate(kz.G2, ZU, 1, tau, 0, 2), ML, 0).reshape(2, 200)
 vk = kz.VerifierKey(g=pwk[0], gamma_g=pwk[5], h=g2p[0], beta_h=g2p[1])
