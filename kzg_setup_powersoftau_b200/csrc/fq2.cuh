@@ -142,8 +142,9 @@ PTAU_HD Fq2 fq2_sqr_inl(const Fq2& a) {
 PTAU_HD Fq2 fq2_sqr_inl(const Fq2& a) {
   Fq t = PTAU_FQ2_M(a.c0, a.c1);
   Fq2 r;
-  // the sum only feeds the multiplication: < 2p unreduced, and 2p * p < p 2^384 keeps the product's range
-  r.c0 = PTAU_FQ2_M(fq_add_nored(a.c0, a.c1), fq_sub(a.c0, a.c1));
+  // sum and difference only feed the multiplication: a0 + a1 and a0 - a1 + p, both < 2p with no conditional step, and
+  // 2p * 2p < p 2^384 keeps the product inside the multiplier's range (it accepts operands up to 3p)
+  r.c0 = PTAU_FQ2_M(fq_add_nored(a.c0, a.c1), fq_sub_plus_p(a.c0, a.c1));
   r.c1 = fq_dbl(t);
   return r;
 }

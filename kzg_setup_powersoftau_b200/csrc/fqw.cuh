@@ -36,6 +36,22 @@ PTAU_HD Fq fq_add_nored(const Fq& a, const Fq& b) {
 #define PX_SUBC(r, a, b) do { r = emu::subc(a, b, px_cf); px_cf = 0; } while (0)
 #endif
 
+// a - b + p without any conditional step: in (0, 2p) for reduced inputs, for differences that only feed a multiplication
+PTAU_HD Fq fq_sub_plus_p(const Fq& a, const Fq& b) {
+  const uint32_t pl[12] = PTAU_P_LIMBS;
+  Fq t, r;
+  PX_DECL;
+  PX_ADD_CC(t.l[0], a.l[0], pl[0]);
+#pragma unroll
+  for (int i = 1; i < 11; i++) PX_ADDC_CC(t.l[i], a.l[i], pl[i]);
+  PX_ADDC(t.l[11], a.l[11], pl[11]);
+  PX_SUB_CC(r.l[0], t.l[0], b.l[0]);
+#pragma unroll
+  for (int i = 1; i < 11; i++) PX_SUBC_CC(r.l[i], t.l[i], b.l[i]);
+  PX_SUBC(r.l[11], t.l[11], b.l[11]);
+  return r;
+}
+
 // t[0..23] = a * b.  Same rows as fq_mul_inl without the reduction rows: after row i the lowest limb of the
 // even-aligned accumulator is limb i of the product.
 PTAU_HD void fq_mul_wide_plain(uint32_t* t, const Fq& a, const Fq& b) {
