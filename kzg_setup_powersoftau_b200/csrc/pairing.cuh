@@ -219,23 +219,23 @@ PTAU_HD_NOINLINE void fq12_cyclotomic_sqr(Fq12& r, const Fq12& a) {
   r.c1.c1 = z1;
   r.c1.c2 = z5;
 }
-// r = a^e for a in the cyclotomic subgroup; e = nbits-bit exponent in 32-bit words, top bit set
+// r = a^e for a in the cyclotomic subgroup; e = nbits-bit exponent in 32-bit words, top bit set.  r must not alias a
+// (the accumulator is r itself: every Fq12 temporary is 576 bytes of local memory per thread, and the working set of
+// a full wave is what decides whether it stays in L2)
 PTAU_HD_NOINLINE void fq12_pow_cyclotomic(Fq12& r, const Fq12& a, const uint32_t* e, int nbits) {
-  Fq12 acc = a;
+  r = a;
 #pragma unroll 1
   for (int i = nbits - 2; i >= 0; --i) {
     PTAU_TOWER_SYNC();
-    fq12_cyclotomic_sqr(acc, acc);
-    if ((e[i >> 5] >> (i & 31)) & 1u) fq12_mul(acc, acc, a);
+    fq12_cyclotomic_sqr(r, r);
+    if ((e[i >> 5] >> (i & 31)) & 1u) fq12_mul(r, r, a);
   }
-  r = acc;
 }
-// a^z for a in the cyclotomic subgroup (z < 0: inverse = conjugate)
+// a^z for a in the cyclotomic subgroup (z < 0: inverse = conjugate); r must not alias a
 PTAU_HD_NOINLINE void fq12_exp_z(Fq12& r, const Fq12& a) {
   const uint32_t za[2] = {0x00010000u, 0xd2010000u};
-  Fq12 t;
-  fq12_pow_cyclotomic(t, a, za, 64);
-  fq12_conj(r, t);
+  fq12_pow_cyclotomic(r, a, za, 64);
+  fq12_conj(r, r);
 }
 
 // f^((p^6 - 1)(p^2 + 1)): the result is in the cyclotomic subgroup
@@ -248,20 +248,21 @@ PTAU_HD_NOINLINE void final_exp_easy(Fq12& m, const Fq12& f) {
   fq12_frob(t, t);
   fq12_mul(m, t, m);  // ^(p^2 + 1)
 }
-// m^((z + p)(z^2 + p^2 - 1)) for a in the cyclotomic subgroup, times `last`
-PTAU_HD_NOINLINE void final_exp_tail(Fq12& r, const Fq12& a, const Fq12& last) {
-  Fq12 t, b, c;
+// r = a^((z + p)(z^2 + p^2 - 1)) * last for a in the cyclotomic subgroup; `a` is used as scratch (destroyed); r, a, last
+// are three different objects
+PTAU_HD_NOINLINE void final_exp_tail(Fq12& r, Fq12& a, const Fq12& last) {
+  Fq12 b;
   fq12_exp_z(b, a);
-  fq12_frob(t, a);
-  fq12_mul(b, b, t);  // ^(z + p)
-  fq12_exp_z(c, b);
-  fq12_exp_z(c, c);
-  fq12_frob(t, b);
-  fq12_frob(t, t);
-  fq12_mul(c, c, t);
-  fq12_conj(t, b);
-  fq12_mul(c, c, t);  // ^(z^2 + p^2 - 1)
-  fq12_mul(r, c, last);
+  fq12_frob(r, a);
+  fq12_mul(b, b, r);  // b = a^(z + p); a is free from here
+  fq12_exp_z(a, b);
+  fq12_exp_z(r, a);   // b^(z^2)
+  fq12_frob(a, b);
+  fq12_frob(a, a);
+  fq12_mul(r, r, a);  // * b^(p^2)
+  fq12_conj(a, b);
+  fq12_mul(r, r, a);  // * b^-1
+  fq12_mul(r, r, last);
 }
 // f^((p^12 - 1) / r)
 PTAU_HD_NOINLINE void final_exponentiation(Fq12& r, const Fq12& f) {
@@ -278,13 +279,13 @@ PTAU_HD_NOINLINE void final_exponentiation(Fq12& r, const Fq12& f) {
     for (int i = 0; i < 4; i++) h1[i] = hc[i];
     fq12_pow_cyclotomic(a, m, h1, 126);  // ^((z-1)^2 / 3)
   }
-  final_exp_tail(r, a, m);  // ^((z + p)(z^2 + p^2 - 1)), + 1
+  final_exp_tail(r, a, m);  // ^((z + p)(z^2 + p^2 - 1)), + 1 (r may be f itself: f is not read any more)
 }
 // f^((p^12 - 1) / r) == 1, decided on the cube: 3 (p^4 - p^2 + 1) / r = (z-1)^2 (z + p)(z^2 + p^2 - 1) + 3, and
 // x -> x^3 is a bijection of the order-r group the value lies in (r is a prime != 3).  (z-1)^2 costs two
 // exponentiations by the sparse z instead of one by the dense 126-bit (z-1)^2 / 3: 37 fewer Fq12 multiplications.
-// Only the boolean is the same as final_exponentiation's; KZG10::check needs nothing else.
-PTAU_HD_NOINLINE bool final_exp_is_one(const Fq12& f) {
+// Only the boolean is the same as final_exponentiation's; KZG10::check needs nothing else.  f is used as scratch.
+PTAU_HD_NOINLINE bool final_exp_is_one(Fq12& f) {
   Fq12 m, a, t;
   final_exp_easy(m, f);
   fq12_exp_z(a, m);
@@ -295,8 +296,8 @@ PTAU_HD_NOINLINE bool final_exp_is_one(const Fq12& f) {
   fq12_mul(a, t, a);  // m^((z - 1)^2)
   fq12_cyclotomic_sqr(t, m);
   fq12_mul(t, t, m);  // m^3
-  final_exp_tail(a, a, t);
-  return fq12_is_one(a);
+  final_exp_tail(f, a, t);
+  return fq12_is_one(f);
 }
 
 // ---- Miller loop (ark-ec 0.2 bls12, TwistType::M) -------------------------------------------------
