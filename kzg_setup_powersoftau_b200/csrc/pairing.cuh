@@ -20,7 +20,7 @@ namespace ptau {
 
 // A block-wide barrier at the top of every iteration of the long loops keeps the warps of a block (and so most of an SM)
 // in the same part of the ~450 KB instruction stream: measured 1.15 -> 1.23 M openings/s at 128 threads per block
-// (profiles/r02_kzg_ab.log).  The kernels keep control flow uniform per block (a thread past the end repeats the last
+// (profiles/r02_kzg_ab2.log).  The kernels keep control flow uniform per block (a thread past the end repeats the last
 // item).  -DPTAU_PAIR_NOSYNC removes the barriers.
 #if defined(__CUDA_ARCH__) && !defined(PTAU_PAIR_NOSYNC)
 #define PTAU_TOWER_SYNC() __syncthreads()
