@@ -70,6 +70,7 @@ extern "C" void hostemul_fq_op(int op, const uint32_t* a, const uint32_t* b, uin
 //   op 3: out[24] = fq2_mul(a, b)  (a, b: c0 | c1, 24 limbs, reduced)
 //   op 4: out[24] = fq2_sqr(a)
 //   op 5: out[24] = a - b + (a < b ? p 2^384 : 0) over 24 limbs (fqw_sub_fix)
+//   op 8: out[12] = a - b + p (fq_sub_plus_p);  op 9: out[12] = a / 2 mod p (fq_half)
 extern "C" void hostemul_fqw_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* out) {
   Fq x, y;
   Fq2 u, v, w;
@@ -114,6 +115,17 @@ extern "C" void hostemul_fqw_op(int op, const uint32_t* a, const uint32_t* b, ui
       std::memcpy(x.l, a, 48);
       std::memcpy(y.l, b, 48);
       fq_mul_wide_k(out, x, y);
+      break;
+    case 8:  // a - b + p without a conditional step (fqw.cuh), 12 limbs
+      std::memcpy(x.l, a, 48);
+      std::memcpy(y.l, b, 48);
+      x = fq_sub_plus_p(x, y);
+      std::memcpy(out, x.l, 48);
+      break;
+    case 9:  // a / 2 mod p (pairing.cuh), 12 limbs
+      std::memcpy(x.l, a, 48);
+      x = fq_half(x);
+      std::memcpy(out, x.l, 48);
       break;
   }
 }

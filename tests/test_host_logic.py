@@ -137,6 +137,15 @@ def test_limb_wide_products_and_lazy_fq2(hostemul):
         want = a - b if a >= b else a - b + P * R
         assert op(5, a, b, 24, 24, 24) == want
     assert op(5, 0, (P - 1) ** 2, 24, 24, 24) == P * R - (P - 1) ** 2
+    # the two conditional-free helpers: a - b + p for reduced a, b (never negative, below 2p) and the halving
+    # (a + (a odd ? p : 0)) >> 1, which is division by 2 in Montgomery form as well
+    half = pow(2, -1, P)
+    singles = [0, 1, 2, P - 1, P - 2, (P - 1) // 2, (P + 1) // 2] + [patterned(P) for _ in range(100)] + \
+              [rnd.randrange(P) for _ in range(200)]
+    for i, a in enumerate(singles):
+        b = singles[(7 * i + 3) % len(singles)]
+        assert op(8, a, b, 12, 12, 12) == a - b + P
+        assert op(9, a, 0, 12, 12, 12) == a * half % P
     # Fq2: values in Montgomery form, c0 | c1
     def f2(v):
         return v[0] | (v[1] << 384)
