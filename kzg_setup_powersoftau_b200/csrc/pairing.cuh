@@ -128,16 +128,16 @@ PTAU_HD void fq12_one(Fq12& r) {
 }
 // r = a * b (3 Fq6 multiplications); r may alias a or b
 PTAU_HD_NOINLINE void fq12_mul(Fq12& r, const Fq12& a, const Fq12& b) {
-  Fq6 v0, v1, s, t;
+  Fq6 s, v0, v1;  // three temporaries: the sum of b's halves lives in v0 until the cross product is formed
+  fq6_add(s, a.c0, a.c1);
+  fq6_add(v0, b.c0, b.c1);
+  fq6_mul(s, s, v0);
   fq6_mul(v0, a.c0, b.c0);
   fq6_mul(v1, a.c1, b.c1);
-  fq6_add(s, a.c0, a.c1);
-  fq6_add(t, b.c0, b.c1);
-  fq6_mul(s, s, t);
   fq6_sub(s, s, v0);
   fq6_sub(r.c1, s, v1);
-  fq6_mul_v(t, v1);
-  fq6_add(r.c0, v0, t);
+  fq6_mul_v(v1, v1);
+  fq6_add(r.c0, v0, v1);
 }
 // r = a^2 by the complex method (2 Fq6 multiplications instead of 3): with t = a0 a1,
 // c0 = (a0 + a1)(a0 + v a1) - t - v t, c1 = 2t; r may alias a
@@ -433,17 +433,20 @@ PTAU_HD void fq6_mul_by_1(Fq6& r, const Fq6& a, const Fq2& b1) {
   r.c2 = t2;
 }
 // f *= (c0 + c1 px v) + (c2 py v) w     (ark: mul_by_014; 13 Fq2 multiplications instead of 18)
+// One Fq6 temporary: aa and bb are formed in place in f.c0 and f.c1 (every Fq6 a thread keeps is 288 bytes of local
+// memory, and the working set of a full wave sits right at the size of L2).
 PTAU_HD_NOINLINE void ell(Fq12& f, const EllCoeff& co, const Fq& px, const Fq& py) {
-  const Fq2 c0 = co.c0, c1 = fq2_mul_fq(co.c1, px), c4 = fq2_mul_fq(co.c2, py);
-  Fq6 aa, bb, s;
-  fq6_mul_by_01(aa, f.c0, c0, c1);
-  fq6_mul_by_1(bb, f.c1, c4);
+  const Fq2 c1 = fq2_mul_fq(co.c1, px), c4 = fq2_mul_fq(co.c2, py);
+  Fq6 s;
   fq6_add(s, f.c1, f.c0);
-  fq6_mul_by_01(s, s, c0, fq2_add(c1, c4));
-  fq6_sub(s, s, aa);
-  fq6_sub(f.c1, s, bb);
-  fq6_mul_v(bb, bb);
-  fq6_add(f.c0, bb, aa);
+  fq6_mul_by_01(f.c0, f.c0, co.c0, c1);  // aa
+  fq6_mul_by_1(f.c1, f.c1, c4);          // bb
+  fq6_mul_by_01(s, s, co.c0, fq2_add(c1, c4));
+  fq6_sub(s, s, f.c0);
+  fq6_sub(s, s, f.c1);   // new c1 = (f0 + f1)(c0 + (c1 + c4) v) - aa - bb
+  fq6_mul_v(f.c1, f.c1);
+  fq6_add(f.c0, f.c1, f.c0);  // new c0 = v bb + aa
+  f.c1 = s;
 }
 
 // Miller value of up to two pairs (P_k affine in G1, Q_k affine on the twist); a pair with use[k] == false
