@@ -38,7 +38,23 @@ LOG2_POINTS = 21
 IMAD_PER_FQMUL = 588  # 12x32-bit CIOS, lo+hi counted separately
 # SURVEY.md 8d algorithmic Fq multiplications per point
 FQMUL = {"g1_unc": 1030, "g2_unc": 1180, "g1_comp": 1500, "g2_comp": 2120}
-HBM_PEAK_GBPS = 6552.0  # MEASURED_PEAKS.json (driver-written copy bandwidth of this pool's B200s)
+HBM_PEAK_FALLBACK_GBPS = 6552.0  # the value MEASURED_PEAKS.json held on this pool's B200s when this was written
+
+
+def hbm_peak():
+    """(GB/s, source): the driver-written copy bandwidth of MEASURED_PEAKS.json when the file travelled with the repo,
+    else the value it held on this pool (the profiling recipe's fallback), saying which."""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            v = float(json.load(f)["hbm_gbs"])
+        if v > 0:
+            return v, "MEASURED_PEAKS.json hbm_gbs"
+    except Exception:
+        pass
+    return HBM_PEAK_FALLBACK_GBPS, "fallback: MEASURED_PEAKS.json absent, its last known value on this pool"
+
+
+HBM_PEAK_GBPS, HBM_PEAK_SOURCE = hbm_peak()
 METRIC = "G1+G2 points/sec parse+decompress+subgroup-check+ark re-encode (2^21 compressed G1 + 2^21 compressed G2 per step)"
 TAU = 0x1234567890ABCDEF1234567890ABCDEF
 # the ncu capture the `traffic` / pipe-busy figures of the roofline object are read from (tools/ncu_summary.py output)
@@ -658,7 +674,7 @@ def main():
             hb = extra["g1_reencode_only(hbm)"]
             line["roofline_hbm"] = {"bound": "hbm", "kernel": "convert_kernel<1, 1, 3, 0> zcash->ark re-encode only (no checks)",
                                     "achieved": hb["GBps"], "peak": HBM_PEAK_GBPS, "unit": "GB/s",
-                                    "frac": hb["GBps"] / HBM_PEAK_GBPS, "traffic": None}
+                                    "frac": hb["GBps"] / HBM_PEAK_GBPS, "traffic": None, "peak_source": HBM_PEAK_SOURCE}
         line["extra"] = extra
         # ---- CPU baseline: the reference's algorithms on this box's host cores (rank 0, N=1 only) ----
         threads = os.cpu_count() or 1
