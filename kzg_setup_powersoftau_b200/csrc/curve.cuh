@@ -316,7 +316,115 @@ struct Park {
     store_fq(24, y.c0);
     store_fq(36, y.c1);
   }
+  // 24-limb (unreduced) values, words 48..95 of the file: only with PTAU_G2_DBL_LAZYC
+  PTAU_HD void store_wide(int at, const uint32_t* t) const {
+#pragma unroll
+    for (int j = 0; j < 24; j++) st(at + j, t[j]);
+  }
+  PTAU_HD void load_wide(int at, uint32_t* t) const {
+#pragma unroll
+    for (int j = 0; j < 24; j++) t[j] = ld(at + j);
+  }
 };
+// words per thread of the operand file
+#ifdef PTAU_G2_DBL_LAZYC
+#define PTAU_PARK_WORDS 96
+#else
+#define PTAU_PARK_WORDS 48
+#endif
+
+// The doubling of the G2 ladder with C = Y^4 never reduced (the Fq2 counterpart of the G1 doubling above), in
+// coordinates scaled by lambda = 1/2 -- (X3/4, Y3/8, Z3/2) is the same Jacobian point as dbl-2009-l's (X3, Y3, Z3):
+//     B = Y^2, C = B^2, A = X^2, D = (X+B)^2 - A - C = 2XB, M = 3A/2, S = D/2
+//     X3 = M^2 - D,  Y3 = M (S - X3) - C,  Z3 = Y Z
+// so C enters Y3 with coefficient 1 and every wide difference below needs at most one conditional + p 2^384.
+// An Fq2 square is taken as (a0+a1)(a0-a1+p) + (2 a0) a1 u with unreduced operands; the wide values of C are parked in
+// the operand file (words 48..95) and come back twice, inside the sums that are reduced instead of C:
+//     D.c1 = redc(2 t0 t1 - 2 x0 x1 - 2 b0 b1)                        = 2 (x0 b1 + x1 b0)            in [0, 4p^2)
+//     D.c0 = redc((t0+t1)(t0-t1+2p) - (x0+x1)(x0-x1+p) - (b0+b1)(b0-b1+p))
+//          = 2 x0 b0 - 2 x1 b1 + p (x0+x1+b0+b1)                                                     in [0, 6p^2)
+// with t = X + B the unreduced sum (t_i = x_i + b_i as integers, which makes both identities exact: no sign fix), and
+//     Y3.c1 = redc(m0 u1 + m1 u0 - C.c1)   in (-2p^2, 2p^2) + fix;   Y3.c0 = redc(m0 u0 - (m1 u1 + C.c0))  in (-5p^2, p^2) + fix
+// 16 wide products + 12 reductions = 4176 MADs instead of 16 + 14 = 4488, and 4 halvings + 9 field additions
+// instead of 26 field additions.  All bounds are < p 2^384 = 9.84 p^2 (fq_redc) and every operand is < 2^384.
+template <int STRIDE>
+PTAU_HD void jac_dbl_lazyc(Jac<Fq2>& p, const Park<STRIDE>& pk) {
+#if defined(__CUDA_ARCH__) && defined(PTAU_G2_LAZYC_CALLS)  // A/B: the three plain Fq2 products as calls (smaller loop body)
+#define PTAU_LZ_SQR(a) fq2_sqr(a)
+#define PTAU_LZ_MUL(a, b) fq2_mul(a, b)
+#else
+#define PTAU_LZ_SQR(a) fq2_sqr_inl(a)
+#define PTAU_LZ_MUL(a, b) fq2_mul_inl(a, b)
+#endif
+  Fq2 B = PTAU_LZ_SQR(p.Y);
+  p.Z = PTAU_LZ_MUL(p.Z, p.Y);
+  uint32_t w0[24], w1[24];
+  // C (never reduced)
+#ifdef PTAU_G2_LAZYC_REGS  // A/B: the wide C stays in registers instead of the operand file
+  uint32_t wc0[24], wc1[24];
+  fq_mul_wide(wc0, fq_add_nored(B.c0, B.c1), fq_sub_plus_p(B.c0, B.c1));
+  fq_mul_wide(wc1, fq_add_nored(B.c0, B.c0), B.c1);
+#define PTAU_LOAD_C0(dst) do { for (int j_ = 0; j_ < 24; j_++) (dst)[j_] = wc0[j_]; } while (0)
+#define PTAU_LOAD_C1(dst) do { for (int j_ = 0; j_ < 24; j_++) (dst)[j_] = wc1[j_]; } while (0)
+#else
+  fq_mul_wide(w0, fq_add_nored(B.c0, B.c1), fq_sub_plus_p(B.c0, B.c1));
+  pk.store_wide(48, w0);
+  fq_mul_wide(w0, fq_add_nored(B.c0, B.c0), B.c1);
+  pk.store_wide(72, w0);
+#define PTAU_LOAD_C0(dst) pk.load_wide(48, dst)
+#define PTAU_LOAD_C1(dst) pk.load_wide(72, dst)
+#endif
+  Fq2 t;
+  t.c0 = fq_add_nored(p.X.c0, B.c0);
+  t.c1 = fq_add_nored(p.X.c1, B.c1);
+  Fq2 A, D;
+  // imaginary parts: A.c1 = 2 x0 x1, D.c1
+  fq_mul_wide(w0, fq_add_nored(p.X.c0, p.X.c0), p.X.c1);
+  fq_mul_wide(w1, fq_add_nored(t.c0, t.c0), t.c1);
+  fqw_sub(w1, w0);
+  A.c1 = fq_redc(w0);
+  PTAU_LOAD_C1(w0);
+  fqw_sub(w1, w0);
+  D.c1 = fq_redc(w1);
+  // real parts
+  fq_mul_wide(w0, fq_add_nored(p.X.c0, p.X.c1), fq_sub_plus_p(p.X.c0, p.X.c1));
+  fq_mul_wide(w1, fq_add_nored(t.c0, t.c1), fq_sub_plus_2p(t.c0, t.c1));
+  fqw_sub(w1, w0);
+  A.c0 = fq_redc(w0);
+  PTAU_LOAD_C0(w0);
+  fqw_sub(w1, w0);
+  D.c0 = fq_redc(w1);
+  // M = 3A/2 = A + A/2
+  Fq2 M;
+  M.c0 = fq_add(A.c0, fq_half(A.c0));
+  M.c1 = fq_add(A.c1, fq_half(A.c1));
+  Fq2 Fv = PTAU_LZ_SQR(M);
+  p.X = fq2_sub(Fv, D);
+  Fq2 U;
+  U.c0 = fq_sub(fq_half(D.c0), p.X.c0);
+  U.c1 = fq_sub(fq_half(D.c1), p.X.c1);
+  // Y3 = M U - C: the Karatsuba rows of fq2_mul_inl with C subtracted before the two reductions
+  uint32_t w2[24];
+  fq_mul_wide(w2, fq_add_nored(M.c0, M.c1), fq_add_nored(U.c0, U.c1));
+  fq_mul_wide(w0, M.c0, U.c0);
+  fq_mul_wide(w1, M.c1, U.c1);
+  fqw_sub(w2, w0);
+  fqw_sub(w2, w1);
+  {
+    uint32_t c[24];
+    PTAU_LOAD_C1(c);
+    fqw_sub_fix(w2, c);
+    p.Y.c1 = fq_redc(w2);
+    PTAU_LOAD_C0(c);
+    fqw_add(w1, c);
+  }
+  fqw_sub_fix(w0, w1);
+  p.Y.c0 = fq_redc(w0);
+#undef PTAU_LZ_SQR
+#undef PTAU_LZ_MUL
+#undef PTAU_LOAD_C0
+#undef PTAU_LOAD_C1
+}
 
 // psi(P) == [z]P   <=>   [|z|]P == -psi(P) = (psi_x, -psi_y); P = (x, y) parked in `pk`
 template <int STRIDE>
@@ -327,7 +435,11 @@ PTAU_HD_NOINLINE bool g2_in_subgroup(Park<STRIDE> pk) {
   q.Z = fq2_one();
 #pragma unroll 1
   for (int i = 62; i >= 0; --i) {
+#ifdef PTAU_G2_DBL_LAZYC
+    jac_dbl_lazyc(q, pk);
+#else
     jac_dbl_ladder(q);
+#endif
     if ((PTAU_Z_ABS >> i) & 1ull) jac_madd(q, pk.load_fq2(0), pk.load_fq2(24));
   }
   // psi_x = conj(x) * (0, cx1) = (x1*cx1, x0*cx1)

@@ -52,6 +52,45 @@ PTAU_HD Fq fq_sub_plus_p(const Fq& a, const Fq& b) {
   return r;
 }
 
+// a / 2: (a + (a odd ? p : 0)) >> 1, the same in Montgomery form
+PTAU_HD Fq fq_half(const Fq& a) {
+  const uint32_t pl[12] = PTAU_P_LIMBS;
+  const uint32_t mask = 0u - (a.l[0] & 1u);
+  uint32_t t[13];
+  uint64_t c = 0;
+#pragma unroll
+  for (int i = 0; i < 12; i++) {
+    c += (uint64_t)a.l[i] + (pl[i] & mask);
+    t[i] = (uint32_t)c;
+    c >>= 32;
+  }
+  t[12] = (uint32_t)c;
+  Fq r;
+#pragma unroll
+  for (int i = 0; i < 12; i++) r.l[i] = (t[i] >> 1) | (t[i + 1] << 31);
+  return r;
+}
+
+// 2p, little-endian limbs
+#define PTAU_2P_LIMBS                                                                      \
+  {0xffff5556u, 0x73fdffffu, 0x62a7ffffu, 0x3d57fffdu, 0xed61ec48u, 0xce61a541u,           \
+   0xe70a257eu, 0xc8ee9709u, 0x869759aeu, 0x96374f6cu, 0x72ffcd34u, 0x340223d4u}
+// a - b + 2p for unreduced sums a, b < 2p: in (0, 4p), still below 2^384
+PTAU_HD Fq fq_sub_plus_2p(const Fq& a, const Fq& b) {
+  const uint32_t pl[12] = PTAU_2P_LIMBS;
+  Fq t, r;
+  PX_DECL;
+  PX_ADD_CC(t.l[0], a.l[0], pl[0]);
+#pragma unroll
+  for (int i = 1; i < 11; i++) PX_ADDC_CC(t.l[i], a.l[i], pl[i]);
+  PX_ADDC(t.l[11], a.l[11], pl[11]);
+  PX_SUB_CC(r.l[0], t.l[0], b.l[0]);
+#pragma unroll
+  for (int i = 1; i < 11; i++) PX_SUBC_CC(r.l[i], t.l[i], b.l[i]);
+  PX_SUBC(r.l[11], t.l[11], b.l[11]);
+  return r;
+}
+
 // t[0..23] = a * b.  Same rows as fq_mul_inl without the reduction rows: after row i the lowest limb of the
 // even-aligned accumulator is limb i of the product.
 PTAU_HD void fq_mul_wide_plain(uint32_t* t, const Fq& a, const Fq& b) {

@@ -102,13 +102,13 @@ __device__ __forceinline__ void stage_out_flat(uint32_t* __restrict__ g, const u
 }
 
 // shared memory of one block: the record staging buffer (BLK x max(stride_in, stride_out)) and, for the G2 kernels
-// with curve checks, the operand file of the subgroup ladder (48 words per thread, transposed: conflict-free)
+// with curve checks, the operand file of the subgroup ladder (PTAU_PARK_WORDS per thread, transposed: conflict-free)
 template <int G, int INFMT, int OUTFMT, bool HEAVY>
 constexpr int convert_smem_words() {
   constexpr int BLK = G == PTAU_G1 ? PTAU_BLOCK_G1 : PTAU_BLOCK_G2;
   constexpr int SIN = smem_stride(record_bytes(G, INFMT) / 4);
   constexpr int SOUT = smem_stride(record_bytes(G, OUTFMT) / 4);
-  return BLK * (SIN > SOUT ? SIN : SOUT) + ((G == PTAU_G2 && HEAVY) ? BLK * 48 : 0);
+  return BLK * (SIN > SOUT ? SIN : SOUT) + ((G == PTAU_G2 && HEAVY) ? BLK * PTAU_PARK_WORDS : 0);
 }
 
 // blocks per SM of the kernels without curve checks (memory-bound; A/B on B200: 2, 6 and 8 give the same 5.76-5.78 TB/s)

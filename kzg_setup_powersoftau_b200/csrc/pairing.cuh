@@ -308,24 +308,7 @@ struct EllCoeff {
   Fq2 c0, c1, c2;
 };
 
-// a / 2: (a + (a odd ? p : 0)) >> 1, the same in Montgomery form
-PTAU_HD Fq fq_half(const Fq& a) {
-  const uint32_t pl[12] = PTAU_P_LIMBS;
-  const uint32_t mask = 0u - (a.l[0] & 1u);
-  uint32_t t[13];
-  uint64_t c = 0;
-#pragma unroll
-  for (int i = 0; i < 12; i++) {
-    c += (uint64_t)a.l[i] + (pl[i] & mask);
-    t[i] = (uint32_t)c;
-    c >>= 32;
-  }
-  t[12] = (uint32_t)c;
-  Fq r;
-#pragma unroll
-  for (int i = 0; i < 12; i++) r.l[i] = (t[i] >> 1) | (t[i + 1] << 31);
-  return r;
-}
+// fq_half: fqw.cuh
 PTAU_HD Fq2 fq2_half(const Fq2& a) {
   Fq2 r;
   r.c0 = fq_half(a.c0);

@@ -77,8 +77,13 @@ PTAU_HD_NOINLINE Fq fq_pow_p34(const Fq& a) {
   for (int s = 1; s < PTAU_P34_STEPS; s++) {
     int c = chain[s];
     int n = c >> 4;
+#if defined(__CUDA_ARCH__) && defined(PTAU_POW_INLINE)  // A/B: the runs of squarings without a call per squaring
+#pragma unroll 1
+    for (int k = 0; k < n; k++) acc = fq_sqr_inl(acc);
+#else
 #pragma unroll 1
     for (int k = 0; k < n; k++) acc = fq_sqr(acc);
+#endif
     if (c & 15) acc = fq_mul(acc, tbl[(c & 15) >> 1]);
   }
   return acc;
@@ -428,7 +433,7 @@ PTAU_HD uint32_t g2_process(const uint32_t* in, int out_fmt, uint32_t* out, uint
 // host build (tests/host_emul): the operand file is a local array
 template <int INFMT, bool HEAVY = true>
 inline uint32_t g2_process(const uint32_t* in, int out_fmt, uint32_t* out, uint32_t checks) {
-  uint32_t file[48];
+  uint32_t file[PTAU_PARK_WORDS];
   Park<1> pk;
   pk.p = file;
   return g2_process<INFMT, HEAVY, 1>(in, out_fmt, out, checks, pk);

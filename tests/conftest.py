@@ -36,6 +36,8 @@ def hostemul():
     """Host build of the product's per-point limb code (tests/host_emul)."""
     import ctypes
 
+    if os.environ.get("PTAU_HOSTEMUL_SO"):  # a host build with other feature macros (A/B of a kernel variant)
+        return ctypes.CDLL(os.environ["PTAU_HOSTEMUL_SO"])
     d = os.path.join(ROOT, "tests", "host_emul")
     so = os.path.join(d, "libptau_hostemul.so")
     csrc = os.path.join(ROOT, "kzg_setup_powersoftau_b200", "csrc")

@@ -130,6 +130,30 @@ extern "C" void hostemul_fqw_op(int op, const uint32_t* a, const uint32_t* b, ui
   }
 }
 
+// one Jacobian doubling in G2 (csrc/curve.cuh): variant 0 = dbl-2009-l as the other code uses it, 1 = the ladder's
+// doubling with C never reduced (jac_dbl_lazyc; coordinates scaled by 1/2).  in / out: X | Y | Z, 72 Montgomery limbs.
+extern "C" void hostemul_g2_dbl(int variant, const uint32_t* in, uint32_t* out) {
+  Jac<Fq2> q;
+  std::memcpy(&q, in, 288);
+  if (variant == 0) {
+    jac_dbl(q);
+  } else {
+    uint32_t file[96];
+    Park<1> pk;
+    pk.p = file;
+    jac_dbl_lazyc(q, pk);
+  }
+  std::memcpy(out, &q, 288);
+}
+// a - b + 2p (fqw.cuh), 12 limbs
+extern "C" void hostemul_fq_sub_plus_2p(const uint32_t* a, const uint32_t* b, uint32_t* out) {
+  Fq x, y;
+  std::memcpy(x.l, a, 48);
+  std::memcpy(y.l, b, 48);
+  x = fq_sub_plus_2p(x, y);
+  std::memcpy(out, x.l, 48);
+}
+
 // the product's pairing code (csrc/pairing.cuh) on the host: same limb arithmetic, same formulas
 extern "C" void hostemul_pairing_product2(const uint8_t* g1, const uint8_t* g2, size_t n, uint8_t* gt_out, uint8_t* is_one) {
   for (size_t i = 0; i < n; i++) {

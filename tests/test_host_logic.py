@@ -164,6 +164,53 @@ def test_limb_wide_products_and_lazy_fq2(hostemul):
         assert got == ((a[0] * a[0] - a[1] * a[1]) * rinv % P, 2 * a[0] * a[1] * rinv % P)
 
 
+def test_limb_g2_ladder_doubling_with_unreduced_c(hostemul):
+    """csrc/curve.cuh jac_dbl_lazyc (the doubling of the G2 subgroup ladder: C = Y^4 kept as two unreduced 768-bit
+    products, coordinates scaled by 1/2) against dbl-2009-l as the rest of the code runs it: for ANY field values
+    X, Y, Z (not only curve points) the outputs must satisfy X' = X3/4, Y' = Y3/8, Z' = Z3/2 exactly and be reduced.
+    Also the helper a - b + 2p on unreduced sums (operands below 2p)."""
+    P = o.P
+    R = 1 << 384
+    rinv = pow(R, -1, P)
+
+    def limbs(vals):
+        w = []
+        for v in vals:
+            w += [(v >> (32 * i)) & 0xFFFFFFFF for i in range(12)]
+        return (ctypes.c_uint32 * len(w))(*w)
+
+    def dbl(variant, vals):
+        out = (ctypes.c_uint32 * 72)()
+        hostemul.hostemul_g2_dbl(variant, limbs(vals), out)
+        v = [sum(int(out[12 * k + i]) << (32 * i) for i in range(12)) for k in range(6)]
+        assert all(x < P for x in v), "unreduced coordinate"
+        return [x * rinv % P for x in v]
+
+    rnd = random.Random(5)
+    edge = [0, 1, 2, P - 1, P - 2, (P - 1) // 2, (P + 1) // 2, R % P, 1 << 380]
+    pats = [0, 1, 0x7FFFFFFF, 0x80000000, 0xFFFFFFFE, 0xFFFFFFFF]
+
+    def patterned():
+        v = 0
+        for i in range(12):
+            v |= rnd.choice(pats) << (32 * i)
+        return v % P
+
+    cases = [[rnd.choice(edge) for _ in range(6)] for _ in range(250)]
+    cases += [[patterned() for _ in range(6)] for _ in range(250)]
+    cases += [[rnd.randrange(P) for _ in range(6)] for _ in range(700)]
+    for vals in cases:
+        a, b = dbl(0, vals), dbl(1, vals)
+        for k, scale in ((0, 4), (1, 4), (2, 8), (3, 8), (4, 2), (5, 2)):
+            assert b[k] * scale % P == a[k], (k, vals)
+    sums = [0, 1, P - 1, P, P + 1, 2 * P - 2, 2 * P - 1] + [rnd.randrange(2 * P) for _ in range(300)]
+    for i, a in enumerate(sums):
+        b = sums[(5 * i + 2) % len(sums)]
+        out = (ctypes.c_uint32 * 12)()
+        hostemul.hostemul_fq_sub_plus_2p(limbs([a]), limbs([b]), out)
+        assert sum(int(out[j]) << (32 * j) for j in range(12)) == a - b + 2 * P
+
+
 def test_limb_code_on_golden_files(hostemul):
     n = 8
     body = golden("n8_powersoftau.bin")[64:]
