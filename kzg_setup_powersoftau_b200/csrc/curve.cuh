@@ -316,7 +316,7 @@ struct Park {
     store_fq(24, y.c0);
     store_fq(36, y.c1);
   }
-  // 24-limb (unreduced) values, words 48..95 of the file: only with PTAU_G2_DBL_LAZYC
+  // 24-limb (unreduced) values, words 48..95 of the file: only with PTAU_G2_LAZYC_PARK
   PTAU_HD void store_wide(int at, const uint32_t* t) const {
 #pragma unroll
     for (int j = 0; j < 24; j++) st(at + j, t[j]);
@@ -327,7 +327,7 @@ struct Park {
   }
 };
 // words per thread of the operand file
-#ifdef PTAU_G2_DBL_LAZYC
+#ifdef PTAU_G2_LAZYC_PARK
 #define PTAU_PARK_WORDS 96
 #else
 #define PTAU_PARK_WORDS 48
@@ -360,13 +360,13 @@ PTAU_HD void jac_dbl_lazyc(Jac<Fq2>& p, const Park<STRIDE>& pk) {
   p.Z = PTAU_LZ_MUL(p.Z, p.Y);
   uint32_t w0[24], w1[24];
   // C (never reduced)
-#ifdef PTAU_G2_LAZYC_REGS  // A/B: the wide C stays in registers instead of the operand file
+#ifndef PTAU_G2_LAZYC_PARK  // the wide C stays in registers (no spills at 255 registers: -Xptxas -v)
   uint32_t wc0[24], wc1[24];
   fq_mul_wide(wc0, fq_add_nored(B.c0, B.c1), fq_sub_plus_p(B.c0, B.c1));
   fq_mul_wide(wc1, fq_add_nored(B.c0, B.c0), B.c1);
 #define PTAU_LOAD_C0(dst) do { for (int j_ = 0; j_ < 24; j_++) (dst)[j_] = wc0[j_]; } while (0)
 #define PTAU_LOAD_C1(dst) do { for (int j_ = 0; j_ < 24; j_++) (dst)[j_] = wc1[j_]; } while (0)
-#else
+#else  // A/B: C parked in the operand file (words 48..95) -- measured slower, profiles/r02c_ab_*.log
   fq_mul_wide(w0, fq_add_nored(B.c0, B.c1), fq_sub_plus_p(B.c0, B.c1));
   pk.store_wide(48, w0);
   fq_mul_wide(w0, fq_add_nored(B.c0, B.c0), B.c1);
@@ -435,9 +435,9 @@ PTAU_HD_NOINLINE bool g2_in_subgroup(Park<STRIDE> pk) {
   q.Z = fq2_one();
 #pragma unroll 1
   for (int i = 62; i >= 0; --i) {
-#ifdef PTAU_G2_DBL_LAZYC
+#ifndef PTAU_G2_DBL_EAGERC
     jac_dbl_lazyc(q, pk);
-#else
+#else  // A/B: dbl-2009-l with every product reduced (the doubling of rounds 1-2)
     jac_dbl_ladder(q);
 #endif
     if ((PTAU_Z_ABS >> i) & 1ull) jac_madd(q, pk.load_fq2(0), pk.load_fq2(24));

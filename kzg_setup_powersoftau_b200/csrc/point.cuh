@@ -77,7 +77,9 @@ PTAU_HD_NOINLINE Fq fq_pow_p34(const Fq& a) {
   for (int s = 1; s < PTAU_P34_STEPS; s++) {
     int c = chain[s];
     int n = c >> 4;
-#if defined(__CUDA_ARCH__) && defined(PTAU_POW_INLINE)  // A/B: the runs of squarings without a call per squaring
+#if defined(__CUDA_ARCH__) && !defined(PTAU_POW_CALLS)
+    // the runs of squarings expanded in place: no call per squaring (G1 compressed 47.1 -> 45.9 ms, G2 compressed
+    // 73.6 -> 72.3 ms per 2^20 points, profiles/r02c_ab_*.log)
 #pragma unroll 1
     for (int k = 0; k < n; k++) acc = fq_sqr_inl(acc);
 #else

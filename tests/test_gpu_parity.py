@@ -27,7 +27,7 @@ def test_native_library_is_the_path():
     assert os.path.exists(_ffi.LIB_PATH)
     assert _ffi.lib().ptau_device_count() >= 1
     maps = open("/proc/self/maps").read()
-    assert "libptau_b200.so" in maps
+    assert os.path.basename(_ffi.LIB_PATH) in maps  # libptau_b200.so, or the A/B build PTAU_LIB names
 
 
 def test_field_ops_on_gpu_carry_stress(ctx):
