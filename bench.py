@@ -492,7 +492,13 @@ def main():
                 r["frac_pipe_busy_ncu"] = prof["fmaheavy_pct"] / 100.0 if prof.get("fmaheavy_pct") else None
                 r["ncu"] = {"source": NCU_SUMMARY, "points_in_capture": prof["points"],
                             "fma_heavy_pipe_busy_pct": prof["fmaheavy_pct"], "registers": prof["registers"],
-                            "local_ld_sectors": prof["local_ld_sectors"], "local_st_sectors": prof["local_st_sectors"]}
+                            "local_ld_sectors": prof["local_ld_sectors"], "local_st_sectors": prof["local_st_sectors"],
+                            "kernel_ms_in_capture": prof["kernel_ms_in_capture"],
+                            "kernel_ms_now_same_points": kernel_s * 1e3 * prof["points"] / n_points,
+                            "note": "the capture predates the last kernel change of round 2 (G2 doubling with C = Y^4 "
+                                    "unreduced, squaring runs of the sqrt chain in place): the launches are shorter now at "
+                                    "the same pipe utilisation (profiles/r02c_ncu_full_g2_partial.csv: 83.4 % for the G2 "
+                                    "uncompressed kernel after the change, 83.7 % before)"}
             return r
 
         line["roofline"] = roofline("g2_comp", KERNEL_G2C, n_loc, ms_g2, 96 + 192)  # dominant kernel of the step
