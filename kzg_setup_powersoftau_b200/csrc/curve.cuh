@@ -338,8 +338,8 @@ struct Park {
 //     B = Y^2, C = B^2, A = X^2, D = (X+B)^2 - A - C = 2XB, M = 3A/2, S = D/2
 //     X3 = M^2 - D,  Y3 = M (S - X3) - C,  Z3 = Y Z
 // so C enters Y3 with coefficient 1 and every wide difference below needs at most one conditional + p 2^384.
-// An Fq2 square is taken as (a0+a1)(a0-a1+p) + (2 a0) a1 u with unreduced operands; the wide values of C are parked in
-// the operand file (words 48..95) and come back twice, inside the sums that are reduced instead of C:
+// An Fq2 square is taken as (a0+a1)(a0-a1+p) + (2 a0) a1 u with unreduced operands; the two wide values of C stay in
+// registers (48 limbs; A/B: parked in the operand file) and are used twice, inside the sums that are reduced instead of C:
 //     D.c1 = redc(2 t0 t1 - 2 x0 x1 - 2 b0 b1)                        = 2 (x0 b1 + x1 b0)            in [0, 4p^2)
 //     D.c0 = redc((t0+t1)(t0-t1+2p) - (x0+x1)(x0-x1+p) - (b0+b1)(b0-b1+p))
 //          = 2 x0 b0 - 2 x1 b1 + p (x0+x1+b0+b1)                                                     in [0, 6p^2)
