@@ -335,6 +335,34 @@ def test_differential_fuzz_c_oracle_vs_limb_code(hostemul, cref):
     assert n_bad > 200  # the mutations really produce rejected records
 
 
+def test_limb_ladders_reject_random_curve_points(hostemul, cref):
+    """Random x coordinates with valid compressed flags: about half decompress to a point of the curve (twist), and such
+    a point is outside the prime-order subgroup with overwhelming probability.  The product's ladders (GLV test in G1,
+    psi test with the unreduced-C doubling in G2) must give the verdict of the reference's multiplication by r
+    (oracle/cpu_ref.c) on every one of them, and the same bytes when the checks are off."""
+    rnd = random.Random(977)
+    for g, size, n in ((1, 48, 60), (2, 96, 40)):
+        recs = []
+        for _ in range(n):
+            b = bytearray(rnd.randrange(o.P).to_bytes(48, "big") if g == 1 else
+                          rnd.randrange(o.P).to_bytes(48, "big") + rnd.randrange(o.P).to_bytes(48, "big"))
+            b[0] = (b[0] & 0x1F) | 0x80 | rnd.choice([0, 0x20])
+            recs.append(bytes(b))
+        data = b"".join(recs)
+        a, sa = _conv(hostemul, g, 2, data, 3, 14)
+        b_, sb = cref.convert(g, 2, data, 3, 14)
+        assert sa == sb
+        assert sum(1 for x in sa if x == 5) >= n // 4   # PTAU_BAD_NOT_IN_SUBGROUP: the ladders really ran and said no
+        assert sum(1 for x in sa if x == 4) >= n // 4     # PTAU_BAD_NOT_ON_CURVE: the others have no square root
+        a, sa = _conv(hostemul, g, 2, data, 3, 0)
+        b_, sb = cref.convert(g, 2, data, 3, 0)
+        assert sa == sb
+        rs = len(a) // n
+        for i in range(n):
+            if sa[i] == 0:
+                assert a[i * rs:(i + 1) * rs] == b_[i * rs:(i + 1) * rs]
+
+
 # ---- C ABI surface ---------------------------------------------------------------
 def _header_symbols():
     text = open(os.path.join(ROOT, "include", "ptau_b200.h")).read()
